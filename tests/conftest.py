@@ -1,0 +1,13 @@
+"""pytest configuration: registers the `gpu` marker and puts the product package
+(`local-hyperdb_b200/hyperdb_b200`) and the test-only `oracle/` on sys.path."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "local-hyperdb_b200"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

@@ -1,0 +1,65 @@
+"""The explicit-arithmetic spec (oracle/canonical.py) against the REAL reference's outputs.
+
+Bit-exact wherever NumPy's arithmetic is deterministic: every float16 metric, and euclidean /
+manhattan / hamming in every dtype.  float32/float64 dot and cosine go through OpenBLAS in the
+reference (unknowable summation order): scores within north_star's tolerances (rel 1e-5 / 1e-12)
+and index lists identical unless the two rows involved are within that tolerance of each other."""
+import numpy as np
+import pytest
+
+import golden_io as G
+from oracle import canonical as K
+
+GOLDEN = G.load_sort_golden()
+TOL = {"float16": 1e-3, "float32": 1e-5, "float64": 1e-12, "uint64": 0, "int64": 0}
+
+
+def exact_expected(case, dtype):
+    return dtype == "float16" or case["metric"] in ("euclidean_metric", "manhattan_distance", "hamming_distance")
+
+
+@pytest.mark.parametrize("entry", GOLDEN, ids=[G.case_id(e[0]) for e in GOLDEN])
+def test_canonical_matches_reference(entry):
+    case, ref_sims, ref_idx, ref_sc = entry
+    V, q, ts = G.inputs(case)
+    sims = K.scores(V, q, case["metric"])
+    dt = str(ref_sims.dtype)
+    assert str(sims.dtype) == dt
+    if exact_expected(case, dt):
+        assert sims.tobytes() == ref_sims.reshape(-1).tobytes()
+    else:
+        a, b = sims.astype(np.float64), ref_sims.reshape(-1).astype(np.float64)
+        # a dot product's rounding error scales with |v||q| (cancellation), not with the result
+        cond = np.ones(len(b)) if case["metric"] == "cosine_similarity" else \
+            np.linalg.norm(V.astype(np.float64), axis=1) * np.linalg.norm(q.astype(np.float64))
+        assert np.all(np.abs(a - b) <= TOL[dt] * np.maximum(np.abs(b), cond))
+    bias = case["bias"] if ts is not None else 0
+    idx, sc = K.rank(V, q, case["k"], case["metric"], ts, bias)
+    if case["n"] == 1 or len(ref_idx) == 0:
+        assert len(idx) == len(ref_idx)
+        return
+    assert len(idx) == len(ref_idx)
+    if exact_expected(case, dt):
+        # same score multiset; canonical order == reference scores canonicalised
+        full = K.total_scores(V, q, case["metric"], ts, bias)
+        assert np.array_equal(sc, ref_sc)
+        assert list(idx) == list(G.canon_order(full, case["k"]))
+    else:
+        np.testing.assert_allclose(sc, ref_sc, rtol=TOL[dt] * 10, atol=TOL[dt] * 1e-2)
+        # identical index lists, except swaps certified as tolerance-ties
+        ref_full = ref_sims.reshape(-1).astype(np.float64)
+        if ts is not None:
+            ref_full = ref_full + bias * np.exp(-np.max(ts) + ts)
+        ref_canon = G.canon_order(ref_full, case["k"])
+        for mine, theirs in zip(idx, ref_canon):
+            if mine != theirs:
+                assert abs(ref_full[mine] - ref_full[theirs]) <= TOL[dt] * max(1.0, abs(ref_full[theirs]))
+
+
+def test_pairwise_sum_matches_numpy_reduce():
+    rng = np.random.default_rng(0)
+    for d in (1, 7, 8, 9, 127, 128, 129, 255, 256, 257, 1000, 4097):
+        for dt in (np.float16, np.float32, np.float64):
+            x = (rng.standard_normal((50, d)) * 3).astype(dt)
+            assert K.row_sum(x).tobytes() == np.add.reduce(x, axis=1).tobytes()
+            assert K.row_norm(x).tobytes() == np.linalg.norm(x, axis=1).tobytes()
