@@ -192,7 +192,13 @@ def hyperdb_bruteforce_tail(vectors, query, top_k, metric, timestamps=None, rece
     keep: optional bool[N] (filters).  Returns (global row ids, float64 scores).  top_k is clamped
     to the number of kept rows (`:1541-1543`); recency is the two-stage composition (quirk 1) and is
     only active when recency_bias != 0 and timestamps are given (`:1312-1313`).
+
+    The query reaches _execute_query through the LRU key, where an ndarray was turned into
+    `tuple(query.tolist())` (`hyperdb/hyperdb.py:1369-1370`) and is rebuilt by np.array (`:1201`):
+    on this path the query is ALWAYS float64, whatever dtype the caller passed, so NumPy promotes the
+    stored matrix to float64 for every query (probed against the real class: tests/golden/hyperdb_tail.npz).
     """
+    query = np.array(tuple(np.asarray(query).tolist()))
     vectors = np.asarray(vectors)
     ids = np.arange(len(vectors)) if keep is None else np.flatnonzero(np.asarray(keep, bool))
     if len(ids) == 0:
