@@ -1,0 +1,132 @@
+/*
+ * hyperdb_b200.h -- C ABI of the B200-native brute-force ranking engine for local-hyperDB.
+ *
+ * The reference has no FFI: its boundary for this path is the Python module
+ * hyperdb/ranking_algorithm.py (imported at hyperdb/hyperdb.py:13) and its single call site
+ * hyperdb/hyperdb.py:1556-1558.  Each entry point below names the reference lines it replaces.
+ * The Python host (local-hyperdb_b200/hyperdb_b200/) binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; hdb_last_error() returns a
+ *     thread-local message (mapped to ValueError / RuntimeError by the host).
+ *   - pointers are plain host or device addresses; `*_space` says which (HDB_HOST / HDB_DEVICE).
+ *   - all work is enqueued on the handle's stream (default: the legacy default stream, which is
+ *     also PyTorch's default current stream).  Calls with host outputs synchronise that stream
+ *     before returning; calls with device outputs do not synchronise.
+ *   - one caller thread per handle.  There is no CPU fallback: without a CUDA device every
+ *     compute entry point fails.
+ */
+#ifndef HYPERDB_B200_H
+#define HYPERDB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hdb_matrix hdb_matrix; /* opaque: one row shard of the stored matrix on one GPU */
+
+enum { HDB_F16 = 0, HDB_F32 = 1, HDB_F64 = 2 };   /* HyperDB fp_precision, hyperdb/hyperdb.py:65-66,80 */
+enum { HDB_HOST = 0, HDB_DEVICE = 1 };
+enum {                                              /* metric dispatch, hyperdb/ranking_algorithm.py:155-163 */
+  HDB_DOT = 0,        /* dot_product        :24-30  */
+  HDB_COSINE = 1,     /* cosine_similarity  :32-42  */
+  HDB_EUCLIDEAN = 2,  /* euclidean_metric   :44-52  */
+  HDB_MANHATTAN = 3,  /* manhattan_distance :54-61  */
+  HDB_HAMMING = 4     /* hamming_distance   :128-147 */
+};
+/* bits of the per-query flags word written by hdb_query */
+enum {
+  HDB_FLAG_FALLBACK = 1,   /* the fused select did not certify; the exact full-vector path produced the result */
+  HDB_FLAG_QUERY_NAN = 2,  /* the query holds a NaN (reference raises ValueError, ranking_algorithm.py:150-151) */
+  HDB_FLAG_TENSOR = 4,     /* candidates came from the tcgen05 batched contraction */
+  HDB_FLAG_UNCERTIFIED = 8 /* device-output mode only: the certificate failed and nothing was recomputed;
+                              the caller must repeat the query with host outputs or path mode 1 */
+};
+
+const char* hdb_last_error(void);
+int hdb_version(void);
+int hdb_device_count(int* count);
+
+/* ---- storage: replaces `self.vectors` (hyperdb/hyperdb.py:127-135, :911) ------------------ */
+/* A shard of n_rows x dim elements of `dtype`, row-major, on CUDA device `device`.
+ * row_offset = global row id of the shard's first row (0 on a single GPU). */
+int hdb_matrix_create(int device, int dtype, int64_t n_rows, int64_t dim, int64_t row_offset,
+                      hdb_matrix** out);
+int hdb_matrix_destroy(hdb_matrix* m);
+/* Copy rows [row_start, row_start+n_rows) from host or device memory (same dtype, row-major). */
+int hdb_matrix_upload(hdb_matrix* m, int64_t row_start, int64_t n_rows, const void* src, int src_space);
+/* Use caller-owned device memory (n_rows x dim, row-major, 16-byte aligned) without copying. */
+int hdb_matrix_adopt(hdb_matrix* m, void* device_rows);
+/* Ingest pass: per-row norms exactly as get_norm_vector computes them (ranking_algorithm.py:8-21),
+ * NaN scan (replaces the per-query scan of :150), error-bound statistics.  Must be called after the
+ * last upload and before the first query.  Fails if the matrix holds a NaN. */
+int hdb_matrix_finalize(hdb_matrix* m);
+/* Run the handle's work on this cudaStream_t (NULL = legacy default stream). */
+int hdb_matrix_set_stream(hdb_matrix* m, void* cuda_stream);
+int hdb_matrix_info(const hdb_matrix* m, int* dtype, int64_t* n_rows, int64_t* dim, int64_t* row_offset,
+                    int64_t* n_kept);
+
+/* ---- row subset: replaces the filters' output (hyperdb/hyperdb.py:1119-1134, :1218-1308) ---- */
+/* Keep only rows whose bit is set (bit i of word i/32, LSB first, local row ids); NULL keeps all. */
+int hdb_matrix_set_mask(hdb_matrix* m, const uint32_t* bits, int src_space);
+/* Keep only local rows in [lo, hi) (apply_skip_doc keeps one contiguous range); (0, n_rows) keeps all. */
+int hdb_matrix_set_range(hdb_matrix* m, int64_t lo, int64_t hi);
+
+/* ---- time decay: recency_bias * exp(ts - max ts), ranking_algorithm.py:179-183 --------------- */
+/* Per-row timestamps (float64, local rows); NULL removes them. */
+int hdb_matrix_set_timestamps(hdb_matrix* m, const double* ts, int src_space);
+/* max of the timestamps over KEPT rows of this shard (hyperdb/hyperdb.py:1334-1344) and their count;
+ * the host all-reduces (MAX) these over shards. */
+int hdb_matrix_kept_ts_max(hdb_matrix* m, double* ts_max, int64_t* n_kept);
+/* Build the decay column exp(ts - ts_max) with the GLOBAL maximum. */
+int hdb_matrix_set_decay_reference(hdb_matrix* m, double ts_max);
+/* Stage 1 of the HyperDB.query composition: replace ts by bias1*exp(ts - ts_max)
+ * in place on the device (what _handle_timestamps returns, hyperdb/hyperdb.py:1344-1346). */
+int hdb_matrix_stage1_recency(hdb_matrix* m, double bias1, double ts_max);
+
+/* ---- the hot path: hyperDB_ranking_algorithm_sort, ranking_algorithm.py:149-204 -------------- */
+/* n_queries independent queries (row-major n_queries x dim, dtype q_dtype) against the shard.
+ * For query b: out_count[b] = min(top_k, kept rows); out_idx[b*top_k + j] = GLOBAL row id and
+ * out_score[b*top_k + j] = float64 score of rank j, ordered by (score desc, row id asc).
+ * Scores are the reference's arithmetic (see DESIGN.md "canonical scores").
+ * out_flags may be NULL.  All outputs live in `out_space`. */
+int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q_space,
+              int64_t n_queries, int64_t top_k, double recency_bias,
+              int64_t* out_idx, double* out_score, int64_t* out_count, uint32_t* out_flags,
+              int out_space);
+
+/* ---- full similarity vector: the metric functions themselves, ranking_algorithm.py:24-61,:128-147 */
+/* out holds n_rows values of the NumPy result dtype promote(matrix dtype, q_dtype)
+ * (uint64 for HDB_HAMMING), reported through *out_dtype (HDB_F16/F32/F64; 3 = uint64). */
+int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_space,
+               void* out, int out_space, int* out_dtype);
+/* L2-normalised copy of `n_rows` x `dim` values (get_norm_vector, ranking_algorithm.py:8-21). */
+int hdb_normalize_rows(int device, int dtype, int64_t n_rows, int64_t dim, const void* src, int src_space,
+                       void* dst, int dst_space);
+
+/* ---- multi-GPU: final merge of the all-gathered per-shard candidates --- */
+/* n_lists lists of `k` (score, global id) records per query, laid out [list][query][k], with counts
+ * [list][query]; writes the merged top-k per query ordered by (score desc, id asc). */
+int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t n_queries, int64_t k,
+                   const double* scores, const int64_t* ids, const int64_t* counts, int in_space,
+                   int64_t* out_idx, double* out_score, int64_t* out_count, int out_space);
+
+/* ---- instrumentation --------------------------------------------------------------------------- */
+/* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
+int64_t hdb_launch_count(int reset);
+/* Time `iters` back-to-back repetitions of the last hdb_query configuration with CUDA events on the
+ * handle's stream (device-resident inputs/outputs); returns the mean milliseconds per repetition.
+ * what: 0 = the whole device-side query (prep + select + certify), 1 = the dominant kernel only
+ * (the streaming sweep, or the batched contraction). */
+int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter);
+/* Force a path for testing: 0 = automatic, 1 = always the exact full-vector path,
+ * 2 = fused sweep only (fail instead of falling back), 3 = tensor-core batched path when eligible. */
+int hdb_matrix_set_path(hdb_matrix* m, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPERDB_B200_H */

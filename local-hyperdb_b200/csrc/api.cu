@@ -1,0 +1,607 @@
+// C ABI of libhyperdb_b200.so (declared in include/hyperdb_b200.h): handle lifetime, workspaces,
+// path selection (fused sweep -> certify, tensor-core batched contraction, exact full-vector path).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hdb_common.cuh"
+#include "hdb_internal.h"
+#include "../../include/hyperdb_b200.h"
+
+namespace hdb {
+thread_local std::string g_error;
+int64_t g_launches = 0;
+int fail(const std::string& msg) { g_error = msg; return 1; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+  return 2;
+}
+}  // namespace hdb
+
+using namespace hdb;
+
+constexpr int64_t kChunk = 64;     // queries per fused batch chunk (bounds the candidate workspace)
+
+struct hdb_matrix {
+  int device = 0, dtype = 0;
+  int64_t n = 0, d = 0, row_offset = 0;
+  void* rows = nullptr;
+  bool owns_rows = false;
+  void* norms = nullptr;
+  void* inv_norms = nullptr;
+  uint32_t* bits = nullptr;
+  int words = 0;
+  float max_norm = 0.f, max_ratio = 1.f;
+  bool finalized = false;
+  uint32_t* mask = nullptr;
+  int64_t lo = 0, hi = 0, n_kept = 0;
+  double* ts = nullptr;
+  double* decay = nullptr;
+  bool decay_valid = false;
+  cudaStream_t stream = nullptr;
+  int path_mode = 0;
+  int grid = 0;
+  // workspaces
+  int64_t ws_q = 0;                 // query capacity of the buffers below
+  void* q_raw = nullptr;            // staged raw queries (f64 worst case)
+  QueryBuffers qb{};
+  uint64_t* cand = nullptr;         // [kChunk][grid][kMaxKP]
+  unsigned long long* tau = nullptr;
+  int* uncertified = nullptr;
+  int64_t* o_idx = nullptr; double* o_score = nullptr; int64_t* o_count = nullptr; uint32_t* o_flags = nullptr;
+  int64_t ws_k = 0;
+  double* totals = nullptr;
+  void* sort_scratch = nullptr; size_t sort_scratch_bytes = 0;
+  unsigned long long* misc = nullptr;   // [2] ordered max bits, count
+  float* stats = nullptr; int* nan_flag = nullptr;
+  // last query (for hdb_time_last_query)
+  struct { bool valid = false; int metric = 0, rdt = 0, kp = 0; int64_t nq = 0, k = 0; double bias = 0; } last;
+};
+
+static MatrixView view_of(const hdb_matrix* m) {
+  MatrixView v;
+  v.rows = m->rows; v.dtype = m->dtype; v.n = m->n; v.d = m->d; v.row_offset = m->row_offset;
+  v.norms = m->norms; v.inv_norms = m->inv_norms; v.bits = m->bits; v.words = m->words;
+  v.max_norm = m->max_norm; v.max_ratio = m->max_ratio;
+  return v;
+}
+static RowFilter filter_of(const hdb_matrix* m, double bias, bool use_decay) {
+  RowFilter f;
+  f.mask = m->mask; f.lo = m->lo; f.hi = m->hi;
+  f.decay = use_decay ? m->decay : nullptr;
+  f.bias = bias;
+  return f;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) count = 1;
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return 0;
+}
+
+static int refresh_kept(hdb_matrix* m) {
+  RowFilter f = filter_of(m, 0.0, false);
+  HDB_TRY(launch_kept_ts_max(nullptr, f, m->n, m->misc, m->misc + 1, m->stream));
+  unsigned long long host[2];
+  HDB_CUDA(cudaMemcpyAsync(host, m->misc, 16, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  m->n_kept = (int64_t)host[1];
+  return 0;
+}
+
+extern "C" {
+
+const char* hdb_last_error(void) { return g_error.c_str(); }
+int hdb_version(void) { return 100; }
+int hdb_device_count(int* count) {
+  HDB_CUDA(cudaGetDeviceCount(count));
+  return 0;
+}
+int64_t hdb_launch_count(int reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int hdb_matrix_create(int device, int dtype, int64_t n_rows, int64_t dim, int64_t row_offset, hdb_matrix** out) {
+  if (!out) return fail("hdb_matrix_create: out is NULL");
+  if (dtype < 0 || dtype > 2) return fail("hdb_matrix_create: dtype must be HDB_F16/F32/F64");
+  if (n_rows < 0 || dim <= 0) return fail("hdb_matrix_create: need n_rows >= 0 and dim > 0");
+  int ndev = 0;
+  HDB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("hdb_matrix_create: no such CUDA device");
+  HDB_CUDA(cudaSetDevice(device));
+  hdb_matrix* m = new hdb_matrix();
+  m->device = device; m->dtype = dtype; m->n = n_rows; m->d = dim; m->row_offset = row_offset;
+  m->lo = 0; m->hi = n_rows; m->n_kept = n_rows;
+  m->grid = sweep_grid_size(device);
+  int rc = dev_alloc(&m->misc, 2);
+  if (!rc) rc = dev_alloc(&m->stats, 2);
+  if (!rc) rc = dev_alloc(&m->nan_flag, 1);
+  if (!rc) rc = dev_alloc(&m->uncertified, 1);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return 0;
+}
+
+int hdb_matrix_destroy(hdb_matrix* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  if (m->owns_rows) cudaFree(m->rows);
+  void* ptrs[] = {m->norms, m->inv_norms, m->bits, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
+                  m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_idx, m->o_score, m->o_count,
+                  m->o_flags, m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete m;
+  return 0;
+}
+
+int hdb_matrix_set_stream(hdb_matrix* m, void* cuda_stream) {
+  if (!m) return fail("null handle");
+  m->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return 0;
+}
+int hdb_matrix_set_path(hdb_matrix* m, int mode) {
+  if (!m) return fail("null handle");
+  if (mode < 0 || mode > 3) return fail("hdb_matrix_set_path: mode must be 0..3");
+  m->path_mode = mode;
+  return 0;
+}
+int hdb_matrix_info(const hdb_matrix* m, int* dtype, int64_t* n_rows, int64_t* dim, int64_t* row_offset, int64_t* n_kept) {
+  if (!m) return fail("null handle");
+  if (dtype) *dtype = m->dtype;
+  if (n_rows) *n_rows = m->n;
+  if (dim) *dim = m->d;
+  if (row_offset) *row_offset = m->row_offset;
+  if (n_kept) *n_kept = m->n_kept;
+  return 0;
+}
+
+int hdb_matrix_upload(hdb_matrix* m, int64_t row_start, int64_t n_rows, const void* src, int src_space) {
+  if (!m) return fail("null handle");
+  if (row_start < 0 || n_rows < 0 || row_start + n_rows > m->n) return fail("hdb_matrix_upload: row range outside the shard");
+  HDB_CUDA(cudaSetDevice(m->device));
+  const size_t row_bytes = (size_t)m->d * dtype_size(m->dtype);
+  if (!m->rows) {
+    HDB_CUDA(cudaMalloc(&m->rows, (size_t)(m->n ? m->n : 1) * row_bytes));
+    m->owns_rows = true;
+  } else if (!m->owns_rows) {
+    return fail("hdb_matrix_upload: the shard uses adopted memory");
+  }
+  if (n_rows == 0) return 0;
+  if (!src) return fail("hdb_matrix_upload: src is NULL");
+  HDB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m->rows) + (size_t)row_start * row_bytes, src, (size_t)n_rows * row_bytes,
+                           src_space == HDB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  m->finalized = false;
+  return 0;
+}
+
+int hdb_matrix_adopt(hdb_matrix* m, void* device_rows) {
+  if (!m) return fail("null handle");
+  if (m->rows && m->owns_rows) return fail("hdb_matrix_adopt: the shard already owns storage");
+  if (!device_rows && m->n > 0) return fail("hdb_matrix_adopt: NULL rows");
+  m->rows = device_rows;
+  m->owns_rows = false;
+  m->finalized = false;
+  return 0;
+}
+
+int hdb_matrix_finalize(hdb_matrix* m) {
+  if (!m) return fail("null handle");
+  HDB_CUDA(cudaSetDevice(m->device));
+  if (!m->rows && m->n > 0) return fail("hdb_matrix_finalize: nothing uploaded");
+  const size_t nsz = (m->dtype == 2) ? 8 : 4;
+  if (m->norms) { cudaFree(m->norms); m->norms = nullptr; }
+  if (m->inv_norms) { cudaFree(m->inv_norms); m->inv_norms = nullptr; }
+  if (m->bits) { cudaFree(m->bits); m->bits = nullptr; }
+  HDB_CUDA(cudaMalloc(&m->norms, (size_t)(m->n ? m->n : 1) * nsz));
+  HDB_CUDA(cudaMalloc(&m->inv_norms, (size_t)(m->n ? m->n : 1) * nsz));
+  HDB_CUDA(cudaMemsetAsync(m->stats, 0, 8, m->stream));
+  HDB_CUDA(cudaMemsetAsync(m->nan_flag, 0, 4, m->stream));
+  MatrixView v = view_of(m);
+  HDB_TRY(launch_row_stats(v, m->norms, m->inv_norms, m->stats, m->nan_flag, m->stream));
+  float hs[2] = {0.f, 1.f};
+  int hnan = 0;
+  HDB_CUDA(cudaMemcpyAsync(hs, m->stats, 8, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaMemcpyAsync(&hnan, m->nan_flag, 4, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  if (hnan) return fail("Vectors and query_vector should not contain NaN values.");
+  m->max_norm = hs[0];
+  m->max_ratio = hs[1] > 0.f ? hs[1] : 1.f;
+  m->words = (int)(((m->d + 31) / 32 + 3) / 4 * 4);
+  m->finalized = true;
+  HDB_TRY(refresh_kept(m));
+  return 0;
+}
+
+static int ensure_bits(hdb_matrix* m) {
+  if (m->bits) return 0;
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->bits), (size_t)(m->n ? m->n : 1) * m->words * 4));
+  return launch_pack_bits(view_of(m), m->bits, m->words, m->stream);
+}
+
+int hdb_matrix_set_mask(hdb_matrix* m, const uint32_t* bits, int src_space) {
+  if (!m) return fail("null handle");
+  HDB_CUDA(cudaSetDevice(m->device));
+  if (!bits) {
+    if (m->mask) { cudaStreamSynchronize(m->stream); cudaFree(m->mask); m->mask = nullptr; }
+  } else {
+    const size_t words = (size_t)((m->n + 31) / 32);
+    if (!m->mask) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->mask), (words ? words : 1) * 4));
+    HDB_CUDA(cudaMemcpyAsync(m->mask, bits, words * 4, src_space == HDB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             m->stream));
+  }
+  m->decay_valid = false;
+  return refresh_kept(m);
+}
+
+int hdb_matrix_set_range(hdb_matrix* m, int64_t lo, int64_t hi) {
+  if (!m) return fail("null handle");
+  if (lo < 0) lo = 0;
+  if (hi > m->n) hi = m->n;
+  if (hi < lo) hi = lo;
+  m->lo = lo; m->hi = hi;
+  m->decay_valid = false;
+  HDB_CUDA(cudaSetDevice(m->device));
+  return refresh_kept(m);
+}
+
+int hdb_matrix_set_timestamps(hdb_matrix* m, const double* ts, int src_space) {
+  if (!m) return fail("null handle");
+  HDB_CUDA(cudaSetDevice(m->device));
+  m->decay_valid = false;
+  if (!ts) {
+    if (m->ts) { cudaStreamSynchronize(m->stream); cudaFree(m->ts); m->ts = nullptr; }
+    if (m->decay) { cudaFree(m->decay); m->decay = nullptr; }
+    return 0;
+  }
+  if (!m->ts) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->ts), (size_t)(m->n ? m->n : 1) * 8));
+  if (!m->decay) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->decay), (size_t)(m->n ? m->n : 1) * 8));
+  HDB_CUDA(cudaMemcpyAsync(m->ts, ts, (size_t)m->n * 8, src_space == HDB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                           m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int hdb_matrix_kept_ts_max(hdb_matrix* m, double* ts_max, int64_t* n_kept) {
+  if (!m) return fail("null handle");
+  if (!m->ts) return fail("hdb_matrix_kept_ts_max: no timestamps set");
+  HDB_CUDA(cudaSetDevice(m->device));
+  RowFilter f = filter_of(m, 0.0, false);
+  HDB_TRY(launch_kept_ts_max(m->ts, f, m->n, m->misc, m->misc + 1, m->stream));
+  unsigned long long host[2];
+  HDB_CUDA(cudaMemcpyAsync(host, m->misc, 16, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  if (ts_max) *ts_max = host[1] ? decode_ordered_double(host[0]) : -INFINITY;
+  if (n_kept) *n_kept = (int64_t)host[1];
+  m->n_kept = (int64_t)host[1];
+  return 0;
+}
+
+int hdb_matrix_set_decay_reference(hdb_matrix* m, double ts_max) {
+  if (!m) return fail("null handle");
+  if (!m->ts) return fail("hdb_matrix_set_decay_reference: no timestamps set");
+  HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(launch_decay(m->ts, m->decay, m->n, ts_max, m->stream));
+  m->decay_valid = true;
+  return 0;
+}
+
+int hdb_matrix_stage1_recency(hdb_matrix* m, double bias1, double ts_max) {
+  if (!m) return fail("null handle");
+  if (!m->ts) return fail("hdb_matrix_stage1_recency: no timestamps set");
+  HDB_CUDA(cudaSetDevice(m->device));
+  m->decay_valid = false;
+  return launch_stage1(m->ts, m->n, bias1, ts_max, m->stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+static int ensure_workspace(hdb_matrix* m, int64_t nq, int64_t k) {
+  const int64_t cq = nq < kChunk ? (nq < 1 ? 1 : nq) : kChunk;       // fused chunk capacity
+  if (m->ws_q < nq) {
+    HDB_TRY(dev_alloc(reinterpret_cast<char**>(&m->q_raw), (size_t)nq * m->d * 8));
+    HDB_TRY(dev_alloc(reinterpret_cast<char**>(&m->qb.qa), (size_t)nq * m->d * 8));
+    HDB_TRY(dev_alloc(&m->qb.qc, (size_t)nq * m->d));
+    HDB_TRY(dev_alloc(&m->qb.qbits, (size_t)nq * m->words));
+    HDB_TRY(dev_alloc(&m->qb.qnorm, (size_t)nq));
+    HDB_TRY(dev_alloc(&m->qb.qflags, (size_t)nq));
+    HDB_TRY(dev_alloc(&m->tau, (size_t)nq));
+    HDB_TRY(dev_alloc(&m->o_count, (size_t)nq));
+    HDB_TRY(dev_alloc(&m->o_flags, (size_t)nq));
+    m->ws_q = nq;
+    m->ws_k = 0;
+  }
+  if (!m->cand) HDB_TRY(dev_alloc(&m->cand, (size_t)kChunk * m->grid * kMaxKP));
+  (void)cq;
+  if (m->ws_k < m->ws_q * (k > 0 ? k : 1)) {
+    const int64_t need = m->ws_q * (k > 0 ? k : 1);
+    HDB_TRY(dev_alloc(&m->o_idx, (size_t)need));
+    HDB_TRY(dev_alloc(&m->o_score, (size_t)need));
+    m->ws_k = need;
+  }
+  if (!m->totals) HDB_TRY(dev_alloc(&m->totals, (size_t)(m->n ? m->n : 1)));
+  return 0;
+}
+
+static int pick_kp(const hdb_matrix* m, int64_t k) {
+  if (m->path_mode == 1) return 0;
+  if (k <= 16) return 32;
+  if (k <= 100) return 128;
+  return 0;
+}
+
+// Enqueue the fused path for queries [b0, b0+cnt) of the prepared batch; results go to (idx, score, count, flags).
+static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int64_t cnt, int64_t k, const RowFilter& f,
+                     int64_t* idx, double* score, int64_t* count, uint32_t* flags) {
+  MatrixView v = view_of(m);
+  HDB_CUDA(cudaMemsetAsync(m->tau + b0, 0, (size_t)cnt * 8, m->stream));
+  const int elt = (m->dtype == 2) ? 8 : 4;
+  for (int64_t i = 0; i < cnt; ++i) {
+    SweepOut so;
+    so.cand = m->cand + (size_t)i * m->grid * kp;
+    so.tau = m->tau + b0 + i;
+    so.grid = m->grid;
+    const void* qa = reinterpret_cast<const char*>(m->qb.qa) + (size_t)(b0 + i) * m->d * elt;
+    const uint32_t* qbits = m->qb.qbits + (size_t)(b0 + i) * m->words;
+    HDB_TRY(launch_sweep(v, metric, qa, qbits, f, kp, so, m->stream));
+  }
+  FinalizeArgs a;
+  a.m = v; a.f = f; a.metric = metric; a.rdt = rdt; a.kp = kp; a.k = (int)k; a.n_kept = m->n_kept; a.grid = m->grid;
+  a.cand = m->cand; a.tau = m->tau + b0;
+  a.qb = m->qb;
+  a.qb.qc += b0 * m->d; a.qb.qbits += b0 * m->words; a.qb.qnorm += b0; a.qb.qflags += b0;
+  a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
+  a.uncertified = m->uncertified;
+  return launch_finalize(a, cnt, m->stream);
+}
+
+static int run_exact(hdb_matrix* m, int metric, int rdt, int64_t b, int64_t k, const RowFilter& f, int64_t* idx, double* score,
+                     int64_t* count) {
+  MatrixView v = view_of(m);
+  HDB_TRY(launch_full_scores(v, f, metric, rdt, m->qb.qc + b * m->d, m->qb.qbits + b * m->words, m->totals, m->stream));
+  return exact_topk(m->device, m->totals, m->n, m->row_offset, k, m->n_kept, idx + b * k, score + b * k, count + b,
+                    &m->sort_scratch, &m->sort_scratch_bytes, m->stream);
+}
+
+int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q_space, int64_t nq, int64_t top_k,
+              double recency_bias, int64_t* out_idx, double* out_score, int64_t* out_count, uint32_t* out_flags,
+              int out_space) {
+  if (!m) return fail("null handle");
+  if (!m->finalized) return fail("hdb_query: call hdb_matrix_finalize first");
+  if (metric < 0 || metric > 4) return fail("Unknown metric");
+  if (q_dtype < 0 || q_dtype > 2) return fail("hdb_query: q_dtype must be HDB_F16/F32/F64");
+  if (nq < 0) return fail("hdb_query: negative query count");
+  if (nq == 0) return 0;
+  if (!queries || !out_count) return fail("hdb_query: NULL argument");
+  HDB_CUDA(cudaSetDevice(m->device));
+  const int64_t k = top_k > 0 ? top_k : 0;
+  if (k > 0 && (!out_idx || !out_score)) return fail("hdb_query: NULL output");
+  const bool use_decay = m->ts != nullptr && m->decay_valid;
+  if (m->ts && !m->decay_valid && recency_bias != 0.0)
+    return fail("hdb_query: timestamps set but hdb_matrix_set_decay_reference was not called");
+  HDB_TRY(ensure_workspace(m, nq, k));
+  const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
+  if (metric == HDB_HAMMING) HDB_TRY(ensure_bits(m));
+
+  const void* q_dev = queries;
+  if (q_space == HDB_HOST) {
+    HDB_CUDA(cudaMemcpyAsync(m->q_raw, queries, (size_t)nq * m->d * dtype_size(q_dtype), cudaMemcpyHostToDevice, m->stream));
+    q_dev = m->q_raw;
+  }
+  HDB_TRY(launch_prep_query(q_dev, q_dtype, nq, m->d, metric, m->dtype, m->words, m->qb, m->stream));
+  const RowFilter f = filter_of(m, recency_bias, use_decay);
+  const bool dev_out = (out_space == HDB_DEVICE);
+  int64_t* idx = dev_out ? out_idx : m->o_idx;
+  double* score = dev_out ? out_score : m->o_score;
+  int64_t* count = dev_out ? out_count : m->o_count;
+  uint32_t* flags = dev_out ? out_flags : m->o_flags;
+
+  int kp = pick_kp(m, k);
+  const size_t qsm = (size_t)m->d * (m->dtype == 2 ? 8 : 4);
+  if (kp && qsm + 40000 > 200 * 1024) kp = 0;                     // query does not fit next to the lists
+  if (kp == 0 && m->path_mode == 2) return fail("hdb_query: fused path forced but not applicable");
+  m->last.valid = true; m->last.metric = metric; m->last.rdt = rdt; m->last.kp = kp; m->last.nq = nq; m->last.k = k;
+  m->last.bias = recency_bias;
+
+  if (k == 0) {
+    HDB_CUDA(cudaMemsetAsync(count, 0, (size_t)nq * 8, m->stream));
+    if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
+  } else if (kp) {
+    HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
+    for (int64_t b0 = 0; b0 < nq; b0 += kChunk) {
+      const int64_t cnt = nq - b0 < kChunk ? nq - b0 : kChunk;
+      HDB_TRY(run_fused(m, metric, rdt, kp, b0, cnt, k, f, idx, score, count, flags));
+    }
+  } else {
+    for (int64_t b = 0; b < nq; ++b) HDB_TRY(run_exact(m, metric, rdt, b, k, f, idx, score, count));
+    if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
+  }
+  if (dev_out) return 0;
+
+  // host outputs: synchronise, repair uncertified queries with the exact path, copy out
+  std::vector<uint32_t> hflags((size_t)nq, 0u);
+  HDB_CUDA(cudaMemcpyAsync(hflags.data(), flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  bool any_nan = false;
+  for (int64_t b = 0; b < nq; ++b) {
+    if (hflags[b] & HDB_FLAG_QUERY_NAN) any_nan = true;
+    if (hflags[b] & HDB_FLAG_UNCERTIFIED) {
+      if (m->path_mode == 2) return fail("hdb_query: fused path forced but the certificate failed");
+      HDB_TRY(run_exact(m, metric, rdt, b, k, f, idx, score, count));
+      hflags[b] = (hflags[b] & ~HDB_FLAG_UNCERTIFIED) | HDB_FLAG_FALLBACK;
+    }
+  }
+  if (any_nan) return fail("Vectors and query_vector should not contain NaN values.");
+  if (k > 0) {
+    HDB_CUDA(cudaMemcpyAsync(out_idx, idx, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, m->stream));
+    HDB_CUDA(cudaMemcpyAsync(out_score, score, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, m->stream));
+  }
+  HDB_CUDA(cudaMemcpyAsync(out_count, count, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  if (out_flags) memcpy(out_flags, hflags.data(), (size_t)nq * 4);
+  return 0;
+}
+
+int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter) {
+  if (!m || !ms_per_iter) return fail("null argument");
+  if (!m->last.valid || m->last.kp == 0 || m->last.k == 0) return fail("hdb_time_last_query: no fused query to replay");
+  if (iters < 1) iters = 1;
+  HDB_CUDA(cudaSetDevice(m->device));
+  const bool use_decay = m->ts != nullptr && m->decay_valid;
+  const RowFilter f = filter_of(m, m->last.bias, use_decay);
+  cudaEvent_t e0, e1;
+  HDB_CUDA(cudaEventCreate(&e0));
+  HDB_CUDA(cudaEventCreate(&e1));
+  const int64_t nq = m->last.nq < kChunk ? m->last.nq : kChunk;
+  MatrixView v = view_of(m);
+  const int elt = (m->dtype == 2) ? 8 : 4;
+  HDB_CUDA(cudaEventRecord(e0, m->stream));
+  for (int it = 0; it < iters; ++it) {
+    if (what == 1) {
+      HDB_CUDA(cudaMemsetAsync(m->tau, 0, 8, m->stream));
+      SweepOut so; so.cand = m->cand; so.tau = m->tau; so.grid = m->grid;
+      (void)elt;
+      HDB_TRY(launch_sweep(v, m->last.metric, m->qb.qa, m->qb.qbits, f, m->last.kp, so, m->stream));
+    } else {
+      HDB_TRY(run_fused(m, m->last.metric, m->last.rdt, m->last.kp, 0, nq, m->last.k, f, m->o_idx, m->o_score, m->o_count,
+                        m->o_flags));
+    }
+  }
+  HDB_CUDA(cudaEventRecord(e1, m->stream));
+  HDB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  HDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_iter = ms / iters;
+  return 0;
+}
+
+int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_space, void* out, int out_space,
+               int* out_dtype) {
+  if (!m) return fail("null handle");
+  if (!m->finalized) return fail("hdb_scores: call hdb_matrix_finalize first");
+  if (metric < 0 || metric > 4) return fail("Unknown metric");
+  if (q_dtype < 0 || q_dtype > 2) return fail("hdb_scores: q_dtype must be HDB_F16/F32/F64");
+  if (!query || !out) return fail("hdb_scores: NULL argument");
+  HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(ensure_workspace(m, 1, 1));
+  const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
+  if (metric == HDB_HAMMING) HDB_TRY(ensure_bits(m));
+  const void* q_dev = query;
+  if (q_space == HDB_HOST) {
+    HDB_CUDA(cudaMemcpyAsync(m->q_raw, query, (size_t)m->d * dtype_size(q_dtype), cudaMemcpyHostToDevice, m->stream));
+    q_dev = m->q_raw;
+  }
+  HDB_TRY(launch_prep_query(q_dev, q_dtype, 1, m->d, metric, m->dtype, m->words, m->qb, m->stream));
+  const size_t esz = (metric == HDB_HAMMING) ? 8 : (size_t)dtype_size(rdt);
+  if (out_dtype) *out_dtype = (metric == HDB_HAMMING) ? 3 : rdt;
+  void* dst = out;
+  void* tmp = nullptr;
+  if (out_space == HDB_HOST) {
+    HDB_CUDA(cudaMalloc(&tmp, (size_t)(m->n ? m->n : 1) * esz));
+    dst = tmp;
+  }
+  int rc = launch_scores_out(view_of(m), metric, rdt, m->qb.qc, m->qb.qbits, dst, m->stream);
+  if (!rc && out_space == HDB_HOST) {
+    cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)m->n * esz, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "hdb_scores copy");
+    uint32_t qf = 0;
+    if (!rc) {
+      e = cudaMemcpy(&qf, m->qb.qflags, 4, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = cuda_fail(e, "hdb_scores flags");
+    }
+    if (!rc && (qf & HDB_FLAG_QUERY_NAN)) rc = fail("Vectors and query_vector should not contain NaN values.");
+  }
+  if (tmp) cudaFree(tmp);
+  return rc;
+}
+
+int hdb_normalize_rows(int device, int dtype, int64_t n_rows, int64_t dim, const void* src, int src_space, void* dst,
+                       int dst_space) {
+  if (dtype < 0 || dtype > 2) return fail("hdb_normalize_rows: bad dtype");
+  if (n_rows < 0 || dim <= 0) return fail("hdb_normalize_rows: bad shape");
+  if (n_rows == 0) return 0;
+  HDB_CUDA(cudaSetDevice(device));
+  const size_t bytes = (size_t)n_rows * dim * dtype_size(dtype);
+  void *dsrc = nullptr, *ddst = nullptr;
+  const void* s = src;
+  void* d = dst;
+  int rc = 0;
+  if (src_space == HDB_HOST) {
+    HDB_CUDA(cudaMalloc(&dsrc, bytes));
+    cudaError_t e = cudaMemcpy(dsrc, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dsrc); return cuda_fail(e, "normalize upload"); }
+    s = dsrc;
+  }
+  if (dst_space == HDB_HOST) {
+    cudaError_t e = cudaMalloc(&ddst, bytes);
+    if (e != cudaSuccess) { if (dsrc) cudaFree(dsrc); return cuda_fail(e, "normalize alloc"); }
+    d = ddst;
+  }
+  rc = launch_normalize_rows(dtype, n_rows, dim, s, d, nullptr);
+  if (!rc && dst_space == HDB_HOST) {
+    cudaError_t e = cudaMemcpy(dst, ddst, bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = cuda_fail(e, "normalize download");
+  }
+  if (dsrc) cudaFree(dsrc);
+  if (ddst) cudaFree(ddst);
+  return rc;
+}
+
+int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t nq, int64_t k, const double* scores,
+                   const int64_t* ids, const int64_t* counts, int in_space, int64_t* out_idx, double* out_score,
+                   int64_t* out_count, int out_space) {
+  if (n_lists <= 0 || nq < 0 || k < 0) return fail("hdb_merge_topk: bad sizes");
+  if (nq == 0) return 0;
+  HDB_CUDA(cudaSetDevice(device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const size_t rec = (size_t)n_lists * nq * (k ? k : 1);
+  std::vector<void*> tmp;
+  auto stage_in = [&](const void* p, size_t bytes, const void** out) -> int {
+    if (in_space == HDB_DEVICE) { *out = p; return 0; }
+    void* d = nullptr;
+    HDB_CUDA(cudaMalloc(&d, bytes ? bytes : 8));
+    tmp.push_back(d);
+    HDB_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s));
+    *out = d;
+    return 0;
+  };
+  const void *ds = nullptr, *di = nullptr, *dc = nullptr;
+  int rc = stage_in(scores, rec * 8, &ds);
+  if (!rc) rc = stage_in(ids, rec * 8, &di);
+  if (!rc) rc = stage_in(counts, (size_t)n_lists * nq * 8, &dc);
+  int64_t* oi = out_idx; double* os = out_score; int64_t* oc = out_count;
+  if (!rc && out_space == HDB_HOST) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, (size_t)nq * (k ? k : 1) * 16 + (size_t)nq * 8);
+    if (e != cudaSuccess) rc = cuda_fail(e, "merge alloc");
+    else {
+      tmp.push_back(d);
+      oi = reinterpret_cast<int64_t*>(d);
+      os = reinterpret_cast<double*>(oi + nq * (k ? k : 1));
+      oc = reinterpret_cast<int64_t*>(os + nq * (k ? k : 1));
+    }
+  }
+  if (!rc) rc = launch_merge_topk(n_lists, nq, k, (const double*)ds, (const int64_t*)di, (const int64_t*)dc, oi, os, oc, s);
+  if (!rc && out_space == HDB_HOST) {
+    cudaError_t e = cudaSuccess;
+    if (k) e = cudaMemcpyAsync(out_idx, oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && k) e = cudaMemcpyAsync(out_score, os, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_count, oc, (size_t)nq * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = cuda_fail(e, "merge download");
+  } else if (!tmp.empty()) {
+    cudaStreamSynchronize(s);
+  }
+  for (void* p : tmp) cudaFree(p);
+  return rc;
+}
+
+}  // extern "C"

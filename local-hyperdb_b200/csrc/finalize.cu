@@ -1,0 +1,325 @@
+// Second half of the hot path: merge the per-CTA candidate keys of the sweep, re-score the KP
+// candidates in the reference's exact arithmetic (canonical.cuh), order them by
+// (float64 score desc, row asc) as hyperdb/ranking_algorithm.py:194-204 would (ties -> lower index,
+// north_star), and CERTIFY that no row outside the candidate list can belong to the top-k.
+// Plus: the exact full-vector path (every row canonical -> stable radix sort) that serves
+//   * the metric functions themselves (hdb_scores; ranking_algorithm.py:24-61,:128-147),
+//   * queries the certificate rejects, top_k beyond the fused classes, and tests,
+// and the multi-GPU final merge of all-gathered candidates.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "canonical.cuh"
+#include "hdb_internal.h"
+#include "../../include/hyperdb_b200.h"
+
+namespace hdb {
+
+constexpr int kSurvCap = 2048;      // candidate keys >= the final threshold that one CTA can merge
+constexpr int kFinThreads = 256;
+constexpr uint32_t kFlagUncertified = 8u;
+
+// Upper bound of the CANONICAL total score of any row whose selection key is <= the KP-th key
+// (score part s).  See DESIGN.md "certificate"; every term is a worst-case rounding bound.
+__device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) {
+  const double D = (double)a.m.d + 8.0;
+  const double uk = 1.1920928955078125e-7;                    // 2^-23: float32 key rounding (2x slack)
+  const double ua = (a.m.dtype == 2) ? 4.440892098500626e-16 : 1.1920928955078125e-7;   // sweep accumulate type
+  const double uR = unit_roundoff(a.rdt);
+  const double uT = unit_roundoff(a.m.dtype);
+  const bool decay = a.f.decay != nullptr;
+  const double chain16 = (a.rdt == 0) ? D * 1.1920928955078125e-7 : 0.0;   // HALF_dot / f16 pairwise run in float32
+  if (a.metric == HDB_HAMMING) return s + fabs(s) * uk;
+  if (a.metric == HDB_DOT || a.metric == HDB_COSINE) {
+    const double A = (double)(a.metric == HDB_DOT ? a.m.max_norm : a.m.max_ratio) * qnorm;   // >= sum |v_i q_i|
+    double e = D * ua + chain16;
+    if (a.metric == HDB_COSINE) e += 3.0 * uT + (a.m.dtype == 0 ? sqrt(D) * 5.9604644775390625e-8 : 0.0);
+    const double b = s + fabs(s) * uk + A * e;
+    return decay ? b + 2.0 * uR * A + fabs(b) * 1e-15 : b + 2.0 * uR * fabs(b);
+  }
+  // euclidean / manhattan: similarity in (0, 1]
+  if (decay) {
+    double e = 8.0 * uR + D * ua + chain16 + ua * qnorm;
+    if (a.rdt == 0 && a.metric == HDB_EUCLIDEAN) e += sqrt(D * 5.9604644775390625e-8);
+    return s + fabs(s) * uk + e;
+  }
+  if (!(s > 0.0)) return INFINITY;
+  const double s_hi = s * (1.0 + uk);
+  double d_lo = 1.0 / s_hi - 1.0 - 4.76837158203125e-7 - ua * qnorm;          // distance of the fast pass, lower bound
+  if (d_lo < 0.0) d_lo = 0.0;
+  double dc;
+  if (a.metric == HDB_EUCLIDEAN) {
+    double d2 = d_lo * d_lo * (1.0 - D * ua - 6.0 * uR - chain16);
+    if (a.rdt == 0) d2 -= D * 5.9604644775390625e-8;                          // float16 squares flushed below 2^-24
+    dc = sqrt(d2 > 0.0 ? d2 : 0.0) * (1.0 - 3.0 * uR);
+  } else {
+    dc = d_lo * (1.0 - D * ua - 4.0 * uR - chain16);
+    if (dc < 0.0) dc = 0.0;
+  }
+  return (1.0 / (1.0 + dc)) * (1.0 + 3.0 * uR);
+}
+
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
+  __shared__ uint64_t surv[kSurvCap];
+  __shared__ double c_tot[kMaxKP];
+  __shared__ uint32_t c_row[kMaxKP];
+  __shared__ double o_tot[kMaxKP];
+  __shared__ uint32_t o_row[kMaxKP];
+  __shared__ int s_count;
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int kk = (int)((int64_t)a.k < a.n_kept ? (int64_t)a.k : a.n_kept);
+  const uint32_t qflag = a.qb.qflags[b];
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  const unsigned long long tau = a.tau[b];
+  const uint64_t* cand = a.cand + b * (int64_t)a.grid * a.kp;
+  const int total = a.grid * a.kp;
+  for (int i = tid; i < total; i += kFinThreads) {
+    uint64_t key = cand[i];
+    if (key != 0 && key >= tau) {
+      int pos = atomicAdd(&s_count, 1);
+      if (pos < kSurvCap) surv[pos] = key;
+    }
+  }
+  __syncthreads();
+  const int found = s_count;
+  if (found > kSurvCap) {          // pathological tie plateau: hand the query to the exact path
+    if (tid == 0) {
+      a.out_count[b] = kk;
+      if (a.out_flags) a.out_flags[b] = qflag | kFlagUncertified;
+      atomicAdd(a.uncertified, 1);
+    }
+    return;
+  }
+  int pow2 = 32;
+  while (pow2 < found) pow2 <<= 1;
+  for (int i = found + tid; i < pow2; i += kFinThreads) surv[i] = 0;
+  __syncthreads();
+  bitonic_desc(surv, pow2, tid, kFinThreads, [] { __syncthreads(); });
+  const int m = found < a.kp ? found : a.kp;          // candidates to certify
+
+  CanonArgs ca;
+  ca.rows = a.m.rows; ca.sdt = a.m.dtype; ca.d = a.m.d;
+  ca.qc = a.qb.qc + b * a.m.d;
+  ca.bits = a.m.bits; ca.words = a.m.words;
+  ca.qbits = a.qb.qbits ? a.qb.qbits + b * a.m.words : nullptr;
+  ca.metric = a.metric;
+  if (tid < m) {
+    const uint32_t row = key_row(surv[tid]);
+    double nrm = 1.0;
+    if (a.metric == HDB_COSINE)
+      nrm = a.m.dtype == 2 ? reinterpret_cast<const double*>(a.m.norms)[row] : (double)reinterpret_cast<const float*>(a.m.norms)[row];
+    const double sim = canonical_similarity_rt(ca, a.rdt, row, nrm);
+    c_tot[tid] = total_score(sim, a.f.decay, a.f.bias, row);
+    c_row[tid] = row;
+  }
+  __syncthreads();
+  if (tid < m) {
+    const double t = c_tot[tid];
+    const uint32_t r = c_row[tid];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const double tj = c_tot[j];
+      rank += (tj > t) || (tj == t && c_row[j] < r);
+    }
+    o_tot[rank] = t;
+    o_row[rank] = r;
+  }
+  __syncthreads();
+  bool certified = true;
+  const bool exact_keys = (a.metric == HDB_HAMMING) && (a.f.decay == nullptr);
+  if (kk > 0 && a.n_kept > (int64_t)m && !exact_keys) {
+    if (m < kk) certified = false;
+    else {
+      const double s_edge = (double)key_score(surv[m - 1]);
+      const double bound = outsider_bound(s_edge, a, a.qb.qnorm[b]);
+      certified = o_tot[kk - 1] > bound;
+    }
+  }
+  if (m < kk) certified = false;
+  for (int i = tid; i < a.k; i += kFinThreads) {
+    const bool have = i < kk && i < m;
+    a.out_idx[b * a.k + i] = have ? (int64_t)o_row[i] + a.m.row_offset : -1;
+    a.out_score[b * a.k + i] = have ? o_tot[i] : -INFINITY;
+  }
+  if (tid == 0) {
+    a.out_count[b] = kk;
+    if (a.out_flags) a.out_flags[b] = qflag | (certified ? 0u : kFlagUncertified);
+    if (!certified) atomicAdd(a.uncertified, 1);
+  }
+}
+
+int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s) {
+  if (nq == 0) return 0;
+  finalize_kernel<<<(unsigned)nq, kFinThreads, 0, s>>>(a);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact full-vector path
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool kept_row(const RowFilter& f, int64_t row) {
+  if (row < f.lo || row >= f.hi) return false;
+  if (f.mask && !((f.mask[row >> 5] >> (row & 31)) & 1u)) return false;
+  return true;
+}
+
+__device__ __forceinline__ CanonArgs canon_args(const MatrixView& m, int metric, const double* qc, const uint32_t* qbits) {
+  CanonArgs ca;
+  ca.rows = m.rows; ca.sdt = m.dtype; ca.d = m.d; ca.qc = qc;
+  ca.bits = m.bits; ca.qbits = qbits; ca.words = m.words; ca.metric = metric;
+  return ca;
+}
+
+__device__ __forceinline__ double row_canonical(const MatrixView& m, CanonArgs& ca, int rdt, int64_t row) {
+  double nrm = 1.0;
+  if (ca.metric == HDB_COSINE)
+    nrm = m.dtype == 2 ? reinterpret_cast<const double*>(m.norms)[row] : (double)reinterpret_cast<const float*>(m.norms)[row];
+  return canonical_similarity_rt(ca, rdt, row, nrm);
+}
+
+__global__ void full_scores_kernel(MatrixView m, RowFilter f, int metric, int rdt, const double* qc,
+                                   const uint32_t* qbits, double* totals) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= m.n) return;
+  if (!kept_row(f, row)) { totals[row] = __longlong_as_double(-1ll); return; }   // -NaN sorts last (descending)
+  CanonArgs ca = canon_args(m, metric, qc, qbits);
+  totals[row] = total_score(row_canonical(m, ca, rdt, row), f.decay, f.bias, row);
+}
+
+int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,
+                       const uint32_t* qbits, double* totals, cudaStream_t s) {
+  if (m.n == 0) return 0;
+  int64_t blocks = (m.n + 127) / 128;
+  full_scores_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, f, metric, rdt, qc, qbits, totals);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// the metric function's own output: dtype R (uint64 for hamming)
+__global__ void scores_out_kernel(MatrixView m, int metric, int rdt, const double* qc, const uint32_t* qbits, void* out) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= m.n) return;
+  CanonArgs ca = canon_args(m, metric, qc, qbits);
+  const double v = row_canonical(m, ca, rdt, row);
+  if (metric == HDB_HAMMING) reinterpret_cast<unsigned long long*>(out)[row] = (unsigned long long)(long long)v;
+  else if (rdt == 0) reinterpret_cast<__half*>(out)[row] = __float2half_rn((float)v);
+  else if (rdt == 1) reinterpret_cast<float*>(out)[row] = (float)v;
+  else reinterpret_cast<double*>(out)[row] = v;
+}
+
+int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits, void* out,
+                      cudaStream_t s) {
+  if (m.n == 0) return 0;
+  int64_t blocks = (m.n + 127) / 128;
+  scores_out_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, metric, rdt, qc, qbits, out);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void iota_kernel(int64_t* v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = i;
+}
+__global__ void take_topk_kernel(const double* keys, const int64_t* vals, int64_t k, int64_t kk, int64_t row_offset,
+                                 int64_t* out_idx, double* out_score, int64_t* out_count) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) {
+    out_idx[i] = i < kk ? vals[i] + row_offset : -1;
+    out_score[i] = i < kk ? keys[i] : -INFINITY;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = kk;
+}
+
+// Stable descending radix sort of (total, row): equal totals keep ascending row order.
+int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
+               int64_t* out_idx, double* out_score, int64_t* out_count, void** scratch, size_t* scratch_bytes,
+               cudaStream_t s) {
+  (void)device;
+  if (n > 0x7fffffff) return fail("exact path: more than 2^31 rows per shard");
+  const int64_t kk = k < n_kept ? k : n_kept;
+  size_t temp = 0;
+  HDB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, temp, (const double*)nullptr, (double*)nullptr,
+                                                     (const int64_t*)nullptr, (int64_t*)nullptr, (int)n, 0, 64, s));
+  const size_t arr = ((size_t)n * 8 + 255) & ~size_t(255);
+  const size_t need = 3 * arr + temp + 256;
+  if (*scratch_bytes < need) {
+    if (*scratch) HDB_CUDA(cudaFree(*scratch));
+    *scratch = nullptr; *scratch_bytes = 0;
+    HDB_CUDA(cudaMalloc(scratch, need));
+    *scratch_bytes = need;
+  }
+  char* base = reinterpret_cast<char*>(*scratch);
+  double* keys_out = reinterpret_cast<double*>(base);
+  int64_t* vals_in = reinterpret_cast<int64_t*>(base + arr);
+  int64_t* vals_out = reinterpret_cast<int64_t*>(base + 2 * arr);
+  void* tmp = base + 3 * arr;
+  if (n > 0) {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    iota_kernel<<<(unsigned)blocks, 256, 0, s>>>(vals_in, n);
+    HDB_LAUNCHED();
+    HDB_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, temp, totals, keys_out, vals_in, vals_out, (int)n, 0, 64, s));
+    HDB_LAUNCHED();
+  }
+  if (k > 0) {
+    int64_t blocks = (k + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    take_topk_kernel<<<(unsigned)blocks, 256, 0, s>>>(keys_out, vals_out, k, kk, row_offset, out_idx, out_score, out_count);
+  } else {
+    take_topk_kernel<<<1, 32, 0, s>>>(keys_out, vals_out, 0, 0, row_offset, out_idx, out_score, out_count);
+  }
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU final merge: n_lists x k records per query -> top-k by (score desc, id asc).
+// One CTA per query; rank by counting (n_lists*k is at most a few thousand records).
+// ---------------------------------------------------------------------------------------------
+__global__ void merge_topk_kernel(int64_t n_lists, int64_t nq, int64_t k, const double* scores, const int64_t* ids,
+                                  const int64_t* counts, int64_t* out_idx, double* out_score, int64_t* out_count) {
+  const int64_t b = blockIdx.x;
+  const int64_t total = n_lists * k;
+  int64_t have = 0;
+  for (int64_t l = 0; l < n_lists; ++l) have += counts[l * nq + b];
+  const int64_t kk = have < k ? have : k;
+  for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+    out_idx[b * k + i] = -1;
+    out_score[b * k + i] = -INFINITY;
+  }
+  __syncthreads();
+  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+    const int64_t l = e / k, j = e % k;
+    if (j >= counts[l * nq + b]) continue;
+    const double t = scores[(l * nq + b) * k + j];
+    const int64_t r = ids[(l * nq + b) * k + j];
+    int64_t rank = 0;
+    for (int64_t l2 = 0; l2 < n_lists && rank < kk; ++l2) {
+      const int64_t c2 = counts[l2 * nq + b];
+      const double* s2 = scores + (l2 * nq + b) * k;
+      const int64_t* i2 = ids + (l2 * nq + b) * k;
+      for (int64_t j2 = 0; j2 < c2; ++j2) {
+        const double t2 = s2[j2];
+        if (t2 > t || (t2 == t && i2[j2] < r)) ++rank;
+        else if (t2 < t) break;                    // each list is sorted descending
+      }
+    }
+    if (rank < kk) { out_idx[b * k + rank] = r; out_score[b * k + rank] = t; }
+  }
+  if (threadIdx.x == 0) out_count[b] = kk;
+}
+
+int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, const double* scores, const int64_t* ids,
+                      const int64_t* counts, int64_t* out_idx, double* out_score, int64_t* out_count, cudaStream_t s) {
+  if (nq == 0) return 0;
+  merge_topk_kernel<<<(unsigned)nq, 256, 0, s>>>(n_lists, nq, k, scores, ids, counts, out_idx, out_score, out_count);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hdb

@@ -1,0 +1,107 @@
+// Internal host-side declarations shared by the translation units of libhyperdb_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace hdb {
+
+extern thread_local std::string g_error;
+extern int64_t g_launches;
+int fail(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define HDB_CUDA(x)                                             \
+  do {                                                          \
+    cudaError_t e__ = (x);                                      \
+    if (e__ != cudaSuccess) return ::hdb::cuda_fail(e__, #x);   \
+  } while (0)
+#define HDB_TRY(x)            \
+  do {                        \
+    int rc__ = (x);           \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+#define HDB_LAUNCHED() (++::hdb::g_launches)
+
+constexpr int kMaxKP = 128;            // largest candidate-list class of the fused pass
+constexpr int kSweepThreads = 256;     // 8 warps per CTA
+constexpr int kSweepWarps = kSweepThreads / 32;
+
+// Row subset + decay, as consumed by every scoring kernel.
+struct RowFilter {
+  const uint32_t* mask;   // 1 bit per local row, or nullptr
+  int64_t lo, hi;         // kept range [lo, hi)
+  const double* decay;    // exp(ts - max ts) per row, or nullptr
+  double bias;            // recency_bias
+};
+
+struct QueryBuffers {     // per-batch device buffers written by prep_query
+  void* qa;               // [B][d] query in the sweep's accumulate type (float, or double for f64 storage)
+  double* qc;             // [B][d] canonical query values (dtype R widened to double)
+  uint32_t* qbits;        // [B][words] sign bits
+  double* qnorm;          // [B] ||qc||_2
+  uint32_t* qflags;       // [B] HDB_FLAG_QUERY_NAN
+};
+
+struct MatrixView {
+  const void* rows;
+  int dtype;
+  int64_t n, d;
+  int64_t row_offset;
+  const void* norms;      // canonical norms: float (f16/f32 storage) or double (f64), zero -> 1
+  const void* inv_norms;  // 1/norm in the accumulate type
+  const uint32_t* bits;   // packed sign bits or nullptr
+  int words;              // words per packed row
+  float max_norm;         // max_i ||v_i||_2
+  float max_ratio;        // max_i ||v_i||_2 / canonical norm_i
+};
+
+// ---- ingest.cu
+int launch_row_stats(const MatrixView& m, void* norms, void* inv_norms, float* d_stats /*[2] max_norm,max_ratio*/,
+                     int* d_nan, cudaStream_t s);
+int launch_pack_bits(const MatrixView& m, uint32_t* bits, int words, cudaStream_t s);
+int launch_kept_ts_max(const double* ts, const RowFilter& f, int64_t n, unsigned long long* d_max_bits,
+                       unsigned long long* d_count, cudaStream_t s);
+int launch_decay(const double* ts, double* decay, int64_t n, double ts_max, cudaStream_t s);
+int launch_stage1(double* ts, int64_t n, double bias1, double ts_max, cudaStream_t s);
+int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int metric, int sdt, int words,
+                      const QueryBuffers& qb, cudaStream_t s);
+int launch_normalize_rows(int dtype, int64_t n, int64_t d, const void* src, void* dst, cudaStream_t s);
+double decode_ordered_double(unsigned long long bits);
+
+// ---- sweep.cu : fused score + select pass (B = 1 per launch)
+struct SweepOut {
+  uint64_t* cand;          // [grid][KP] per-CTA candidate keys (descending)
+  unsigned long long* tau; // global running threshold (must be zeroed before the launch)
+  int grid;
+};
+int sweep_grid_size(int device);
+int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const RowFilter& f, int kp,
+                 const SweepOut& out, cudaStream_t s);
+
+// ---- finalize.cu : merge + canonical re-score + certification; exact full-vector path
+struct FinalizeArgs {
+  MatrixView m;
+  RowFilter f;
+  int metric, rdt;               // result dtype R
+  int kp, k;                     // candidate class, requested k (already clamped to >= 0)
+  int64_t n_kept;
+  int grid;                      // CTAs of the sweep
+  const uint64_t* cand;          // [B][grid][kp]
+  const unsigned long long* tau; // [B]
+  QueryBuffers qb;
+  int64_t* out_idx; double* out_score; int64_t* out_count; uint32_t* out_flags;   // device
+  int* uncertified;              // device counter: queries that need the exact path
+};
+int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s);
+int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,
+                       const uint32_t* qbits, double* totals /*[n], masked rows = -NaN*/, cudaStream_t s);
+int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits,
+                      void* out /*dtype R or uint64*/, cudaStream_t s);
+int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
+               int64_t* out_idx, double* out_score, int64_t* out_count, void** scratch, size_t* scratch_bytes,
+               cudaStream_t s);
+int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, const double* scores, const int64_t* ids,
+                      const int64_t* counts, int64_t* out_idx, double* out_score, int64_t* out_count, cudaStream_t s);
+
+}  // namespace hdb

@@ -1,0 +1,439 @@
+// Fused score + select pass over one row shard (single query per launch): the replacement of
+//   metric_func(vectors, q)            hyperdb/ranking_algorithm.py:168 (np.dot / norm / sum over N x D)
+//   + recency_bias*exp(ts - max ts)    :179-186
+//   argpartition / argsort             :199-200
+// in ONE streaming read of the matrix.  HBM-bound: every row is read exactly once with 128-bit
+// coalesced ld.global.nc loads (8 rows in flight per warp), the query lives in shared memory in the
+// accumulate type, per-row scores are reduced with warp shuffles, and the epilogue (cosine norm,
+// time decay, row mask/range, NaN -> -inf) feeds a per-warp candidate list guarded by a grid-wide
+// threshold.  The N-length score vector is never written.  Output: per-CTA top-KP selection keys;
+// csrc/finalize.cu merges them, re-scores the KP candidates in the reference's exact arithmetic and
+// certifies the top-k (DESIGN.md "select then certify").
+#include "hdb_common.cuh"
+#include "hdb_internal.h"
+#include "../../include/hyperdb_b200.h"
+
+namespace hdb {
+
+constexpr int kRows = 8;              // rows per warp per group
+
+template <typename T> struct Store;
+template <> struct Store<__half> { using Acc = float; static constexpr int kPerVec = 8; };
+template <> struct Store<float>  { using Acc = float; static constexpr int kPerVec = 4; };
+template <> struct Store<double> { using Acc = double; static constexpr int kPerVec = 2; };
+
+struct SweepParams {
+  const char* rows;
+  int64_t n, d;
+  int64_t row_bytes;
+  int nvec;                 // 16-byte vectors per row (vector path) or elements per row (scalar path)
+  const void* qa;           // query in the accumulate type (global)
+  const void* inv_norms;    // accumulate type, or nullptr (not cosine)
+  RowFilter f;
+  uint64_t* cand;
+  unsigned long long* tau;
+  int metric;
+};
+
+__device__ __forceinline__ float abs_of(float x) { return fabsf(x); }
+__device__ __forceinline__ double abs_of(double x) { return fabs(x); }
+__device__ __forceinline__ float sqrt_of(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_of(double x) { return sqrt(x); }
+
+// MC: 0 = dot/cosine, 1 = squared L2, 2 = L1
+template <int MC, typename Acc>
+__device__ __forceinline__ void accum(Acc& a, Acc v, Acc q) {
+  if (MC == 0) {
+    a = fma(v, q, a);
+  } else if (MC == 1) {
+    Acc df = v - q;
+    a = fma(df, df, a);
+  } else {
+    a += abs_of(v - q);
+  }
+}
+
+template <int MC>
+__device__ __forceinline__ void accum_vec(float& a, const uint4& raw, const float* q, __half) {
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 v = __half22float2(h[i]);
+    accum<MC, float>(a, v.x, q[2 * i]);
+    accum<MC, float>(a, v.y, q[2 * i + 1]);
+  }
+}
+template <int MC>
+__device__ __forceinline__ void accum_vec(float& a, const uint4& raw, const float* q, float) {
+  const float* v = reinterpret_cast<const float*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) accum<MC, float>(a, v[i], q[i]);
+}
+template <int MC>
+__device__ __forceinline__ void accum_vec(double& a, const uint4& raw, const double* q, double) {
+  const double* v = reinterpret_cast<const double*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) accum<MC, double>(a, v[i], q[i]);
+}
+
+// 8 per-lane partial sums -> every lane holds the full sum of row ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
+template <typename Acc>
+__device__ __forceinline__ Acc reduce8(Acc (&acc)[kRows], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    Acc send = b4 ? acc[i] : acc[i + 4];
+    Acc keep = b4 ? acc[i + 4] : acc[i];
+    acc[i] = keep + __shfl_xor_sync(kFull, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    Acc send = b3 ? acc[i] : acc[i + 2];
+    Acc keep = b3 ? acc[i + 2] : acc[i];
+    acc[i] = keep + __shfl_xor_sync(kFull, send, 8);
+  }
+  {
+    Acc send = b2 ? acc[0] : acc[1];
+    Acc keep = b2 ? acc[1] : acc[0];
+    acc[0] = keep + __shfl_xor_sync(kFull, send, 4);
+  }
+  acc[0] += __shfl_xor_sync(kFull, acc[0], 2);
+  acc[0] += __shfl_xor_sync(kFull, acc[0], 1);
+  return acc[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-warp candidate list in shared memory (CAP = 4*KP... see kCap), guarded by thresholds.
+// ---------------------------------------------------------------------------------------------
+template <int KP> struct ListCfg { static constexpr int kCap = (KP <= 32) ? 128 : 2 * KP; };
+
+template <int KP>
+struct WarpList {
+  static constexpr int kCap = ListCfg<KP>::kCap;
+  uint64_t* buf;       // this warp's kCap slots
+  int cnt;
+  uint64_t tau;        // keys <= tau cannot be in the global top-KP
+
+  __device__ __forceinline__ void compact(int lane, unsigned long long* s_tau, unsigned long long* g_tau) {
+    for (int i = cnt + lane; i < kCap; i += 32) buf[i] = 0;
+    __syncwarp();
+    bitonic_desc(buf, kCap, lane, 32, [] { __syncwarp(); });
+    if (cnt >= KP) {
+      cnt = KP;
+      uint64_t mine = buf[KP - 1];
+      if (mine > tau) {
+        tau = mine;
+        if (lane == 0) {
+          atomicMax(s_tau, (unsigned long long)mine);
+          atomicMax(g_tau, (unsigned long long)mine);
+        }
+      }
+    }
+  }
+
+  // warp-collective: lanes with `pass` append their key
+  __device__ __forceinline__ void push(bool pass, uint64_t key, int lane, unsigned long long* s_tau,
+                                       unsigned long long* g_tau) {
+    unsigned m = __ballot_sync(kFull, pass);
+    if (m == 0) return;
+    if (pass) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
+    cnt += __popc(m);
+    __syncwarp();
+    // first fill: establish a threshold as soon as KP entries exist; later: only when nearly full
+    if (cnt > kCap - 32 || (tau == 0 && cnt >= KP)) compact(lane, s_tau, g_tau);
+  }
+};
+
+template <int KP>
+__device__ __forceinline__ void cta_merge_and_store(uint64_t* s_lists, WarpList<KP>& wl, int lane, int warp,
+                                                    unsigned long long* s_tau, unsigned long long* g_tau,
+                                                    uint64_t* cand_out) {
+  constexpr int kCap = ListCfg<KP>::kCap;
+  wl.compact(lane, s_tau, g_tau);
+  // keep at most KP per warp, zero the rest, then sort the CTA's kSweepWarps*kCap slots
+  for (int i = KP + lane; i < kCap; i += 32) wl.buf[i] = 0;
+  __syncthreads();
+  bitonic_desc(s_lists, kSweepWarps * kCap, (int)threadIdx.x, kSweepThreads, [] { __syncthreads(); });
+  for (int i = threadIdx.x; i < KP; i += kSweepThreads) cand_out[i] = s_lists[i];
+}
+
+__device__ __forceinline__ unsigned group_keep_mask(const RowFilter& f, int64_t row0, int64_t n) {
+  // 8 consecutive rows starting at a multiple of 8 share one mask word
+  unsigned bits = 0xffu;
+  if (f.mask) bits = (f.mask[row0 >> 5] >> (row0 & 31)) & 0xffu;
+  int64_t hi = f.hi < n ? f.hi : n;
+  if (row0 < f.lo) { int64_t s = f.lo - row0; bits = s >= 8 ? 0u : (bits & (0xffu << s)); }
+  if (row0 + 8 > hi) { int64_t keep = hi - row0; bits = keep <= 0 ? 0u : (bits & (0xffu >> (8 - keep))); }
+  return bits;
+}
+
+// ---------------------------------------------------------------------------------------------
+// float sweeps
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MC, int KP, bool VEC>
+__global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) {
+  using Acc = typename Store<T>::Acc;
+  constexpr int kPerVec = Store<T>::kPerVec;
+  constexpr int kCap = ListCfg<KP>::kCap;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* s_lists = reinterpret_cast<uint64_t*>(smem_raw);                       // [warps][kCap]
+  unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(s_lists + kSweepWarps * kCap);
+  Acc* s_q = reinterpret_cast<Acc*>(s_tau + 2);                                    // [d], 16-byte aligned
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) *s_tau = 0;
+  for (int64_t j = threadIdx.x; j < p.d; j += kSweepThreads) s_q[j] = reinterpret_cast<const Acc*>(p.qa)[j];
+  __syncthreads();
+
+  WarpList<KP> wl;
+  wl.buf = s_lists + warp * kCap;
+  wl.cnt = 0;
+  wl.tau = 0;
+
+  const int64_t ngroups = (p.n + kRows - 1) / kRows;
+  const int64_t wstride = (int64_t)gridDim.x * kSweepWarps;
+  const int my_row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const bool rep = (lane & 3) == 0;
+  const Acc* inv = reinterpret_cast<const Acc*>(p.inv_norms);
+  int since_refresh = 0;
+
+  for (int64_t g = (int64_t)blockIdx.x * kSweepWarps + warp; g < ngroups; g += wstride) {
+    const int64_t row0 = g * kRows;
+    const unsigned keep = group_keep_mask(p.f, row0, p.n);
+    if (keep == 0) continue;
+    // refresh the threshold from the CTA (cheap) and, now and then, from the grid
+    {
+      unsigned long long t = *reinterpret_cast<volatile unsigned long long*>(s_tau);
+      if (++since_refresh >= 16) {
+        since_refresh = 0;
+        unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(p.tau);
+        if (gt > t) { t = gt; if (lane == 0) atomicMax(s_tau, gt); }
+      }
+      if (t > wl.tau) wl.tau = t;
+    }
+    // per-row side inputs, issued before the streaming loop so their latency is hidden
+    const int64_t mrow = row0 + my_row;
+    const bool mine_kept = (keep >> my_row) & 1u;
+    Acc my_inv = Acc(1);
+    double my_decay = 0.0;
+    if (rep && mine_kept) {
+      if (inv) my_inv = inv[mrow];
+      if (p.f.decay) my_decay = p.f.decay[mrow];
+    }
+
+    Acc acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = Acc(0);
+    const char* base = p.rows + row0 * p.row_bytes;
+
+    if (VEC) {
+#pragma unroll 2
+      for (int c = lane; c < p.nvec; c += 32) {
+        uint4 raw[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if ((keep >> r) & 1u) raw[r] = ld_stream16(base + r * p.row_bytes + (int64_t)c * 16);
+          else raw[r] = make_uint4(0, 0, 0, 0);
+        }
+        Acc q[kPerVec];
+#pragma unroll
+        for (int i = 0; i < kPerVec; ++i) q[i] = s_q[c * kPerVec + i];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) accum_vec<MC>(acc[r], raw[r], q, T());
+      }
+    } else {
+      for (int c = lane; c < p.nvec; c += 32) {
+        const Acc q = s_q[c];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if ((keep >> r) & 1u) {
+            const T* rowp = reinterpret_cast<const T*>(base + r * p.row_bytes);
+            accum<MC, Acc>(acc[r], (Acc)rowp[c], q);
+          }
+        }
+      }
+    }
+
+    Acc total = reduce8(acc, lane);
+    // epilogue: similarity, decay, key
+    float score;
+    if (MC == 0) {
+      total = total * my_inv;
+      if (p.f.decay) score = (float)((double)total + p.f.bias * my_decay);
+      else score = (float)total;
+    } else {
+      Acc dist = (MC == 1) ? sqrt_of(total) : total;
+      Acc sim = Acc(1) / (Acc(1) + dist);
+      if (p.f.decay) score = (float)((double)sim + p.f.bias * my_decay);
+      else score = (float)sim;
+    }
+    const uint64_t key = make_key(score, (uint32_t)mrow);
+    wl.push(rep && mine_kept && key > wl.tau, key, lane, s_tau, p.tau);
+  }
+
+  cta_merge_and_store<KP>(s_lists, wl, lane, warp, s_tau, p.tau, p.cand + (int64_t)blockIdx.x * KP);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hamming sweep on the bit-packed matrix: words (multiple of 4) u32 per row = nvec 16-byte vectors.
+// LPR lanes share a row (LPR = smallest power of two >= nvec, capped at 32); score = D - popcount(xor).
+// ---------------------------------------------------------------------------------------------
+struct HammingParams {
+  const uint32_t* bits;
+  const uint32_t* qbits;
+  int64_t n, d;
+  int nvec, lpr;
+  RowFilter f;
+  uint64_t* cand;
+  unsigned long long* tau;
+};
+
+template <int KP>
+__global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_kernel(HammingParams p) {
+  constexpr int kCap = ListCfg<KP>::kCap;
+  constexpr int kPasses = 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* s_lists = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(s_lists + kSweepWarps * kCap);
+  uint4* s_q = reinterpret_cast<uint4*>(s_tau + 2);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) *s_tau = 0;
+  for (int j = threadIdx.x; j < p.nvec; j += kSweepThreads) s_q[j] = reinterpret_cast<const uint4*>(p.qbits)[j];
+  __syncthreads();
+
+  WarpList<KP> wl;
+  wl.buf = s_lists + warp * kCap;
+  wl.cnt = 0;
+  wl.tau = 0;
+
+  const int lpr = p.lpr, rpp = 32 / lpr;                // rows per pass
+  const int sub = lane % lpr, slot = lane / lpr;
+  const int64_t rows_per_group = (int64_t)rpp * kPasses;
+  const int64_t ngroups = (p.n + rows_per_group - 1) / rows_per_group;
+  const int64_t wstride = (int64_t)gridDim.x * kSweepWarps;
+  const int64_t hi = p.f.hi < p.n ? p.f.hi : p.n;
+  int since_refresh = 0;
+
+  for (int64_t g = (int64_t)blockIdx.x * kSweepWarps + warp; g < ngroups; g += wstride) {
+    {
+      unsigned long long t = *reinterpret_cast<volatile unsigned long long*>(s_tau);
+      if (++since_refresh >= 16) {
+        since_refresh = 0;
+        unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(p.tau);
+        if (gt > t) { t = gt; if (lane == 0) atomicMax(s_tau, gt); }
+      }
+      if (t > wl.tau) wl.tau = t;
+    }
+    const int64_t row0 = g * rows_per_group;
+    int diff[kPasses];
+    bool kept[kPasses];
+#pragma unroll
+    for (int r = 0; r < kPasses; ++r) {
+      const int64_t row = row0 + (int64_t)r * rpp + slot;
+      bool k = row >= p.f.lo && row < hi;
+      if (k && p.f.mask) k = (p.f.mask[row >> 5] >> (row & 31)) & 1u;
+      kept[r] = k;
+      int dsum = 0;
+      if (k) {
+        const uint4* rowp = reinterpret_cast<const uint4*>(p.bits) + row * p.nvec;
+        for (int c = sub; c < p.nvec; c += lpr) {
+          uint4 v = ld_stream16(rowp + c);
+          uint4 q = s_q[c];
+          dsum += __popc(v.x ^ q.x) + __popc(v.y ^ q.y) + __popc(v.z ^ q.z) + __popc(v.w ^ q.w);
+        }
+      }
+      diff[r] = dsum;
+    }
+#pragma unroll
+    for (int r = 0; r < kPasses; ++r) {
+      int dsum = diff[r];
+      for (int o = lpr >> 1; o; o >>= 1) dsum += __shfl_xor_sync(kFull, dsum, o);
+      const int64_t row = row0 + (int64_t)r * rpp + slot;
+      float score = (float)((int)p.d - dsum);
+      if (p.f.decay && kept[r] && sub == 0) score = (float)((double)score + p.f.bias * p.f.decay[row]);
+      const uint64_t key = make_key(score, (uint32_t)row);
+      wl.push(sub == 0 && kept[r] && key > wl.tau, key, lane, s_tau, p.tau);
+    }
+  }
+  cta_merge_and_store<KP>(s_lists, wl, lane, warp, s_tau, p.tau, p.cand + (int64_t)blockIdx.x * KP);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static size_t list_smem(int kp) { return (size_t)kSweepWarps * (kp <= 32 ? 128 : 2 * kp) * 8 + 16; }
+
+int sweep_grid_size(int device) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return sms * 2;                       // __launch_bounds__(256, 2): two CTAs resident per SM
+}
+
+template <typename T, int MC, int KP, bool VEC>
+static int launch_one(const SweepParams& p, int grid, size_t smem, cudaStream_t s) {
+  auto kern = sweep_kernel<T, MC, KP, VEC>;
+  if (smem > 48 * 1024) HDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kSweepThreads, smem, s>>>(p);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T, int MC, int KP>
+static int launch_vec(const SweepParams& p, bool vec, int grid, size_t smem, cudaStream_t s) {
+  return vec ? launch_one<T, MC, KP, true>(p, grid, smem, s) : launch_one<T, MC, KP, false>(p, grid, smem, s);
+}
+template <typename T, int MC>
+static int launch_kp(const SweepParams& p, bool vec, int kp, int grid, size_t smem, cudaStream_t s) {
+  return kp <= 32 ? launch_vec<T, MC, 32>(p, vec, grid, smem, s) : launch_vec<T, MC, 128>(p, vec, grid, smem, s);
+}
+template <typename T>
+static int launch_mc(const SweepParams& p, bool vec, int mc, int kp, int grid, size_t smem, cudaStream_t s) {
+  if (mc == 0) return launch_kp<T, 0>(p, vec, kp, grid, smem, s);
+  if (mc == 1) return launch_kp<T, 1>(p, vec, kp, grid, smem, s);
+  return launch_kp<T, 2>(p, vec, kp, grid, smem, s);
+}
+
+int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const RowFilter& f, int kp,
+                 const SweepOut& out, cudaStream_t s) {
+  if (m.n >= (int64_t(1) << 32)) return fail("sweep: more than 2^32 rows per shard");
+  if (kp != 32 && kp != 128) return fail("sweep: unsupported candidate class");
+  if (metric == HDB_HAMMING) {
+    HammingParams hp;
+    hp.bits = m.bits; hp.qbits = qbits; hp.n = m.n; hp.d = m.d;
+    hp.nvec = m.words / 4;
+    int lpr = 1;
+    while (lpr < hp.nvec && lpr < 32) lpr <<= 1;
+    hp.lpr = lpr;
+    hp.f = f; hp.cand = out.cand; hp.tau = out.tau;
+    size_t smem = list_smem(kp) + (size_t)hp.nvec * 16;
+    if (smem > 200 * 1024) return fail("sweep: dimension too large for the fused hamming pass");
+    if (kp <= 32) {
+      if (smem > 48 * 1024) HDB_CUDA(cudaFuncSetAttribute(sweep_hamming_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sweep_hamming_kernel<32><<<out.grid, kSweepThreads, smem, s>>>(hp);
+    } else {
+      if (smem > 48 * 1024) HDB_CUDA(cudaFuncSetAttribute(sweep_hamming_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sweep_hamming_kernel<128><<<out.grid, kSweepThreads, smem, s>>>(hp);
+    }
+    HDB_LAUNCHED();
+    HDB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  SweepParams p;
+  p.rows = reinterpret_cast<const char*>(m.rows);
+  p.n = m.n; p.d = m.d;
+  p.row_bytes = m.d * dtype_size(m.dtype);
+  const bool vec = (p.row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(m.rows) & 15) == 0);
+  p.nvec = vec ? (int)(p.row_bytes / 16) : (int)m.d;
+  p.qa = qa;
+  p.inv_norms = (metric == HDB_COSINE) ? m.inv_norms : nullptr;
+  p.f = f; p.cand = out.cand; p.tau = out.tau; p.metric = metric;
+  const int mc = (metric == HDB_DOT || metric == HDB_COSINE) ? 0 : (metric == HDB_EUCLIDEAN ? 1 : 2);
+  size_t smem = list_smem(kp) + (size_t)m.d * (m.dtype == 2 ? 8 : 4);
+  if (smem > 200 * 1024) return fail("sweep: dimension too large for the fused pass");
+  if (m.dtype == 0) return launch_mc<__half>(p, vec, mc, kp, out.grid, smem, s);
+  if (m.dtype == 1) return launch_mc<float>(p, vec, mc, kp, out.grid, smem, s);
+  return launch_mc<double>(p, vec, mc, kp, out.grid, smem, s);
+}
+
+}  // namespace hdb

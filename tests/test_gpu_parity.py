@@ -1,0 +1,215 @@
+"""Parity of the CUDA path (through the C ABI, via the drop-in module) against the oracle and the
+committed outputs of the real reference.  Bar (north_star): top-k indices identical with ties to the
+lower index; scores bit-equal where NumPy's arithmetic is deterministic (all float16 metrics,
+euclidean/manhattan/hamming in every dtype), else within rel 1e-5 (fp32) / 1e-12 (fp64)."""
+import numpy as np
+import pytest
+
+import golden_io as G
+from oracle import canonical as K
+from oracle import reference_port as P
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = G.load_sort_golden()
+TOL = {"float16": 1e-3, "float32": 1e-5, "float64": 1e-12, "uint64": 0}
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hyperdb_b200
+    return hyperdb_b200
+
+
+def exact_expected(metric, dtype):
+    return dtype == "float16" or metric in ("euclidean_metric", "manhattan_distance", "hamming_distance")
+
+
+def check_against_oracle(V, q, ts, bias, k, metric, idx, sc, keep=None):
+    """idx/sc from the CUDA path vs the canonical oracle (same arithmetic spec)."""
+    oi, os_ = K.rank(V, q, k, metric, ts, bias, keep)
+    rdt = str(np.promote_types(np.asarray(V).dtype if np.asarray(V).dtype.kind == "f" else np.float64,
+                               np.asarray(q).dtype if np.asarray(q).dtype.kind == "f" else np.float64))
+    assert len(idx) == len(oi)
+    if exact_expected(metric, rdt):
+        assert list(idx) == list(oi)
+        if ts is None:
+            assert np.array_equal(sc, os_)
+        else:
+            np.testing.assert_allclose(sc, os_, rtol=1e-14)       # exp() of CUDA vs NumPy: <= 1 ulp apart
+    else:
+        np.testing.assert_allclose(sc, os_, rtol=TOL[rdt], atol=TOL[rdt] * 1e-3)
+        full = K.total_scores(V, q, metric, ts, bias, keep)
+        for mine, theirs in zip(idx, oi):
+            if mine != theirs:      # only acceptable as a certified tolerance-tie
+                assert abs(full[mine] - full[theirs]) <= TOL[rdt] * max(1.0, abs(full[theirs]))
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["auto", "exact-path"])
+@pytest.mark.parametrize("entry", GOLDEN, ids=[G.case_id(e[0]) for e in GOLDEN])
+def test_sort_golden(hb, entry, mode):
+    case, ref_sims, ref_idx, ref_sc = entry
+    V, q, ts = G.inputs(case)
+    bias = case["bias"] if ts is not None else 0
+    hb.ranking_algorithm.set_path_mode(mode)
+    try:
+        idx, sc = hb.hyperDB_ranking_algorithm_sort(V, q, top_k=case["k"], metric=case["metric"], timestamps=ts, recency_bias=bias)
+    finally:
+        hb.ranking_algorithm.set_path_mode(0)
+    if case["k"] <= 0:
+        assert idx == [] and sc == []
+        return
+    idx, sc = np.asarray(idx), np.asarray(sc, float).reshape(-1)
+    check_against_oracle(V, q, ts, bias, case["k"], case["metric"], idx, sc)
+    # and against what the REAL reference returned (tests/golden/sort_golden.npz)
+    dt = str(ref_sims.dtype)
+    assert len(idx) == len(ref_idx)
+    if exact_expected(case["metric"], dt) and ts is None:
+        assert np.array_equal(sc, ref_sc)
+    else:
+        np.testing.assert_allclose(sc, ref_sc, rtol=max(TOL[dt], 1e-13) * 10, atol=TOL[dt] * 1e-2)
+
+
+METRIC_FN = {"dot_product": "dot_product", "cosine_similarity": "cosine_similarity", "euclidean_metric": "euclidean_metric",
+             "manhattan_distance": "manhattan_distance", "hamming_distance": "hamming_distance"}
+
+
+@pytest.mark.parametrize("entry", GOLDEN[::3], ids=[G.case_id(e[0]) for e in GOLDEN[::3]])
+def test_metric_functions_golden(hb, entry):
+    case, ref_sims, _, _ = entry
+    V, q, _ts = G.inputs(case)
+    V0, q0 = V.copy(), q.copy()
+    out = getattr(hb, METRIC_FN[case["metric"]])(V, q)
+    assert np.array_equal(V, V0) and np.array_equal(q, q0)        # no in-place binarisation (quirk 9)
+    dt = str(ref_sims.dtype)
+    assert str(out.dtype) == dt and out.shape == ref_sims.reshape(-1).shape
+    if exact_expected(case["metric"], dt):
+        assert out.tobytes() == ref_sims.reshape(-1).tobytes()
+    else:
+        a, b = out.astype(float), ref_sims.reshape(-1).astype(float)
+        cond = np.ones(len(b)) if case["metric"] == "cosine_similarity" else \
+            np.linalg.norm(V.astype(float), axis=1) * np.linalg.norm(q.astype(float))
+        assert np.all(np.abs(a - b) <= TOL[dt] * np.maximum(np.abs(b), cond))
+
+
+def test_get_norm_vector(hb):
+    rng = np.random.default_rng(11)
+    for dt in (np.float16, np.float32, np.float64):
+        x = (rng.standard_normal((40, 77)) * 3).astype(dt)
+        x[5] = 0
+        assert hb.get_norm_vector(x).tobytes() == P.unit_rows(x).tobytes()
+        assert hb.get_norm_vector(x[3]).tobytes() == P.unit_rows(x[3]).tobytes()
+
+
+# ---- the reference's own KATs against the drop-in (tests/test_ranking_algorithm.py of the reference) ------
+def test_reference_kats_on_gpu(hb):
+    r = hb.euclidean_metric(np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]]), np.array([1, 1, 1]))
+    assert r.shape == (3,) and np.all(r > 0)
+    with pytest.raises(ValueError):
+        hb.euclidean_metric(np.array([]), np.array([]))
+    assert np.array_equal(hb.cosine_similarity(np.array([[1, 0], [0, 1]]), np.array([1, 0])), [1.0, 0.0])
+    assert np.allclose(hb.manhattan_distance(np.array([[1, 0], [0, 1]]), np.array([1, 0])), [1.0, 1 / 3])
+    assert np.array_equal(hb.hamming_distance(np.array([[1, 1], [0, 1], [1, 0]]), np.array([1, 1])), [2, 1, 1])
+    V = np.array([[1, 0], [0, 1], [0.5, 0.5]])
+    q = np.array([1, 0])
+    ts = [1627825200.0, 1627911600.0, 1627998000.0]
+    table = [("cosine_similarity", 0, [0, 2, 1]), ("cosine_similarity", 1, [2, 0, 1]), ("euclidean_metric", 0, [0, 2, 1]),
+             ("manhattan_distance", 0, [0, 2, 1]), ("hamming_distance", 0, [0, 2, 1])]
+    for metric, bias, want in table:
+        idx, _ = hb.hyperDB_ranking_algorithm_sort(V, q, metric=metric, timestamps=ts, recency_bias=bias)
+        assert list(idx) == want, metric
+        idx, _ = hb.custom_ranking_algorithm_sort(V, q, metric=metric, timestamps=ts, recency_bias=bias)
+        assert list(idx) == want, metric
+    with pytest.raises(ValueError):
+        hb.hyperDB_ranking_algorithm_sort(np.array([[1, 0], [0, 1]]), np.array([1, 0]), metric="unknown_metric")
+    with pytest.raises(ValueError):
+        hb.hyperDB_ranking_algorithm_sort(np.array([1, 0]), np.array([1, 0]), metric="euclidean_metric")
+    with pytest.raises(ValueError):
+        hb.hyperDB_ranking_algorithm_sort(np.array([[1, 0], [0, 1], [np.nan, np.nan]]), np.array([1, 0]))
+    with pytest.raises(ValueError):
+        hb.hyperDB_ranking_algorithm_sort(np.array([[1, 0], [0, 1]]), np.array([np.nan, 0]))
+
+
+def test_edge_quirks_on_gpu(hb, capsys):
+    V = np.eye(5)
+    assert len(hb.hyperDB_ranking_algorithm_sort(V, V[0], 50)[0]) == 5
+    assert hb.hyperDB_ranking_algorithm_sort(V, V[0], 0) == ([], [])
+    assert hb.hyperDB_ranking_algorithm_sort(V, V[0], -1) == ([], [])
+    i, s = hb.hyperDB_ranking_algorithm_sort(V[:1], V[0], 3)
+    assert list(i) == [0] and np.asarray(s).shape == (1, 1) and s[0, 0] == 1.0
+    assert "Only one document left" in capsys.readouterr().out
+    # list of row arrays (what the filters hand over, hyperdb/hyperdb.py:1305)
+    rows = [np.array([1.0, 0.0]), np.array([0.0, 1.0]), np.array([0.5, 0.5])]
+    i, _ = hb.hyperDB_ranking_algorithm_sort(rows, np.array([1.0, 0.0]), timestamps=[1.0, 2.0, 3.0], recency_bias=0)
+    assert list(i) == [0, 2, 1]
+
+
+def test_pokemon_c1(hb):
+    z = G.load_pokemon()
+    V32 = z["vectors"]
+    V64 = V32.astype(np.float64)
+    for row in (0, 25, 77, 150):
+        for tag, V, q in (("f32", V32, V32[row]), ("f64", V64, V64[row]), ("mixed", V64, V32[row])):
+            i, s = hb.hyperDB_ranking_algorithm_sort(V, q, top_k=5, metric="cosine_similarity")
+            assert list(i) == list(z[f"idx_{tag}_{row}"])
+            np.testing.assert_allclose(s, z[f"sc_{tag}_{row}"], rtol=1e-5 if tag == "f32" else 1e-12)
+
+
+# ---- fused sweep == exact path on larger inputs; certification statistics ----------------------------------
+SWEEP_CASES = [(dt, m, n, d, kind) for dt in ("f16", "f32", "f64")
+               for m in ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance")
+               for (n, d, kind) in ((20000, 96, "unit"), (50021, 200, "scaled"), (30000, 33, "coarse"))]
+
+
+@pytest.mark.parametrize("vdt,metric,n,d,kind", SWEEP_CASES)
+def test_fused_equals_exact(hb, vdt, metric, n, d, kind):
+    import cases as C
+    import zlib
+    case = dict(seed=zlib.crc32(f"{vdt}{metric}{n}{d}".encode()) % 100000, n=n, d=d, vdt=vdt, qdt=vdt, kind=kind, ts=True, ts_span=10.0)
+    V, q, ts = C.make_inputs(case)
+    m = hb.DeviceMatrix(V)
+    rng = np.random.default_rng(1)
+    keep = rng.random(n) < 0.6
+    fallbacks = 0
+    try:
+        for (k, use_ts, use_mask) in ((10, False, False), (100, False, False), (16, True, False), (10, False, True), (7, True, True)):
+            m.set_mask(keep if use_mask else None)
+            m.set_timestamps(ts if use_ts else None)
+            if use_ts:
+                m.refresh_decay()
+            bias = 0.4 if use_ts else 0.0
+            m.set_path(1)
+            ei, es, ec, _ = m.query(q, k, metric, bias)
+            m.set_path(0)
+            fi, fs, fc, ff = m.query(q, k, metric, bias)
+            fallbacks += int(ff[0] & 1)
+            assert ec[0] == fc[0] == min(k, int(keep.sum()) if use_mask else n)
+            assert list(fi[0]) == list(ei[0]), (k, use_ts, use_mask)
+            assert np.array_equal(fs[0], es[0])
+            if k == 10:      # and the exact path itself against the oracle
+                check_against_oracle(V, q, ts if use_ts else None, bias, k, metric, ei[0], es[0], keep if use_mask else None)
+    finally:
+        m.close()
+    if kind == "unit":
+        assert fallbacks == 0, "fused pass should certify on well-separated data"
+
+
+def test_range_and_batch(hb):
+    rng = np.random.default_rng(5)
+    V = rng.standard_normal((5000, 64)).astype(np.float32)
+    Q = rng.standard_normal((9, 64)).astype(np.float32)
+    m = hb.DeviceMatrix(V)
+    try:
+        m.set_range(100, 4321)
+        keep = np.zeros(5000, bool)
+        keep[100:4321] = True
+        idx, sc, cnt, _ = m.query(Q, 10, "cosine_similarity")
+        for b in range(len(Q)):
+            check_against_oracle(V, Q[b], None, 0.0, 10, "cosine_similarity", idx[b], sc[b], keep)
+        m.set_range(0, 5000)
+        idx, sc, cnt, _ = m.query(Q, 5000, "euclidean_metric")        # k = N: exact path
+        assert cnt.tolist() == [5000] * 9
+        oi, os_ = K.rank(V, Q[3], 5000, "euclidean_metric")
+        assert list(idx[3]) == list(oi) and np.array_equal(sc[3], os_)
+    finally:
+        m.close()
