@@ -122,6 +122,13 @@ int64_t hdb_launch_count(int reset);
  * what: 0 = the whole device-side query (prep + select + certify), 1 = the dominant kernel only
  * (the streaming sweep, or the batched contraction). */
 int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter);
+/* Per-launch timing of the dominant kernel INSIDE normal hdb_query calls: after
+ * hdb_profile_enable(m, max_pairs) every launch of the streaming sweep (or batched contraction) is
+ * bracketed by a CUDA event pair on the handle's stream (up to max_pairs; 0 disables);
+ * hdb_profile_read synchronises, returns the number of recorded launches and the sum of their
+ * durations in milliseconds, and resets the recorder. */
+int hdb_profile_enable(hdb_matrix* m, int max_pairs);
+int hdb_profile_read(hdb_matrix* m, int* n_launches, float* total_ms);
 /* Force a path for testing: 0 = automatic, 1 = always the exact full-vector path,
  * 2 = fused sweep only (fail instead of falling back), 3 = tensor-core batched path when eligible. */
 int hdb_matrix_set_path(hdb_matrix* m, int mode);

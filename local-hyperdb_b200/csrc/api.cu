@@ -55,6 +55,9 @@ struct hdb_matrix {
   void* sort_scratch = nullptr; size_t sort_scratch_bytes = 0;
   unsigned long long* misc = nullptr;   // [2] ordered max bits, count
   float* stats = nullptr; int* nan_flag = nullptr;
+  // per-launch event pairs around the dominant kernel (hdb_profile_*)
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
   // last query (for hdb_time_last_query)
   struct { bool valid = false; int metric = 0, rdt = 0, kp = 0; int64_t nq = 0, k = 0; double bias = 0; } last;
 };
@@ -136,6 +139,7 @@ int hdb_matrix_destroy(hdb_matrix* m) {
                   m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_idx, m->o_score, m->o_count,
                   m->o_flags, m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   delete m;
   return 0;
 }
@@ -348,7 +352,10 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
     so.grid = m->grid;
     const void* qa = reinterpret_cast<const char*>(m->qb.qa) + (size_t)(b0 + i) * m->d * elt;
     const uint32_t* qbits = m->qb.qbits + (size_t)(b0 + i) * m->words;
+    const bool prof = m->prof_used + 2 <= m->prof_ev.size();
+    if (prof) HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used], m->stream));
     HDB_TRY(launch_sweep(v, metric, qa, qbits, f, kp, so, m->stream));
+    if (prof) { HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used + 1], m->stream)); m->prof_used += 2; }
   }
   FinalizeArgs a;
   a.m = v; a.f = f; a.metric = metric; a.rdt = rdt; a.kp = kp; a.k = (int)k; a.n_kept = m->n_kept; a.grid = m->grid;
@@ -444,6 +451,36 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   HDB_CUDA(cudaMemcpyAsync(out_count, count, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
   HDB_CUDA(cudaStreamSynchronize(m->stream));
   if (out_flags) memcpy(out_flags, hflags.data(), (size_t)nq * 4);
+  return 0;
+}
+
+int hdb_profile_enable(hdb_matrix* m, int max_pairs) {
+  if (!m) return fail("null handle");
+  HDB_CUDA(cudaSetDevice(m->device));
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  m->prof_ev.clear();
+  m->prof_used = 0;
+  for (int i = 0; i < 2 * max_pairs; ++i) {
+    cudaEvent_t e;
+    HDB_CUDA(cudaEventCreate(&e));
+    m->prof_ev.push_back(e);
+  }
+  return 0;
+}
+
+int hdb_profile_read(hdb_matrix* m, int* n_launches, float* total_ms) {
+  if (!m || !n_launches || !total_ms) return fail("null argument");
+  HDB_CUDA(cudaSetDevice(m->device));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  float sum = 0.f;
+  for (size_t i = 0; i + 1 < m->prof_used; i += 2) {
+    float ms = 0.f;
+    HDB_CUDA(cudaEventElapsedTime(&ms, m->prof_ev[i], m->prof_ev[i + 1]));
+    sum += ms;
+  }
+  *n_launches = (int)(m->prof_used / 2);
+  *total_ms = sum;
+  m->prof_used = 0;
   return 0;
 }
 

@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   __shared__ double o_tot[kMaxKP];
   __shared__ uint32_t o_row[kMaxKP];
   __shared__ int s_count;
+  __shared__ unsigned s_hist[256];
+  __shared__ int s_sel[3];
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
   const int kk = (int)((int64_t)a.k < a.n_kept ? (int64_t)a.k : a.n_kept);
@@ -82,14 +84,51 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     }
   }
   __syncthreads();
-  const int found = s_count;
-  if (found > kSurvCap) {          // pathological tie plateau: hand the query to the exact path
-    if (tid == 0) {
-      a.out_count[b] = kk;
-      if (a.out_flags) a.out_flags[b] = qflag | kFlagUncertified;
-      atomicAdd(a.uncertified, 1);
+  int found = s_count;
+  if (found > kSurvCap) {
+    // No useful threshold was established (small shard: every warp saw fewer than KP rows).  Radix-select
+    // the KP-th largest key over all per-CTA candidates, 8 bits per pass, until the survivors fit.
+    unsigned long long prefix = 0, pmask = 0;
+    int need = a.kp;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += kFinThreads) s_hist[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < total; i += kFinThreads) {
+        const uint64_t key = cand[i];
+        if (key != 0 && (key & pmask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, chosen = 0;
+        for (int bin = 255; bin >= 0; --bin) {
+          const int c = (int)s_hist[bin];
+          if (cum + c >= need) { chosen = bin; break; }
+          if (bin > 0) cum += c;
+        }
+        need -= cum;
+        s_sel[0] = chosen;
+        s_sel[1] = need;
+        s_sel[2] = ((a.kp - need) + (int)s_hist[chosen] <= kSurvCap) ? 1 : 0;
+      }
+      __syncthreads();
+      prefix |= (unsigned long long)s_sel[0] << shift;
+      pmask |= 0xffull << shift;
+      need = s_sel[1];
+      const int done = s_sel[2];
+      __syncthreads();
+      if (done) break;
     }
-    return;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int i = tid; i < total; i += kFinThreads) {
+      const uint64_t key = cand[i];
+      if (key != 0 && key >= prefix) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < kSurvCap) surv[pos] = key;
+      }
+    }
+    __syncthreads();
+    found = s_count < kSurvCap ? s_count : kSurvCap;
   }
   int pow2 = 32;
   while (pow2 < found) pow2 <<= 1;

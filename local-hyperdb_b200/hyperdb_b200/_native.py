@@ -48,6 +48,8 @@ SIGNATURES = {
     "hdb_launch_count": (C.c_int64, [C.c_int]),
     "hdb_time_last_query": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "hdb_matrix_set_path": (C.c_int, [vp, C.c_int]),
+    "hdb_profile_enable": (C.c_int, [vp, C.c_int]),
+    "hdb_profile_read": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
 }
 
 

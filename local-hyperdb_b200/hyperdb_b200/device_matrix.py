@@ -228,3 +228,12 @@ class DeviceMatrix:
         ms = C.c_float()
         N.check(N.lib().hdb_time_last_query(self._h, int(what), int(iters), C.byref(ms)))
         return ms.value
+
+    def profile_enable(self, max_pairs):
+        N.check(N.lib().hdb_profile_enable(self._h, int(max_pairs)))
+
+    def profile_read(self):
+        """(launches of the dominant kernel recorded since the last read, their summed duration in ms)."""
+        n, ms = C.c_int(), C.c_float()
+        N.check(N.lib().hdb_profile_read(self._h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
