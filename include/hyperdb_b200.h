@@ -108,9 +108,12 @@ int hdb_normalize_rows(int device, int dtype, int64_t n_rows, int64_t dim, const
                        void* dst, int dst_space);
 
 /* ---- multi-GPU: final merge of the all-gathered per-shard candidates --- */
-/* n_lists lists of `k` (score, global id) records per query, laid out [list][query][k], with counts
- * [list][query]; writes the merged top-k per query ordered by (score desc, id asc). */
-int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t n_queries, int64_t k,
+/* n_lists candidate lists (one per shard) for nq queries: list l has scores at scores + l*list_stride
+ * laid out [query][k], ids at ids + l*list_stride, counts at counts + l*list_stride laid out [query]
+ * (strides in 8-byte elements; list_stride = 0 means dense arrays [list][query][k] / [list][query]).
+ * The strided form lets one all-gathered buffer [list][scores | ids | counts ...] be merged in place.
+ * Writes the merged top-k per query ordered by (score desc, id asc). */
+int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t n_queries, int64_t k, int64_t list_stride,
                    const double* scores, const int64_t* ids, const int64_t* counts, int in_space,
                    int64_t* out_idx, double* out_score, int64_t* out_count, int out_space);
 

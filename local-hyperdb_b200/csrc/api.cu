@@ -592,13 +592,16 @@ int hdb_normalize_rows(int device, int dtype, int64_t n_rows, int64_t dim, const
   return rc;
 }
 
-int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t nq, int64_t k, const double* scores,
+int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t nq, int64_t k, int64_t list_stride, const double* scores,
                    const int64_t* ids, const int64_t* counts, int in_space, int64_t* out_idx, double* out_score,
                    int64_t* out_count, int out_space) {
   if (n_lists <= 0 || nq < 0 || k < 0) return fail("hdb_merge_topk: bad sizes");
   if (nq == 0) return 0;
   HDB_CUDA(cudaSetDevice(device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (list_stride != 0 && in_space != HDB_DEVICE) return fail("hdb_merge_topk: strided input must be device memory");
+  const int64_t ls_rec = list_stride ? list_stride : nq * k;
+  const int64_t ls_cnt = list_stride ? list_stride : nq;
   const size_t rec = (size_t)n_lists * nq * (k ? k : 1);
   std::vector<void*> tmp;
   auto stage_in = [&](const void* p, size_t bytes, const void** out) -> int {
@@ -626,7 +629,7 @@ int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t nq, i
       oc = reinterpret_cast<int64_t*>(os + nq * (k ? k : 1));
     }
   }
-  if (!rc) rc = launch_merge_topk(n_lists, nq, k, (const double*)ds, (const int64_t*)di, (const int64_t*)dc, oi, os, oc, s);
+  if (!rc) rc = launch_merge_topk(n_lists, nq, k, ls_rec, ls_cnt, (const double*)ds, (const int64_t*)di, (const int64_t*)dc, oi, os, oc, s);
   if (!rc && out_space == HDB_HOST) {
     cudaError_t e = cudaSuccess;
     if (k) e = cudaMemcpyAsync(out_idx, oi, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s);

@@ -319,12 +319,12 @@ int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, 
 // multi-GPU final merge: n_lists x k records per query -> top-k by (score desc, id asc).
 // One CTA per query; rank by counting (n_lists*k is at most a few thousand records).
 // ---------------------------------------------------------------------------------------------
-__global__ void merge_topk_kernel(int64_t n_lists, int64_t nq, int64_t k, const double* scores, const int64_t* ids,
+__global__ void merge_topk_kernel(int64_t n_lists, int64_t nq, int64_t k, int64_t ls_rec, int64_t ls_cnt, const double* scores, const int64_t* ids,
                                   const int64_t* counts, int64_t* out_idx, double* out_score, int64_t* out_count) {
   const int64_t b = blockIdx.x;
   const int64_t total = n_lists * k;
   int64_t have = 0;
-  for (int64_t l = 0; l < n_lists; ++l) have += counts[l * nq + b];
+  for (int64_t l = 0; l < n_lists; ++l) have += counts[l * ls_cnt + b];
   const int64_t kk = have < k ? have : k;
   for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
     out_idx[b * k + i] = -1;
@@ -333,14 +333,14 @@ __global__ void merge_topk_kernel(int64_t n_lists, int64_t nq, int64_t k, const 
   __syncthreads();
   for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
     const int64_t l = e / k, j = e % k;
-    if (j >= counts[l * nq + b]) continue;
-    const double t = scores[(l * nq + b) * k + j];
-    const int64_t r = ids[(l * nq + b) * k + j];
+    if (j >= counts[l * ls_cnt + b]) continue;
+    const double t = scores[l * ls_rec + b * k + j];
+    const int64_t r = ids[l * ls_rec + b * k + j];
     int64_t rank = 0;
     for (int64_t l2 = 0; l2 < n_lists && rank < kk; ++l2) {
-      const int64_t c2 = counts[l2 * nq + b];
-      const double* s2 = scores + (l2 * nq + b) * k;
-      const int64_t* i2 = ids + (l2 * nq + b) * k;
+      const int64_t c2 = counts[l2 * ls_cnt + b];
+      const double* s2 = scores + l2 * ls_rec + b * k;
+      const int64_t* i2 = ids + l2 * ls_rec + b * k;
       for (int64_t j2 = 0; j2 < c2; ++j2) {
         const double t2 = s2[j2];
         if (t2 > t || (t2 == t && i2[j2] < r)) ++rank;
@@ -352,10 +352,10 @@ __global__ void merge_topk_kernel(int64_t n_lists, int64_t nq, int64_t k, const 
   if (threadIdx.x == 0) out_count[b] = kk;
 }
 
-int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, const double* scores, const int64_t* ids,
+int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, int64_t ls_rec, int64_t ls_cnt, const double* scores, const int64_t* ids,
                       const int64_t* counts, int64_t* out_idx, double* out_score, int64_t* out_count, cudaStream_t s) {
   if (nq == 0) return 0;
-  merge_topk_kernel<<<(unsigned)nq, 256, 0, s>>>(n_lists, nq, k, scores, ids, counts, out_idx, out_score, out_count);
+  merge_topk_kernel<<<(unsigned)nq, 256, 0, s>>>(n_lists, nq, k, ls_rec, ls_cnt, scores, ids, counts, out_idx, out_score, out_count);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;

@@ -101,7 +101,7 @@ int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc
 int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
                int64_t* out_idx, double* out_score, int64_t* out_count, void** scratch, size_t* scratch_bytes,
                cudaStream_t s);
-int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, const double* scores, const int64_t* ids,
+int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, int64_t ls_rec, int64_t ls_cnt, const double* scores, const int64_t* ids,
                       const int64_t* counts, int64_t* out_idx, double* out_score, int64_t* out_count, cudaStream_t s);
 
 }  // namespace hdb

@@ -44,7 +44,7 @@ SIGNATURES = {
     "hdb_query": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, i64, i64, C.c_double, vp, vp, vp, vp, C.c_int]),
     "hdb_scores": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]),
     "hdb_normalize_rows": (C.c_int, [C.c_int, C.c_int, i64, i64, vp, C.c_int, vp, C.c_int]),
-    "hdb_merge_topk": (C.c_int, [C.c_int, vp, i64, i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]),
+    "hdb_merge_topk": (C.c_int, [C.c_int, vp, i64, i64, i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]),
     "hdb_launch_count": (C.c_int64, [C.c_int]),
     "hdb_time_last_query": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "hdb_matrix_set_path": (C.c_int, [vp, C.c_int]),

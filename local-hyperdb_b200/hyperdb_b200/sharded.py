@@ -1,0 +1,143 @@
+"""Row-sharded ranking over the GPUs of one box: one process per GPU (torch.distributed / NCCL over
+NVLink 5), rank r holds the contiguous row block [r*N/G, (r+1)*N/G) in a DeviceMatrix.
+
+Per query batch: every rank runs the fused sweep + certify on its shard and emits its local top-k as
+(float64 score, GLOBAL row id); ONE exchange step -- an all-gather of 2*B*k + 2*B 8-byte words per
+rank -- and a final G*k -> k merge with the same (score desc, id asc) key.  Contiguous shards + global
+ids keep the lower-index tie rule exact across shards.  The only other cross-shard dependency is the
+time-decay reference max(ts) over kept rows (hyperdb/hyperdb.py:1334-1344): an 8-byte all-reduce(MAX)
+whenever timestamps or the row subset change.
+
+The compute engine is injectable so the host logic (bounds, packing, exchange, flag handling) is
+covered by world_size-2 gloo tests on CPU with a test-side engine; the product engine is CudaEngine
+(no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _native as N
+
+
+def shard_bounds(n_total: int, world: int, rank: int):
+    """Contiguous, balanced: the first n_total % world shards get one extra row."""
+    base, extra = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def packed_len(b: int, k: int) -> int:
+    """Words (int64) of one rank's message: scores[b*k] | ids[b*k] | counts[b] | flags[b]."""
+    return 2 * b * k + 2 * b
+
+
+class CudaEngine:
+    """Local shard on the current CUDA device, results kept on the device."""
+
+    def __init__(self, matrix):
+        import torch
+        self.m = matrix
+        self.torch = torch
+        self.device = torch.device("cuda", matrix.device)
+
+    def kept_ts_max(self):
+        return self.m.kept_ts_max()
+
+    def set_decay_reference(self, ts_max):
+        self.m.set_decay_reference(ts_max)
+
+    def n_kept(self):
+        return self.m.n_kept
+
+    def local_topk(self, queries, k, metric, bias, exact=False):
+        """-> packed int64 CUDA tensor [packed_len(B, k)] (scores bit-cast)."""
+        torch = self.torch
+        q = queries if torch.is_tensor(queries) else torch.as_tensor(queries)
+        q = q.to(self.device).contiguous()
+        b = 1 if q.dim() == 1 else q.shape[0]
+        buf = torch.empty(packed_len(b, k), dtype=torch.int64, device=self.device)
+        sc = buf[: b * k].view(torch.float64)
+        ids = buf[b * k: 2 * b * k]
+        cnt = buf[2 * b * k: 2 * b * k + b]
+        flags64 = buf[2 * b * k + b:]
+        flags = torch.zeros(b, dtype=torch.int32, device=self.device)
+        self.m.set_path(1 if exact else 0)
+        try:
+            self.m.query_device(q, k, metric, bias, ids, sc, cnt, flags)
+        finally:
+            self.m.set_path(0)
+        flags64.copy_(flags)
+        return buf
+
+    def merge(self, gathered, b, k):
+        """gathered: int64 CUDA tensor [G, packed_len]; -> (idx [b,k], score [b,k], count [b], any_uncertified tensor)."""
+        torch = self.torch
+        g, ln = gathered.shape
+        idx = torch.empty((b, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((b, k), dtype=torch.float64, device=self.device)
+        cnt = torch.empty(b, dtype=torch.int64, device=self.device)
+        base = gathered.data_ptr()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(N.lib().hdb_merge_topk(self.device.index, C.c_void_p(stream), g, b, k, ln,
+                                       C.c_void_p(base), C.c_void_p(base + 8 * b * k), C.c_void_p(base + 16 * b * k),
+                                       N.HDB_DEVICE, C.c_void_p(idx.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                       C.c_void_p(cnt.data_ptr()), N.HDB_DEVICE))
+        flags = gathered[:, 2 * b * k + b:]
+        return idx, sc, cnt, (flags & N.FLAG_UNCERTIFIED).any()
+
+
+class ShardedMatrix:
+    """engine: the local shard (CudaEngine in production); group: torch.distributed process group."""
+
+    def __init__(self, engine, n_total, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = int(n_total)
+        self.exchanges = 0
+
+    def _comm_device(self):
+        return getattr(self.engine, "device", "cpu")
+
+    def refresh_decay(self):
+        """All-reduce(MAX) of the kept-row timestamp maximum, then rebuild every shard's decay column."""
+        import torch
+        mx, cnt = self.engine.kept_ts_max()
+        t = torch.tensor([mx if cnt > 0 else float("-inf")], dtype=torch.float64, device=self._comm_device())
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        if t.item() != float("-inf"):
+            self.engine.set_decay_reference(t.item())
+        return t.item()
+
+    def total_kept(self):
+        import torch
+        t = torch.tensor([self.engine.n_kept()], dtype=torch.int64, device=self._comm_device())
+        if self.world > 1:
+            self.dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def query_async(self, queries, top_k, metric, recency_bias=0.0, exact=False):
+        """Enqueue sweep -> all-gather -> merge; returns device tensors (idx, score, count, uncertified flag)."""
+        import torch
+        k = max(int(top_k), 0)
+        b = 1 if getattr(queries, "ndim", 1) == 1 else queries.shape[0]
+        mine = self.engine.local_topk(queries, k, metric, recency_bias, exact=exact)
+        if self.world > 1:
+            gathered = torch.empty(self.world * mine.numel(), dtype=mine.dtype, device=mine.device)
+            self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            self.exchanges += 1
+            gathered = gathered.view(self.world, mine.numel())
+        else:
+            gathered = mine.view(1, -1)
+        return self.engine.merge(gathered, b, k)
+
+    def query(self, queries, top_k, metric, recency_bias=0.0):
+        """Host results, identical on every rank: (idx [B,k], scores [B,k], counts [B])."""
+        idx, sc, cnt, bad = self.query_async(queries, top_k, metric, recency_bias)
+        if bool(bad):      # every rank sees every flag after the all-gather: same branch everywhere
+            idx, sc, cnt, bad = self.query_async(queries, top_k, metric, recency_bias, exact=True)
+        return idx.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
