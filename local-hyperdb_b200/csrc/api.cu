@@ -49,8 +49,9 @@ struct hdb_matrix {
   uint64_t* cand = nullptr;         // [kChunk][grid][kMaxKP]
   unsigned long long* tau = nullptr;
   int* uncertified = nullptr;
+  // host-output staging: one device block [idx | score | count | flags] mirrored by one pinned host block
+  char* o_block = nullptr; char* h_block = nullptr; size_t o_block_bytes = 0;
   int64_t* o_idx = nullptr; double* o_score = nullptr; int64_t* o_count = nullptr; uint32_t* o_flags = nullptr;
-  int64_t ws_k = 0;
   double* totals = nullptr;
   void* sort_scratch = nullptr; size_t sort_scratch_bytes = 0;
   unsigned long long* misc = nullptr;   // [2] ordered max bits, count
@@ -136,9 +137,10 @@ int hdb_matrix_destroy(hdb_matrix* m) {
   cudaStreamSynchronize(m->stream);
   if (m->owns_rows) cudaFree(m->rows);
   void* ptrs[] = {m->norms, m->inv_norms, m->bits, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
-                  m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_idx, m->o_score, m->o_count,
-                  m->o_flags, m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag};
+                  m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_block,
+                  m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (m->h_block) cudaFreeHost(m->h_block);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   delete m;
   return 0;
@@ -315,19 +317,24 @@ static int ensure_workspace(hdb_matrix* m, int64_t nq, int64_t k) {
     HDB_TRY(dev_alloc(&m->qb.qnorm, (size_t)nq));
     HDB_TRY(dev_alloc(&m->qb.qflags, (size_t)nq));
     HDB_TRY(dev_alloc(&m->tau, (size_t)nq));
-    HDB_TRY(dev_alloc(&m->o_count, (size_t)nq));
-    HDB_TRY(dev_alloc(&m->o_flags, (size_t)nq));
     m->ws_q = nq;
-    m->ws_k = 0;
   }
   if (!m->cand) HDB_TRY(dev_alloc(&m->cand, (size_t)kChunk * m->grid * kMaxKP));
   (void)cq;
-  if (m->ws_k < m->ws_q * (k > 0 ? k : 1)) {
-    const int64_t need = m->ws_q * (k > 0 ? k : 1);
-    HDB_TRY(dev_alloc(&m->o_idx, (size_t)need));
-    HDB_TRY(dev_alloc(&m->o_score, (size_t)need));
-    m->ws_k = need;
+  const size_t kk = (size_t)(k > 0 ? k : 1);
+  const size_t need = (size_t)nq * kk * 16 + (size_t)nq * 8 + (size_t)nq * 4;
+  if (m->o_block_bytes < need) {
+    if (m->o_block) cudaFree(m->o_block);
+    if (m->h_block) cudaFreeHost(m->h_block);
+    m->o_block = nullptr; m->h_block = nullptr; m->o_block_bytes = 0;
+    HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->o_block), need));
+    HDB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->h_block), need));
+    m->o_block_bytes = need;
   }
+  m->o_idx = reinterpret_cast<int64_t*>(m->o_block);
+  m->o_score = reinterpret_cast<double*>(m->o_block + (size_t)nq * kk * 8);
+  m->o_count = reinterpret_cast<int64_t*>(m->o_block + (size_t)nq * kk * 16);
+  m->o_flags = reinterpret_cast<uint32_t*>(m->o_block + (size_t)nq * kk * 16 + (size_t)nq * 8);
   if (!m->totals) HDB_TRY(dev_alloc(&m->totals, (size_t)(m->n ? m->n : 1)));
   return 0;
 }
@@ -430,27 +437,40 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   }
   if (dev_out) return 0;
 
-  // host outputs: synchronise, repair uncertified queries with the exact path, copy out
-  std::vector<uint32_t> hflags((size_t)nq, 0u);
-  HDB_CUDA(cudaMemcpyAsync(hflags.data(), flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, m->stream));
+  // host outputs: ONE device->pinned-host copy of [idx | score | count | flags], one synchronisation;
+  // queries the certificate rejected are repaired with the exact path and copied again
+  const size_t kk = (size_t)(k > 0 ? k : 1);
+  const size_t blk = (size_t)nq * kk * 16 + (size_t)nq * 8 + (size_t)nq * 4;
+  const int64_t* h_idx = reinterpret_cast<const int64_t*>(m->h_block);
+  const double* h_score = reinterpret_cast<const double*>(m->h_block + (size_t)nq * kk * 8);
+  const int64_t* h_count = reinterpret_cast<const int64_t*>(m->h_block + (size_t)nq * kk * 16);
+  uint32_t* h_flags = reinterpret_cast<uint32_t*>(m->h_block + (size_t)nq * kk * 16 + (size_t)nq * 8);
+  HDB_CUDA(cudaMemcpyAsync(m->h_block, m->o_block, blk, cudaMemcpyDeviceToHost, m->stream));
   HDB_CUDA(cudaStreamSynchronize(m->stream));
-  bool any_nan = false;
+  bool any_nan = false, repaired = false;
+  std::vector<uint32_t> fixed;
   for (int64_t b = 0; b < nq; ++b) {
-    if (hflags[b] & HDB_FLAG_QUERY_NAN) any_nan = true;
-    if (hflags[b] & HDB_FLAG_UNCERTIFIED) {
+    if (h_flags[b] & HDB_FLAG_QUERY_NAN) any_nan = true;
+    if (h_flags[b] & HDB_FLAG_UNCERTIFIED) {
       if (m->path_mode == 2) return fail("hdb_query: fused path forced but the certificate failed");
       HDB_TRY(run_exact(m, metric, rdt, b, k, f, idx, score, count));
-      hflags[b] = (hflags[b] & ~HDB_FLAG_UNCERTIFIED) | HDB_FLAG_FALLBACK;
+      if (fixed.empty()) fixed.assign(h_flags, h_flags + nq);
+      fixed[b] = (fixed[b] & ~HDB_FLAG_UNCERTIFIED) | HDB_FLAG_FALLBACK;
+      repaired = true;
     }
   }
   if (any_nan) return fail("Vectors and query_vector should not contain NaN values.");
-  if (k > 0) {
-    HDB_CUDA(cudaMemcpyAsync(out_idx, idx, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, m->stream));
-    HDB_CUDA(cudaMemcpyAsync(out_score, score, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, m->stream));
+  if (repaired) {
+    HDB_CUDA(cudaMemcpyAsync(m->h_block, m->o_block, blk, cudaMemcpyDeviceToHost, m->stream));
+    HDB_CUDA(cudaStreamSynchronize(m->stream));
+    memcpy(h_flags, fixed.data(), (size_t)nq * 4);
   }
-  HDB_CUDA(cudaMemcpyAsync(out_count, count, (size_t)nq * 8, cudaMemcpyDeviceToHost, m->stream));
-  HDB_CUDA(cudaStreamSynchronize(m->stream));
-  if (out_flags) memcpy(out_flags, hflags.data(), (size_t)nq * 4);
+  if (k > 0) {
+    memcpy(out_idx, h_idx, (size_t)nq * k * 8);
+    memcpy(out_score, h_score, (size_t)nq * k * 8);
+  }
+  memcpy(out_count, h_count, (size_t)nq * 8);
+  if (out_flags) memcpy(out_flags, h_flags, (size_t)nq * 4);
   return 0;
 }
 

@@ -95,6 +95,85 @@ __device__ typename Arith<RDT>::C pairwise_sum(Term term, int n) {
   return A::acc_done(ret);
 }
 
+// Warp-cooperative form of the same summation, bit-identical to pairwise_sum: the recursion's leaves
+// (<=128 elements) are independent, and inside a leaf the 8 interleaved accumulators are independent
+// chains, so 8 lanes own one leaf (4 leaves per warp at a time); the 8 accumulators are combined by a
+// 3-step butterfly, which is exactly ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) because IEEE addition is
+// commutative.  Leaf results are then combined in the recursion's post-order by every lane redundantly.
+// `term(i)` must be readable by any lane; all 32 lanes must call.  scratch: kPwMaxLeaves int2 + C slots.
+constexpr int kPwMaxLeaves = 64;
+struct PwScratch { int2 leaf[kPwMaxLeaves]; double res[kPwMaxLeaves]; };
+
+template <int RDT, typename Term>
+__device__ typename Arith<RDT>::C pairwise_sum_warp(Term term, int n, int lane, PwScratch* sc) {
+  using A = Arith<RDT>;
+  using C = typename A::C;
+  // enumerate the leaves in order (every lane walks the same recursion; lane 0 records them)
+  int nleaves = 0;
+  {
+    int2 st[30];
+    int sp = 0;
+    st[0] = make_int2(0, n);
+    while (sp >= 0) {
+      const int2 f = st[sp--];
+      if (f.y <= 128) {
+        if (nleaves < kPwMaxLeaves && lane == 0) sc->leaf[nleaves] = f;
+        ++nleaves;
+        continue;
+      }
+      int half = f.y / 2;
+      half -= half % 8;
+      st[++sp] = make_int2(f.x + half, f.y - half);     // right pushed first: left is popped first
+      st[++sp] = make_int2(f.x, half);
+    }
+  }
+  if (nleaves > kPwMaxLeaves) return pairwise_sum<RDT>(term, n);      // very long rows: sequential form
+  __syncwarp();
+  const int sub = lane & 7, grp = lane >> 3;
+  for (int base = 0; base < nleaves; base += 4) {
+    const int li = base + grp;
+    const bool have = li < nleaves;
+    const int2 f = have ? sc->leaf[li] : make_int2(0, 0);
+    C acc = 0;
+    const int m = f.y, full = m - (m % 8);
+    if (have && m >= 8) {
+      acc = term(f.x + sub);
+      for (int i = 8; i < full; i += 8) acc = A::acc_add(acc, term(f.x + i + sub));
+    }
+    acc = A::acc_add(acc, __shfl_xor_sync(kFull, acc, 1));
+    acc = A::acc_add(acc, __shfl_xor_sync(kFull, acc, 2));
+    acc = A::acc_add(acc, __shfl_xor_sync(kFull, acc, 4));
+    if (have && sub == 0) {
+      if (m < 8) {
+        acc = 0;
+        for (int i = 0; i < m; ++i) acc = A::acc_add(acc, term(f.x + i));
+      } else {
+        for (int i = full; i < m; ++i) acc = A::acc_add(acc, term(f.x + i));
+      }
+      sc->res[li] = (double)acc;
+    }
+  }
+  __syncwarp();
+  // combine the leaf results in post-order (same stack machine as pairwise_sum, leaves looked up)
+  struct Frame { int off, n, state; C left; };
+  Frame st[30];
+  int sp = 0, next_leaf = 0;
+  st[0] = Frame{0, n, 0, C(0)};
+  C ret = 0;
+  while (sp >= 0) {
+    Frame& f = st[sp];
+    if (f.n <= 128) { ret = A::from_double(sc->res[next_leaf++]); --sp; continue; }
+    int half = f.n / 2;
+    half -= half % 8;
+    if (f.state == 0) { f.state = 1; st[sp + 1] = Frame{f.off, half, 0, C(0)}; ++sp; continue; }
+    if (f.state == 1) { f.left = ret; f.state = 2; st[sp + 1] = Frame{f.off + half, f.n - half, 0, C(0)}; ++sp; continue; }
+    ret = A::acc_add(f.left, ret);
+    --sp;
+  }
+  __syncwarp();
+  return A::acc_done(ret);
+}
+
 // np.linalg.norm of one row/vector in dtype DT: sqrt(add.reduce(x*x)); zero -> caller's business.
 template <int DT>
 __device__ typename Arith<DT>::C canonical_norm(const void* x, int64_t d) {
@@ -116,10 +195,12 @@ template <int RDT, typename GetV, typename GetQ>
 __device__ typename Arith<RDT>::C canonical_dot(GetV gv, GetQ gq, int d) {
   if (RDT == 0) {
     float acc = 0.f;
+#pragma unroll 8
     for (int j = 0; j < d; ++j) acc = __fmaf_rn((float)gv(j), (float)gq(j), acc);   // products exact in fp32
     return Arith<RDT>::from_double((double)Arith<0>::rnd(acc));
   } else if (RDT == 1) {
     double acc = 0.0;
+#pragma unroll 8
     for (int j = 0; j < d; ++j) acc = __fma_rn((double)gv(j), (double)gq(j), acc);  // products exact in fp64
     return Arith<RDT>::from_double((double)(float)acc);
   } else {
@@ -139,57 +220,60 @@ __device__ typename Arith<RDT>::C canonical_dot(GetV gv, GetQ gq, int d) {
 }
 
 struct CanonArgs {
-  const void* rows;      // storage, row-major
   int sdt;               // storage dtype
   int64_t d;
   const double* qc;      // canonical query (values of dtype R, or unit query for cosine), length d
-  const uint32_t* bits;  // packed sign bits (hamming) or nullptr
-  const uint32_t* qbits;
+  const uint32_t* qbits; // packed sign bits of the query (hamming) or nullptr
   int words;             // 32-bit words per packed row
   int metric;
 };
 
-// Similarity of one row in the reference's arithmetic, returned as the R-typed value widened to double
-// (hamming: the integer D - popcount).
+// Element-wise half of a canonical score (parallelisable): the per-column term the reference feeds into
+// its reduction.  v = stored element, q = canonical query element (both widened to double).
 template <int RDT>
-__device__ double canonical_similarity(const CanonArgs& a, int64_t row, double nrm) {
+__device__ __forceinline__ typename Arith<RDT>::C canonical_term(int metric, double v, double q, double nrm, int sdt) {
+  using A = Arith<RDT>;
+  using C = typename A::C;
+  if (metric == 0) return A::from_double(v);
+  if (metric == 1) return A::from_double(unit_elem(v, nrm, sdt));
+  C df = A::sub(A::from_double(v), A::from_double(q));
+  return metric == 2 ? A::mul(df, df) : C(fabs(df));
+}
+
+// Order-dependent half: the reference's reduction over the terms (sequential by nature).
+template <int RDT, typename GetTerm, typename GetQ>
+__device__ double canonical_reduce(int metric, GetTerm term, GetQ gq, int d) {
+  using A = Arith<RDT>;
+  using C = typename A::C;
+  if (metric <= 1) return (double)canonical_dot<RDT>(term, gq, d);
+  C dist = pairwise_sum<RDT>(term, d);
+  if (metric == 2) dist = A::sqrt(dist);
+  return (double)A::div(C(1), A::add(C(1), dist));
+}
+
+// Similarity of one row in the reference's arithmetic, returned as the R-typed value widened to double
+// (hamming: the integer D - popcount).  `rowp` points at the row's d stored elements, `bitrow` at its
+// packed sign bits; nrm is the row's canonical norm (cosine only).
+template <int RDT>
+__device__ double canonical_similarity(const CanonArgs& a, const void* rowp, const uint32_t* bitrow, double nrm) {
   using A = Arith<RDT>;
   using C = typename A::C;
   const int d = (int)a.d;
   if (a.metric == 4) {
-    const uint32_t* r = a.bits + row * (int64_t)a.words;
     int diff = 0;
-    for (int w = 0; w < a.words; ++w) diff += __popc(r[w] ^ a.qbits[w]);
+    for (int w = 0; w < a.words; ++w) diff += __popc(bitrow[w] ^ a.qbits[w]);
     return (double)(d - diff);
   }
-  const char* base = reinterpret_cast<const char*>(a.rows) + row * a.d * dtype_size(a.sdt);
   auto gq = [&](int j) -> C { return A::from_double(a.qc[j]); };
-  if (a.metric == 0) {
-    auto gv = [&](int j) -> C { return A::from_double(load_as_double(base, a.sdt, j)); };
-    return (double)canonical_dot<RDT>(gv, gq, d);
-  }
-  if (a.metric == 1) {
-    auto gv = [&](int j) -> C { return A::from_double(unit_elem(load_as_double(base, a.sdt, j), nrm, a.sdt)); };
-    return (double)canonical_dot<RDT>(gv, gq, d);
-  }
-  if (a.metric == 2) {
-    auto term = [&](int j) -> C {
-      C df = A::sub(A::from_double(load_as_double(base, a.sdt, j)), gq(j));
-      return A::mul(df, df);
-    };
-    C dist = A::sqrt(pairwise_sum<RDT>(term, d));
-    return (double)A::div(C(1), A::add(C(1), dist));
-  }
-  auto term = [&](int j) -> C { return fabs(A::sub(A::from_double(load_as_double(base, a.sdt, j)), gq(j))); };
-  C dist = pairwise_sum<RDT>(term, d);
-  return (double)A::div(C(1), A::add(C(1), dist));
+  auto term = [&](int j) -> C { return canonical_term<RDT>(a.metric, load_as_double(rowp, a.sdt, j), a.qc[j], nrm, a.sdt); };
+  return canonical_reduce<RDT>(a.metric, term, gq, d);
 }
 
-// nrm: the row's canonical norm (zero already replaced by 1); only read for cosine
-__device__ __forceinline__ double canonical_similarity_rt(const CanonArgs& a, int rdt, int64_t row, double nrm) {
-  if (rdt == 0) return canonical_similarity<0>(a, row, nrm);
-  if (rdt == 1) return canonical_similarity<1>(a, row, nrm);
-  return canonical_similarity<2>(a, row, nrm);
+__device__ __forceinline__ double canonical_similarity_rt(const CanonArgs& a, int rdt, const void* rowp,
+                                                          const uint32_t* bitrow, double nrm) {
+  if (rdt == 0) return canonical_similarity<0>(a, rowp, bitrow, nrm);
+  if (rdt == 1) return canonical_similarity<1>(a, rowp, bitrow, nrm);
+  return canonical_similarity<2>(a, rowp, bitrow, nrm);
 }
 
 // ranking_algorithm.py:171-186: float64 score, NaN -> -inf, + recency_bias * exp(ts - max ts)

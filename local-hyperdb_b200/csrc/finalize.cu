@@ -15,8 +15,35 @@
 namespace hdb {
 
 constexpr int kSurvCap = 2048;      // candidate keys >= the final threshold that one CTA can merge
-constexpr int kFinThreads = 256;
+constexpr int kFinThreads = 512;
 constexpr uint32_t kFlagUncertified = 8u;
+
+template <typename CS> __device__ __forceinline__ CS to_carrier(__half x) { return (CS)__half2float(x); }
+template <typename CS> __device__ __forceinline__ CS to_carrier(float x) { return (CS)x; }
+template <typename CS> __device__ __forceinline__ CS to_carrier(double x) { return (CS)x; }
+
+// 16 strided elements of one row, all loads issued before any use (hides the global-load latency)
+template <typename T>
+__device__ __forceinline__ void load_batch(const void* src, int64_t j0, int64_t d, double (&v)[16]) {
+  const T* p = reinterpret_cast<const T*>(src);
+  T raw[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int64_t j = j0 + 32 * u;
+    raw[u] = p[j < d ? j : j0];
+  }
+#pragma unroll
+  for (int u = 0; u < 16; ++u) v[u] = (double)(float)raw[u];
+}
+template <>
+__device__ __forceinline__ void load_batch<double>(const void* src, int64_t j0, int64_t d, double (&v)[16]) {
+  const double* p = reinterpret_cast<const double*>(src);
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int64_t j = j0 + 32 * u;
+    v[u] = p[j < d ? j : j0];
+  }
+}
 
 // Upper bound of the CANONICAL total score of any row whose selection key is <= the KP-th key
 // (score part s).  See DESIGN.md "certificate"; every term is a worst-case rounding bound.
@@ -58,6 +85,87 @@ __device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) 
   return (1.0 / (1.0 + dc)) * (1.0 + 3.0 * uR);
 }
 
+// Typed fast path of the canonical re-scoring: T = storage type, SDT/RDT = storage / result dtype ids
+// (SDT <= RDT).  Same arithmetic as canonical_term / canonical_reduce, without runtime dtype switches or
+// double round-trips; v / norm is skipped when the norm is exactly 1 (x / 1 == x in IEEE arithmetic).
+template <typename T, int SDT, int RDT>
+__device__ void rescore_smem(const FinalizeArgs& a, int64_t b, const uint64_t* surv, int m, double* c_tot,
+                             uint32_t* c_row, unsigned char* smem, PwScratch* s_pw) {
+  using AR = Arith<RDT>;
+  using AS = Arith<SDT>;
+  using C = typename AR::C;
+  using CS = typename AS::C;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = (int)a.m.d;
+  const int pitch = d | 1;                                                // odd: conflict-free column walks
+  C* s_q = reinterpret_cast<C*>(smem);
+  C* s_terms = reinterpret_cast<C*>(smem + (((size_t)d * sizeof(C) + 15) & ~size_t(15)));
+  const int64_t avail = (int64_t)a.smem_bytes - (reinterpret_cast<unsigned char*>(s_terms) - smem);
+  int batch = (int)(avail / ((int64_t)pitch * sizeof(C)));
+  if (batch > m) batch = m;
+  const double* qc = a.qb.qc + b * a.m.d;
+  for (int j = tid; j < d; j += kFinThreads) s_q[j] = AR::from_double(qc[j]);
+  const T* grows = reinterpret_cast<const T*>(a.m.rows);
+  const int metric = a.metric;
+  for (int base = 0; base < m; base += batch) {
+    const int nb = (m - base) < batch ? (m - base) : batch;
+    __syncthreads();
+    // ---- phase A
+    for (int r = warp; r < nb; r += kFinThreads / 32) {
+      const uint32_t row = key_row(surv[base + r]);
+      const T* src = grows + (int64_t)row * d;
+      CS nrm = CS(1);
+      if (metric == HDB_COSINE) nrm = SDT == 2 ? (CS) reinterpret_cast<const double*>(a.m.norms)[row]
+                                                : (CS) reinterpret_cast<const float*>(a.m.norms)[row];
+      C* dst = s_terms + (size_t)r * pitch;
+      for (int j0 = lane; j0 < d; j0 += 32 * 8) {
+        T raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int j = j0 + 32 * u; raw[u] = src[j < d ? j : j0]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 32 * u;
+          if (j < d) {
+            const CS vs = to_carrier<CS>(raw[u]);
+            C term;
+            if (metric == 0) term = (C)vs;
+            else if (metric == 1) term = (nrm == CS(1)) ? (C)vs : (C)AS::div(vs, nrm);
+            else {
+              const C df = AR::sub((C)vs, s_q[j]);
+              term = metric == 2 ? AR::mul(df, df) : C(fabs(df));
+            }
+            dst[j] = term;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase B
+    if (metric <= 1) {
+      const int t = tid - base;
+      if (t >= 0 && t < nb) {
+        const uint32_t row = key_row(surv[tid]);
+        const C* terms = s_terms + (size_t)t * pitch;
+        const double sim = canonical_reduce<RDT>(metric, [&](int j) { return terms[j]; }, [&](int j) { return s_q[j]; }, d);
+        c_tot[tid] = total_score(sim, a.f.decay, a.f.bias, row);
+        c_row[tid] = row;
+      }
+    } else {
+      for (int r = warp; r < nb; r += kFinThreads / 32) {
+        const uint32_t row = key_row(surv[base + r]);
+        const C* terms = s_terms + (size_t)r * pitch;
+        C dist = pairwise_sum_warp<RDT>([&](int j) { return terms[j]; }, d, lane, &s_pw[warp]);
+        if (metric == 2) dist = AR::sqrt(dist);
+        const double sim = (double)AR::div(C(1), AR::add(C(1), dist));
+        if (lane == 0) {
+          c_tot[base + r] = total_score(sim, a.f.decay, a.f.bias, row);
+          c_row[base + r] = row;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   __shared__ uint64_t surv[kSurvCap];
   __shared__ double c_tot[kMaxKP];
@@ -66,6 +174,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   __shared__ uint32_t o_row[kMaxKP];
   __shared__ int s_count;
   __shared__ unsigned s_hist[256];
+  __shared__ PwScratch s_pw[kFinThreads / 32];
   __shared__ int s_sel[3];
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -76,11 +185,19 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   const unsigned long long tau = a.tau[b];
   const uint64_t* cand = a.cand + b * (int64_t)a.grid * a.kp;
   const int total = a.grid * a.kp;
-  for (int i = tid; i < total; i += kFinThreads) {
-    uint64_t key = cand[i];
-    if (key != 0 && key >= tau) {
-      int pos = atomicAdd(&s_count, 1);
-      if (pos < kSurvCap) surv[pos] = key;
+  for (int i0 = tid; i0 < total; i0 += kFinThreads * 8) {       // 8 loads in flight per thread
+    uint64_t key[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * kFinThreads;
+      key[u] = i < total ? cand[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (key[u] != 0 && key[u] >= tau) {
+        int pos = atomicAdd(&s_count, 1);
+        if (pos < kSurvCap) surv[pos] = key[u];
+      }
     }
   }
   __syncthreads();
@@ -130,25 +247,55 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     __syncthreads();
     found = s_count < kSurvCap ? s_count : kSurvCap;
   }
-  int pow2 = 32;
-  while (pow2 < found) pow2 <<= 1;
-  for (int i = found + tid; i < pow2; i += kFinThreads) surv[i] = 0;
-  __syncthreads();
-  bitonic_desc(surv, pow2, tid, kFinThreads, [] { __syncthreads(); });
+  // order the survivors: rank by counting when they are few (one barrier), bitonic sort otherwise
+  if (found <= kFinThreads) {
+    uint64_t mine = 0;
+    int rank = 0;
+    if (tid < found) {
+      mine = surv[tid];
+      for (int j = 0; j < found; ++j) rank += surv[j] > mine;
+    }
+    __syncthreads();
+    if (tid < found) surv[rank] = mine;
+    __syncthreads();
+  } else {
+    int pow2 = 512;
+    while (pow2 < found) pow2 <<= 1;
+    for (int i = found + tid; i < pow2; i += kFinThreads) surv[i] = 0;
+    __syncthreads();
+    bitonic_desc(surv, pow2, tid, kFinThreads, [] { __syncthreads(); });
+  }
   const int m = found < a.kp ? found : a.kp;          // candidates to certify
 
-  CanonArgs ca;
-  ca.rows = a.m.rows; ca.sdt = a.m.dtype; ca.d = a.m.d;
-  ca.qc = a.qb.qc + b * a.m.d;
-  ca.bits = a.m.bits; ca.words = a.m.words;
-  ca.qbits = a.qb.qbits ? a.qb.qbits + b * a.m.words : nullptr;
-  ca.metric = a.metric;
-  if (tid < m) {
+  // Canonical re-scoring in two phases: (A) all threads compute the per-column terms of the candidate rows
+  // (coalesced global reads, element-wise reference arithmetic) into shared memory; (B) the reference's
+  // order-dependent reduction out of shared memory (thread per candidate for the dot chains, warp per
+  // candidate for NumPy's pairwise sums).
+  extern __shared__ __align__(16) unsigned char fin_smem[];
+  if (a.smem_bytes > 0) {
+    const int combo = a.m.dtype * 3 + a.rdt;
+    switch (combo) {
+      case 0: rescore_smem<__half, 0, 0>(a, b, surv, m, c_tot, c_row, fin_smem, s_pw); break;
+      case 1: rescore_smem<__half, 0, 1>(a, b, surv, m, c_tot, c_row, fin_smem, s_pw); break;
+      case 2: rescore_smem<__half, 0, 2>(a, b, surv, m, c_tot, c_row, fin_smem, s_pw); break;
+      case 4: rescore_smem<float, 1, 1>(a, b, surv, m, c_tot, c_row, fin_smem, s_pw); break;
+      case 5: rescore_smem<float, 1, 2>(a, b, surv, m, c_tot, c_row, fin_smem, s_pw); break;
+      default: rescore_smem<double, 2, 2>(a, b, surv, m, c_tot, c_row, fin_smem, s_pw); break;
+    }
+  } else if (tid < m) {
+    // hamming, or rows too long for shared memory: straight from global memory
+    CanonArgs ca;
+    ca.sdt = a.m.dtype; ca.d = a.m.d; ca.words = a.m.words;
+    ca.qbits = a.qb.qbits ? a.qb.qbits + b * a.m.words : nullptr;
+    ca.metric = a.metric;
+    ca.qc = a.qb.qc + b * a.m.d;
     const uint32_t row = key_row(surv[tid]);
+    const uint32_t* bitrow = a.m.bits ? a.m.bits + (int64_t)row * a.m.words : nullptr;
     double nrm = 1.0;
     if (a.metric == HDB_COSINE)
       nrm = a.m.dtype == 2 ? reinterpret_cast<const double*>(a.m.norms)[row] : (double)reinterpret_cast<const float*>(a.m.norms)[row];
-    const double sim = canonical_similarity_rt(ca, a.rdt, row, nrm);
+    const char* rowp = reinterpret_cast<const char*>(a.m.rows) + (int64_t)row * a.m.d * dtype_size(a.m.dtype);
+    const double sim = canonical_similarity_rt(ca, a.rdt, rowp, bitrow, nrm);
     c_tot[tid] = total_score(sim, a.f.decay, a.f.bias, row);
     c_row[tid] = row;
   }
@@ -188,9 +335,22 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   }
 }
 
-int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s) {
+int launch_finalize(const FinalizeArgs& a_in, int64_t nq, cudaStream_t s) {
   if (nq == 0) return 0;
-  finalize_kernel<<<(unsigned)nq, kFinThreads, 0, s>>>(a);
+  FinalizeArgs a = a_in;
+  // query (8 B/dim) + the terms of as many candidate rows as fit in ~160 KB; 0 = read global memory directly
+  const int64_t row_pitch = (a.m.d | 1) * (a.rdt == 2 ? 8 : 4);
+  const int64_t qbytes = (a.m.d * (a.rdt == 2 ? 8 : 4) + 15) & ~int64_t(15);
+  int64_t want = qbytes + row_pitch * a.kp;
+  if (want > 160 * 1024) want = 160 * 1024;
+  if (want < qbytes + row_pitch || a.metric == HDB_HAMMING) want = 0;
+  a.smem_bytes = (int)want;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HDB_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  finalize_kernel<<<(unsigned)nq, kFinThreads, (size_t)a.smem_bytes, s>>>(a);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;
@@ -207,8 +367,8 @@ __device__ __forceinline__ bool kept_row(const RowFilter& f, int64_t row) {
 
 __device__ __forceinline__ CanonArgs canon_args(const MatrixView& m, int metric, const double* qc, const uint32_t* qbits) {
   CanonArgs ca;
-  ca.rows = m.rows; ca.sdt = m.dtype; ca.d = m.d; ca.qc = qc;
-  ca.bits = m.bits; ca.qbits = qbits; ca.words = m.words; ca.metric = metric;
+  ca.sdt = m.dtype; ca.d = m.d; ca.qc = qc;
+  ca.qbits = qbits; ca.words = m.words; ca.metric = metric;
   return ca;
 }
 
@@ -216,7 +376,9 @@ __device__ __forceinline__ double row_canonical(const MatrixView& m, CanonArgs& 
   double nrm = 1.0;
   if (ca.metric == HDB_COSINE)
     nrm = m.dtype == 2 ? reinterpret_cast<const double*>(m.norms)[row] : (double)reinterpret_cast<const float*>(m.norms)[row];
-  return canonical_similarity_rt(ca, rdt, row, nrm);
+  const void* rowp = reinterpret_cast<const char*>(m.rows) + row * m.d * dtype_size(m.dtype);
+  const uint32_t* bitrow = m.bits ? m.bits + row * (int64_t)m.words : nullptr;
+  return canonical_similarity_rt(ca, rdt, rowp, bitrow, nrm);
 }
 
 __global__ void full_scores_kernel(MatrixView m, RowFilter f, int metric, int rdt, const double* qc,

@@ -92,6 +92,7 @@ struct FinalizeArgs {
   QueryBuffers qb;
   int64_t* out_idx; double* out_score; int64_t* out_count; uint32_t* out_flags;   // device
   int* uncertified;              // device counter: queries that need the exact path
+  int smem_bytes;                // dynamic shared memory of the finalize kernel (set by launch_finalize)
 };
 int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s);
 int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,

@@ -179,29 +179,53 @@ int launch_stage1(double* ts, int64_t n, double bias1, double ts_max, cudaStream
 }
 
 // ---------------------------------------------------------------------------------------------
-// One CTA per query.
+// One CTA per query.  The query's canonical norm (np.linalg.norm in the query's own dtype) is split like
+// the candidate re-scoring: squares element-wise by all threads into shared memory, NumPy's pairwise
+// reduction by one thread out of shared memory.
 template <int QDT>
-__device__ double query_unit_norm(const void* q, int64_t d) {
-  typename Arith<QDT>::C n = canonical_norm<QDT>(q, d);
-  if (n == 0) n = 1;
-  return (double)n;
+__device__ double query_unit_norm(const void* q, int64_t d, void* s_sq, int tid, int nthreads, bool staged) {
+  using A = Arith<QDT>;
+  using C = typename A::C;
+  __shared__ double s_result;
+  C* sq = reinterpret_cast<C*>(s_sq);
+  if (staged) {
+    for (int64_t j = tid; j < d; j += nthreads) {
+      C v = A::from_double(load_as_double(q, QDT, j));
+      sq[j] = A::mul(v, v);
+    }
+    __syncthreads();
+  }
+  __shared__ PwScratch s_pw;
+  if (staged) {
+    if (tid < 32) {
+      C n = A::sqrt(pairwise_sum_warp<QDT>([&](int i) { return sq[i]; }, (int)d, tid, &s_pw));
+      if (n == 0) n = 1;
+      if (tid == 0) s_result = (double)n;
+    }
+  } else if (tid == 0) {
+    C n = canonical_norm<QDT>(q, d);
+    if (n == 0) n = 1;
+    s_result = (double)n;
+  }
+  __syncthreads();
+  return s_result;
 }
 
 __global__ void prep_query_kernel(const void* queries, int qdt, int64_t d, int metric, int sdt, int words,
-                                  QueryBuffers qb) {
-  __shared__ double s_norm;
+                                  QueryBuffers qb, int stage) {
+  extern __shared__ __align__(16) unsigned char s_query[];
   __shared__ double s_red[32];
   __shared__ int s_nan;
   const int64_t b = blockIdx.x;
   const char* q = reinterpret_cast<const char*>(queries) + b * d * dtype_size(qdt);
-  if (threadIdx.x == 0) {
-    s_nan = 0;
-    s_norm = 1.0;
-    if (metric == HDB_COSINE)
-      s_norm = qdt == 0 ? query_unit_norm<0>(q, d) : (qdt == 1 ? query_unit_norm<1>(q, d) : query_unit_norm<2>(q, d));
+  if (threadIdx.x == 0) s_nan = 0;
+  double nrm = 1.0;
+  if (metric == HDB_COSINE) {
+    if (qdt == 0) nrm = query_unit_norm<0>(q, d, s_query, threadIdx.x, blockDim.x, stage);
+    else if (qdt == 1) nrm = query_unit_norm<1>(q, d, s_query, threadIdx.x, blockDim.x, stage);
+    else nrm = query_unit_norm<2>(q, d, s_query, threadIdx.x, blockDim.x, stage);
   }
   __syncthreads();
-  const double nrm = s_norm;
   const bool acc_f64 = (sdt == 2);
   double sq = 0.0;
   bool bad = false;
@@ -214,14 +238,13 @@ __global__ void prep_query_kernel(const void* queries, int qdt, int64_t d, int m
     else reinterpret_cast<float*>(qb.qa)[b * d + j] = (float)c;
     sq += c * c;
   }
-  if (qb.qbits) {
-    for (int w = threadIdx.x; w < words; w += blockDim.x) {
-      uint32_t word = 0;
-      for (int t = 0; t < 32; ++t) {
-        int64_t j = (int64_t)w * 32 + t;
-        if (j < d && load_as_double(q, qdt, j) > 0.0) word |= (1u << t);
-      }
-      qb.qbits[b * words + w] = word;
+  if (qb.qbits) {       // sign bits: one coalesced 32-element read + ballot per word
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int w = threadIdx.x >> 5; w < words; w += nwarps) {
+      const int64_t j = (int64_t)w * 32 + lane;
+      const bool on = j < d && load_as_double(q, qdt, j) > 0.0;
+      const unsigned word = __ballot_sync(kFull, on);
+      if (lane == 0) qb.qbits[b * words + w] = word;
     }
   }
   sq = warp_sum(sq);
@@ -239,7 +262,9 @@ __global__ void prep_query_kernel(const void* queries, int qdt, int64_t d, int m
 int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int metric, int sdt, int words,
                       const QueryBuffers& qb, cudaStream_t s) {
   if (nq == 0) return 0;
-  prep_query_kernel<<<(unsigned)nq, 128, 0, s>>>(q, q_dtype, d, metric, sdt, words, qb);
+  const size_t bytes = (size_t)d * (q_dtype == 2 ? 8 : 4);          // squares in the carrier type
+  const int stage = bytes <= 40 * 1024;
+  prep_query_kernel<<<(unsigned)nq, 128, stage ? bytes : 0, s>>>(q, q_dtype, d, metric, sdt, words, qb, stage);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;

@@ -27,8 +27,8 @@ def shard_bounds(n_total: int, world: int, rank: int):
 
 
 def packed_len(b: int, k: int) -> int:
-    """Words (int64) of one rank's message: scores[b*k] | ids[b*k] | counts[b] | flags[b]."""
-    return 2 * b * k + 2 * b
+    """Words (int64) of one rank's message: scores[b*k] | ids[b*k] | counts[b] | flags (b uint32, two per word)."""
+    return 2 * b * k + b + (b + 1) // 2
 
 
 class CudaEngine:
@@ -59,31 +59,34 @@ class CudaEngine:
         sc = buf[: b * k].view(torch.float64)
         ids = buf[b * k: 2 * b * k]
         cnt = buf[2 * b * k: 2 * b * k + b]
-        flags64 = buf[2 * b * k + b:]
-        flags = torch.zeros(b, dtype=torch.int32, device=self.device)
+        flags = buf[2 * b * k + b:].view(torch.int32)
         self.m.set_path(1 if exact else 0)
         try:
             self.m.query_device(q, k, metric, bias, ids, sc, cnt, flags)
         finally:
             self.m.set_path(0)
-        flags64.copy_(flags)
         return buf
 
     def merge(self, gathered, b, k):
-        """gathered: int64 CUDA tensor [G, packed_len]; -> (idx [b,k], score [b,k], count [b], any_uncertified tensor)."""
+        """gathered: int64 CUDA tensor [G, packed_len]; -> (idx [b,k], score [b,k], count [b], flags int32 [G,b])."""
         torch = self.torch
         g, ln = gathered.shape
-        idx = torch.empty((b, k), dtype=torch.int64, device=self.device)
-        sc = torch.empty((b, k), dtype=torch.float64, device=self.device)
-        cnt = torch.empty(b, dtype=torch.int64, device=self.device)
+        flags = gathered[:, 2 * b * k + b:].view(torch.int32)[:, :b]
+        if g == 1:           # single shard: the local result is the result
+            row = gathered[0]
+            return (row[b * k: 2 * b * k].view(b, k), row[: b * k].view(torch.float64).view(b, k),
+                    row[2 * b * k: 2 * b * k + b], flags)
+        out = torch.empty(2 * b * k + b, dtype=torch.int64, device=self.device)      # one block: one D2H copy later
+        idx = out[: b * k].view(b, k)
+        sc = out[b * k: 2 * b * k].view(torch.float64).view(b, k)
+        cnt = out[2 * b * k:]
         base = gathered.data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         N.check(N.lib().hdb_merge_topk(self.device.index, C.c_void_p(stream), g, b, k, ln,
                                        C.c_void_p(base), C.c_void_p(base + 8 * b * k), C.c_void_p(base + 16 * b * k),
                                        N.HDB_DEVICE, C.c_void_p(idx.data_ptr()), C.c_void_p(sc.data_ptr()),
                                        C.c_void_p(cnt.data_ptr()), N.HDB_DEVICE))
-        flags = gathered[:, 2 * b * k + b:]
-        return idx, sc, cnt, (flags & N.FLAG_UNCERTIFIED).any()
+        return idx, sc, cnt, flags
 
 
 class ShardedMatrix:
@@ -121,7 +124,7 @@ class ShardedMatrix:
         return int(t.item())
 
     def query_async(self, queries, top_k, metric, recency_bias=0.0, exact=False):
-        """Enqueue sweep -> all-gather -> merge; returns device tensors (idx, score, count, uncertified flag)."""
+        """Enqueue sweep -> all-gather -> merge; returns device tensors (idx, score, count, per-shard flags)."""
         import torch
         k = max(int(top_k), 0)
         b = 1 if getattr(queries, "ndim", 1) == 1 else queries.shape[0]
@@ -137,7 +140,16 @@ class ShardedMatrix:
 
     def query(self, queries, top_k, metric, recency_bias=0.0):
         """Host results, identical on every rank: (idx [B,k], scores [B,k], counts [B])."""
-        idx, sc, cnt, bad = self.query_async(queries, top_k, metric, recency_bias)
-        if bool(bad):      # every rank sees every flag after the all-gather: same branch everywhere
-            idx, sc, cnt, bad = self.query_async(queries, top_k, metric, recency_bias, exact=True)
+        idx, sc, cnt, flags = self.query_async(queries, top_k, metric, recency_bias)
+        flags = flags.cpu().numpy()
+        if (flags & N.FLAG_QUERY_NAN).any():
+            raise ValueError("Vectors and query_vector should not contain NaN values.")
+        if (flags & N.FLAG_UNCERTIFIED).any():      # every rank sees every flag after the all-gather: same branch everywhere
+            idx, sc, cnt, flags = self.query_async(queries, top_k, metric, recency_bias, exact=True)
+        b, k = idx.shape
+        if idx.data_ptr() + 8 * b * k == sc.data_ptr():          # merged block [idx | score | count]: one copy
+            import torch
+            blk = torch.as_strided(idx, (2 * b * k + b,), (1,)).cpu()
+            return (blk[: b * k].view(b, k).numpy(), blk[b * k: 2 * b * k].view(torch.float64).view(b, k).numpy(),
+                    blk[2 * b * k:].numpy())
         return idx.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
