@@ -65,8 +65,16 @@ __device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) 
   }
   // euclidean / manhattan: similarity in (0, 1]
   if (decay) {
-    double e = 8.0 * uR + D * ua + chain16 + ua * qnorm;
-    if (a.rdt == 0 && a.metric == HDB_EUCLIDEAN) e += sqrt(D * 5.9604644775390625e-8);
+    // total = sim + bias*decay.  With bias >= 0 the outsider's similarity is at most min(1, s'), and the
+    // similarity's error is relative to it (d(sim) <= d(dist)/(1+dist)^2 <= rel(dist) * sim).
+    const double smax = (a.f.bias >= 0.0) ? fmin(1.0, fmax(s, 0.0) * (1.0 + uk) + 1e-300) : 1.0;
+    double rel = (a.metric == HDB_EUCLIDEAN) ? 0.5 * (D * ua + 6.0 * uR + chain16) + 6.0 * uR
+                                             : (D * ua + 4.0 * uR + chain16) + 3.0 * uR;
+    double e = rel * smax + ua * qnorm;
+    if (a.rdt == 0 && a.metric == HDB_EUCLIDEAN) {
+      const double under = D * 5.9604644775390625e-8, dmin = 1.0 / smax - 1.0;
+      e += (dmin > 1e-2) ? under / (2.0 * dmin) : sqrt(under);
+    }
     return s + fabs(s) * uk + e;
   }
   if (!(s > 0.0)) return INFINITY;

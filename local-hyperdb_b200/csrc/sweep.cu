@@ -157,13 +157,13 @@ __device__ __forceinline__ void cta_merge_and_store(uint64_t* s_lists, WarpList<
   for (int i = threadIdx.x; i < KP; i += kSweepThreads) cand_out[i] = s_lists[i];
 }
 
-__device__ __forceinline__ unsigned group_keep_mask(const RowFilter& f, int64_t row0, int64_t n) {
-  // 8 consecutive rows starting at a multiple of 8 share one mask word
-  unsigned bits = 0xffu;
-  if (f.mask) bits = (f.mask[row0 >> 5] >> (row0 & 31)) & 0xffu;
-  int64_t hi = f.hi < n ? f.hi : n;
-  if (row0 < f.lo) { int64_t s = f.lo - row0; bits = s >= 8 ? 0u : (bits & (0xffu << s)); }
-  if (row0 + 8 > hi) { int64_t keep = hi - row0; bits = keep <= 0 ? 0u : (bits & (0xffu >> (8 - keep))); }
+// keep bits of the 32-row window w (rows 32w .. 32w+31): mask word AND kept range AND row count
+__device__ __forceinline__ uint32_t window_keep_bits(const RowFilter& f, int64_t w, int64_t n) {
+  uint32_t bits = f.mask ? f.mask[w] : 0xffffffffu;
+  const int64_t row0 = w * 32;
+  const int64_t hi = f.hi < n ? f.hi : n;
+  if (row0 < f.lo) { const int64_t s = f.lo - row0; bits = s >= 32 ? 0u : (bits & (0xffffffffu << s)); }
+  if (row0 + 32 > hi) { const int64_t keep = hi - row0; bits = keep <= 0 ? 0u : (bits & (0xffffffffu >> (32 - keep))); }
   return bits;
 }
 
@@ -190,85 +190,103 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
   wl.cnt = 0;
   wl.tau = 0;
 
-  const int64_t ngroups = (p.n + kRows - 1) / kRows;
+  // A warp walks windows of 32 consecutive rows (one mask word) and, inside a window, batches of up to 8
+  // KEPT rows: dropped rows are never loaded and 8 independent 16-byte loads per lane stay in flight
+  // whatever the mask density is.
+  const int64_t nwin = (p.n + 31) / 32;
   const int64_t wstride = (int64_t)gridDim.x * kSweepWarps;
   const int my_row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const bool rep = (lane & 3) == 0;
   const Acc* inv = reinterpret_cast<const Acc*>(p.inv_norms);
   int since_refresh = 0;
+  const int64_t g0 = (int64_t)blockIdx.x * kSweepWarps + warp;
+  uint32_t next_bits = (g0 < nwin) ? window_keep_bits(p.f, g0, p.n) : 0u;
 
-  for (int64_t g = (int64_t)blockIdx.x * kSweepWarps + warp; g < ngroups; g += wstride) {
-    const int64_t row0 = g * kRows;
-    const unsigned keep = group_keep_mask(p.f, row0, p.n);
-    if (keep == 0) continue;
+  for (int64_t g = g0; g < nwin; g += wstride) {
+    uint32_t bits = next_bits;
+    next_bits = (g + wstride < nwin) ? window_keep_bits(p.f, g + wstride, p.n) : 0u;    // prefetch the next mask word
+    if (bits == 0) continue;
     // refresh the threshold from the CTA (cheap) and, now and then, from the grid
     {
       unsigned long long t = *reinterpret_cast<volatile unsigned long long*>(s_tau);
-      if (++since_refresh >= 16) {
+      if (++since_refresh >= 4) {
         since_refresh = 0;
         unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(p.tau);
         if (gt > t) { t = gt; if (lane == 0) atomicMax(s_tau, gt); }
       }
       if (t > wl.tau) wl.tau = t;
     }
-    // per-row side inputs, issued before the streaming loop so their latency is hidden
-    const int64_t mrow = row0 + my_row;
-    const bool mine_kept = (keep >> my_row) & 1u;
-    Acc my_inv = Acc(1);
-    double my_decay = 0.0;
-    if (rep && mine_kept) {
-      if (inv) my_inv = inv[mrow];
-      if (p.f.decay) my_decay = p.f.decay[mrow];
-    }
-
-    Acc acc[kRows];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) acc[r] = Acc(0);
+    const int64_t row0 = g * 32;
     const char* base = p.rows + row0 * p.row_bytes;
-
-    if (VEC) {
-#pragma unroll 2
-      for (int c = lane; c < p.nvec; c += 32) {
-        uint4 raw[kRows];
+    while (bits) {
+      // the next (up to) 8 kept rows of the window: warp-uniform offsets
+      uint32_t ro[kRows];                 // byte offsets inside the window (32 rows < 4 GB)
+      unsigned keep = 0;
+      int my_off = 0;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          if ((keep >> r) & 1u) raw[r] = ld_stream16(base + r * p.row_bytes + (int64_t)c * 16);
-          else raw[r] = make_uint4(0, 0, 0, 0);
-        }
-        Acc q[kPerVec];
-#pragma unroll
-        for (int i = 0; i < kPerVec; ++i) q[i] = s_q[c * kPerVec + i];
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) accum_vec<MC>(acc[r], raw[r], q, T());
+      for (int r = 0; r < kRows; ++r) {
+        const int pos = __ffs(bits) - 1;
+        const bool ok = bits != 0;
+        ro[r] = (uint32_t)(ok ? pos : 0) * (uint32_t)p.row_bytes;
+        keep |= (ok ? 1u : 0u) << r;
+        if (r == my_row) my_off = pos;
+        bits &= bits - 1;
       }
-    } else {
-      for (int c = lane; c < p.nvec; c += 32) {
-        const Acc q = s_q[c];
+      // per-row side inputs, issued before the streaming loop so their latency is hidden
+      const bool mine_kept = (keep >> my_row) & 1u;
+      const int64_t mrow = row0 + my_off;
+      Acc my_inv = Acc(1);
+      double my_decay = 0.0;
+      if (rep && mine_kept) {
+        if (inv) my_inv = inv[mrow];
+        if (p.f.decay) my_decay = p.f.decay[mrow];
+      }
+
+      Acc acc[kRows];
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          if ((keep >> r) & 1u) {
-            const T* rowp = reinterpret_cast<const T*>(base + r * p.row_bytes);
-            accum<MC, Acc>(acc[r], (Acc)rowp[c], q);
+      for (int r = 0; r < kRows; ++r) acc[r] = Acc(0);
+
+      if (VEC) {
+#pragma unroll 2
+        for (int c = lane; c < p.nvec; c += 32) {
+          uint4 raw[kRows];
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) {
+            if ((keep >> r) & 1u) raw[r] = ld_stream16(base + (ro[r] + (uint32_t)c * 16u));
+            else raw[r] = make_uint4(0, 0, 0, 0);
+          }
+          Acc q[kPerVec];
+#pragma unroll
+          for (int i = 0; i < kPerVec; ++i) q[i] = s_q[c * kPerVec + i];
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) accum_vec<MC>(acc[r], raw[r], q, T());
+        }
+      } else {
+        for (int c = lane; c < p.nvec; c += 32) {
+          const Acc q = s_q[c];
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) {
+            if ((keep >> r) & 1u) accum<MC, Acc>(acc[r], (Acc) reinterpret_cast<const T*>(base + ro[r])[c], q);
           }
         }
       }
-    }
 
-    Acc total = reduce8(acc, lane);
-    // epilogue: similarity, decay, key
-    float score;
-    if (MC == 0) {
-      total = total * my_inv;
-      if (p.f.decay) score = (float)((double)total + p.f.bias * my_decay);
-      else score = (float)total;
-    } else {
-      Acc dist = (MC == 1) ? sqrt_of(total) : total;
-      Acc sim = Acc(1) / (Acc(1) + dist);
-      if (p.f.decay) score = (float)((double)sim + p.f.bias * my_decay);
-      else score = (float)sim;
+      Acc total = reduce8(acc, lane);
+      // epilogue: similarity, decay, key
+      float score;
+      if (MC == 0) {
+        total = total * my_inv;
+        if (p.f.decay) score = (float)((double)total + p.f.bias * my_decay);
+        else score = (float)total;
+      } else {
+        Acc dist = (MC == 1) ? sqrt_of(total) : total;
+        Acc sim = Acc(1) / (Acc(1) + dist);
+        if (p.f.decay) score = (float)((double)sim + p.f.bias * my_decay);
+        else score = (float)sim;
+      }
+      const uint64_t key = make_key(score, (uint32_t)mrow);
+      wl.push(rep && mine_kept && key > wl.tau, key, lane, s_tau, p.tau);
     }
-    const uint64_t key = make_key(score, (uint32_t)mrow);
-    wl.push(rep && mine_kept && key > wl.tau, key, lane, s_tau, p.tau);
   }
 
   cta_merge_and_store<KP>(s_lists, wl, lane, warp, s_tau, p.tau, p.cand + (int64_t)blockIdx.x * KP);
@@ -314,6 +332,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_kernel(Hamming
   const int64_t wstride = (int64_t)gridDim.x * kSweepWarps;
   const int64_t hi = p.f.hi < p.n ? p.f.hi : p.n;
   int since_refresh = 0;
+  const bool single_vec = p.nvec <= lpr;
+  const uint4 my_q = (sub < p.nvec) ? s_q[sub] : make_uint4(0, 0, 0, 0);
 
   for (int64_t g = (int64_t)blockIdx.x * kSweepWarps + warp; g < ngroups; g += wstride) {
     {
@@ -334,16 +354,36 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_kernel(Hamming
       bool k = row >= p.f.lo && row < hi;
       if (k && p.f.mask) k = (p.f.mask[row >> 5] >> (row & 31)) & 1u;
       kept[r] = k;
-      int dsum = 0;
-      if (k) {
-        const uint4* rowp = reinterpret_cast<const uint4*>(p.bits) + row * p.nvec;
-        for (int c = sub; c < p.nvec; c += lpr) {
-          uint4 v = ld_stream16(rowp + c);
-          uint4 q = s_q[c];
-          dsum += __popc(v.x ^ q.x) + __popc(v.y ^ q.y) + __popc(v.z ^ q.z) + __popc(v.w ^ q.w);
-        }
+    }
+    if (single_vec) {
+      // one 16-byte vector per lane per row: issue all kPasses loads before the first popcount
+      uint4 v[kPasses];
+#pragma unroll
+      for (int r = 0; r < kPasses; ++r) {
+        const int64_t row = row0 + (int64_t)r * rpp + slot;
+        v[r] = (kept[r] && sub < p.nvec) ? ld_stream16(reinterpret_cast<const uint4*>(p.bits) + row * p.nvec + sub)
+                                         : make_uint4(0, 0, 0, 0);
       }
-      diff[r] = dsum;
+#pragma unroll
+      for (int r = 0; r < kPasses; ++r) {
+        const uint4 q = (kept[r] && sub < p.nvec) ? my_q : make_uint4(0, 0, 0, 0);
+        diff[r] = __popc(v[r].x ^ q.x) + __popc(v[r].y ^ q.y) + __popc(v[r].z ^ q.z) + __popc(v[r].w ^ q.w);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kPasses; ++r) {
+        const int64_t row = row0 + (int64_t)r * rpp + slot;
+        int dsum = 0;
+        if (kept[r]) {
+          const uint4* rowp = reinterpret_cast<const uint4*>(p.bits) + row * p.nvec;
+          for (int c = sub; c < p.nvec; c += lpr) {
+            uint4 v = ld_stream16(rowp + c);
+            uint4 q = s_q[c];
+            dsum += __popc(v.x ^ q.x) + __popc(v.y ^ q.y) + __popc(v.z ^ q.z) + __popc(v.w ^ q.w);
+          }
+        }
+        diff[r] = dsum;
+      }
     }
 #pragma unroll
     for (int r = 0; r < kPasses; ++r) {

@@ -1,0 +1,95 @@
+"""Row sharding on real GPUs.  With one GPU: two shards live on the same device and are merged through
+hdb_merge_topk (the 'no cluster' fake of SURVEY.md section 4).  With >= 2 GPUs: one process per GPU over NCCL."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import canonical as K
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_shards_one_gpu_merge():
+    import torch
+    import hyperdb_b200 as hb
+    from hyperdb_b200.sharded import CudaEngine, shard_bounds
+    rng = np.random.default_rng(7)
+    n, d = 30011, 64
+    V = rng.standard_normal((n, d)).astype(np.float16)
+    V[20000] = V[3]                                         # tie across the shard boundary -> lower id first
+    Q = rng.standard_normal((4, d)).astype(np.float16)
+    Q[1] = V[3]
+    ts = 1.7e9 + rng.uniform(0, 5, n)
+    for metric in ("dot_product", "cosine_similarity", "manhattan_distance", "hamming_distance"):
+        engines, parts = [], []
+        for r in range(2):
+            lo, hi = shard_bounds(n, 2, r)
+            m = hb.DeviceMatrix(V[lo:hi], row_offset=lo)
+            m.set_timestamps(ts[lo:hi])
+            engines.append(CudaEngine(m))
+        ref = max(e.kept_ts_max()[0] for e in engines)
+        for e in engines:
+            e.set_decay_reference(ref)
+            parts.append(e.local_topk(torch.as_tensor(Q), 10, metric, 0.25))
+        gathered = torch.stack(parts)
+        idx, sc, cnt, flags = engines[0].merge(gathered, len(Q), 10)
+        if (flags.cpu().numpy() & 8).any():                 # certificate failed somewhere: repair like ShardedMatrix.query
+            parts = [e.local_topk(torch.as_tensor(Q), 10, metric, 0.25, exact=True) for e in engines]
+            idx, sc, cnt, flags = engines[0].merge(torch.stack(parts), len(Q), 10)
+            assert not (flags.cpu().numpy() & 8).any()
+        idx, sc = idx.cpu().numpy(), sc.cpu().numpy()
+        for b in range(len(Q)):
+            oi, os_ = K.rank(V, Q[b], 10, metric, ts, 0.25)
+            assert list(idx[b]) == list(oi), (metric, b)
+            np.testing.assert_allclose(sc[b], os_, rtol=1e-14)
+        for e in engines:
+            e.m.close()
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "local-hyperdb_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import hyperdb_b200 as hb
+    from hyperdb_b200.sharded import CudaEngine, ShardedMatrix, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rng = np.random.default_rng(3)
+    n, d = 200_003, 128
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((2, d)).astype(np.float32)
+    ts = 1.7e9 + rng.uniform(0, 5, n)
+    keep = rng.random(n) < 0.5
+    lo, hi = shard_bounds(n, world, rank)
+    m = hb.DeviceMatrix(V[lo:hi], device=rank, row_offset=lo)
+    m.set_timestamps(ts[lo:hi])
+    m.set_mask(keep[lo:hi])
+    sm = ShardedMatrix(CudaEngine(m), n)
+    sm.refresh_decay()
+    assert sm.total_kept() == int(keep.sum())
+    for metric in ("cosine_similarity", "euclidean_metric", "hamming_distance"):
+        idx, sc, cnt = sm.query(Q, 10, metric, 0.3)
+        for b in range(len(Q)):
+            oi, os_ = K.rank(V, Q[b], 10, metric, ts, 0.3, keep)
+            assert list(idx[b]) == list(oi), (metric, b)
+            np.testing.assert_allclose(sc[b], os_, rtol=1e-5)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def test_nccl_world(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    mp.spawn(_nccl_worker, args=(world, 29733, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))

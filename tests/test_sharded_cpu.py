@@ -1,0 +1,72 @@
+"""Host logic of the row-sharded path under torch.distributed/gloo, world_size 2, no GPU:
+shard bounds, message packing, the single all-gather, the decay all-reduce(MAX) over kept rows, the
+uncertified-flag repair branch.  The local engine is the oracle (tests/sharding_fakes.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hyperdb_b200.sharded import ShardedMatrix, packed_len, shard_bounds
+from oracle import canonical as K
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 8, 1000, 10_000_000, 100_000_003):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_packed_len():
+    assert packed_len(1, 10) == 22 and packed_len(3, 4) == 24 + 3 + 2
+
+
+def _worker(rank, world, port, fail_first, result_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.join(here, "golden"), os.path.dirname(here), os.path.join(os.path.dirname(here), "local-hyperdb_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from sharding_fakes import OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(42)
+    n, d = 1001, 24
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    V[500] = V[10]                      # an exact tie across the shard boundary
+    Q = rng.standard_normal((3, d)).astype(np.float32)
+    Q[0] = V[10]
+    ts = 1.7e9 + rng.uniform(0, 9, n)
+    keep = rng.random(n) < 0.7
+    lo, hi = shard_bounds(n, world, rank)
+    eng = OracleEngine(V[lo:hi], lo, ts[lo:hi], keep[lo:hi], fail_first=fail_first)
+    sm = ShardedMatrix(eng, n)
+    ref = sm.refresh_decay()
+    assert ref == ts[keep].max()
+    assert sm.total_kept() == int(keep.sum())
+    for metric in ("cosine_similarity", "euclidean_metric", "hamming_distance"):
+        idx, sc, cnt = sm.query(Q, 7, metric, 0.3)
+        for b in range(len(Q)):
+            oi, os_ = K.rank(V, Q[b], 7, metric, ts, 0.3, keep)
+            assert list(idx[b]) == list(oi), (metric, b)
+            assert np.array_equal(sc[b], os_)
+            assert cnt[b] == 7
+    assert sm.exchanges == (6 if fail_first else 3)
+    assert eng.calls == ([False, True] * 3 if fail_first else [False] * 3)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+
+
+@pytest.mark.parametrize("fail_first", [False, True])
+def test_world2_gloo(tmp_path, fail_first):
+    port = 29600 + (os.getpid() % 200) + (50 if fail_first else 0)
+    mp.spawn(_worker, args=(2, port, fail_first, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
