@@ -399,6 +399,130 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_kernel(Hamming
   cta_merge_and_store<KP>(s_lists, wl, lane, warp, s_tau, p.tau, p.cand + (int64_t)blockIdx.x * KP);
 }
 
+// Fast form for rows of at most 32 vectors (d <= 4096): LPR (compile time) lanes share a row, a warp takes one
+// 32-row window (one mask word) per iteration, every lane issues min(LPR,8) independent 16-byte loads, and the
+// per-lane popcounts are reduced with a TRANSPOSING butterfly so that every lane ends up owning the total
+// of one distinct row: one ballot/push per round instead of one per row group.
+template <int PPR, int LPR>
+__device__ __forceinline__ int transpose_reduce(int (&v)[PPR], int sub) {
+#pragma unroll
+  for (int o = LPR / 2; o >= PPR && o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < PPR; ++i) v[i] += __shfl_xor_sync(kFull, v[i], o);
+  }
+  int n = PPR;
+#pragma unroll
+  for (int o = PPR / 2; o >= 1; o >>= 1) {
+    const bool up = sub & o;
+    const int half = n / 2;
+#pragma unroll
+    for (int i = 0; i < PPR / 2; ++i) {
+      if (i < half) {
+        const int send = up ? v[i] : v[i + half];
+        const int keep = up ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(kFull, send, o);
+      }
+    }
+    n = half;
+  }
+  return v[0];                       // total of pass (sub & (PPR-1))
+}
+
+template <int KP, int LPR>
+__global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_lpr_kernel(HammingParams p) {
+  constexpr int kCap = ListCfg<KP>::kCap;
+  constexpr int PPR = LPR < 8 ? LPR : 8;       // passes per round = loads in flight per lane
+  constexpr int ROUNDS = LPR / PPR;
+  constexpr int RPP = 32 / LPR;                // rows per pass
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* s_lists = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(s_lists + kSweepWarps * kCap);
+  uint4* s_q = reinterpret_cast<uint4*>(s_tau + 2);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) *s_tau = 0;
+  for (int j = threadIdx.x; j < p.nvec; j += kSweepThreads) s_q[j] = reinterpret_cast<const uint4*>(p.qbits)[j];
+  __syncthreads();
+
+  WarpList<KP> wl;
+  wl.buf = s_lists + warp * kCap;
+  wl.cnt = 0;
+  wl.tau = 0;
+
+  const int sub = lane % LPR, slot = lane / LPR;
+  const bool lane_has = sub < p.nvec;
+  const uint4 my_q = lane_has ? s_q[sub] : make_uint4(0, 0, 0, 0);
+  const bool rep = sub < PPR;
+  const int my_pass = sub & (PPR - 1);
+  const int64_t nwin = (p.n + 31) / 32;
+  const int64_t wstride = (int64_t)gridDim.x * kSweepWarps;
+  const uint4* vbits = reinterpret_cast<const uint4*>(p.bits);
+  int since_refresh = 0;
+  const int64_t g0 = (int64_t)blockIdx.x * kSweepWarps + warp;
+  uint32_t next_bits = (g0 < nwin) ? window_keep_bits(p.f, g0, p.n) : 0u;
+
+  for (int64_t g = g0; g < nwin; g += wstride) {
+    const uint32_t bits = next_bits;
+    next_bits = (g + wstride < nwin) ? window_keep_bits(p.f, g + wstride, p.n) : 0u;
+    if (bits == 0) continue;
+    {
+      unsigned long long t = *reinterpret_cast<volatile unsigned long long*>(s_tau);
+      if (++since_refresh >= 8) {
+        since_refresh = 0;
+        unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(p.tau);
+        if (gt > t) { t = gt; if (lane == 0) atomicMax(s_tau, gt); }
+      }
+      if (t > wl.tau) wl.tau = t;
+    }
+    const int64_t row0 = g * 32;
+#pragma unroll
+    for (int round = 0; round < ROUNDS; ++round) {
+      const int my_loc = (round * PPR + my_pass) * RPP + slot;        // the row this lane will own after the reduce
+      const bool my_kept = (bits >> my_loc) & 1u;
+      double my_decay = 0.0;
+      if (p.f.decay && rep && my_kept) my_decay = p.f.decay[row0 + my_loc];
+      uint4 v[PPR];
+#pragma unroll
+      for (int r = 0; r < PPR; ++r) {
+        const int loc = (round * PPR + r) * RPP + slot;
+        const bool k = ((bits >> loc) & 1u) && lane_has;
+        v[r] = k ? ld_stream16(vbits + (row0 + loc) * p.nvec + sub) : my_q;      // dropped rows: xor = 0
+      }
+      int cnt[PPR];
+#pragma unroll
+      for (int r = 0; r < PPR; ++r)
+        cnt[r] = __popc(v[r].x ^ my_q.x) + __popc(v[r].y ^ my_q.y) + __popc(v[r].z ^ my_q.z) + __popc(v[r].w ^ my_q.w);
+      const int diff = transpose_reduce<PPR, LPR>(cnt, sub);
+      float score = (float)((int)p.d - diff);
+      if (p.f.decay) score = (float)((double)score + p.f.bias * my_decay);
+      const uint64_t key = make_key(score, (uint32_t)(row0 + my_loc));
+      wl.push(rep && my_kept && key > wl.tau, key, lane, s_tau, p.tau);
+    }
+  }
+  cta_merge_and_store<KP>(s_lists, wl, lane, warp, s_tau, p.tau, p.cand + (int64_t)blockIdx.x * KP);
+}
+
+template <int KP, int LPR>
+static int launch_hamming_lpr(const HammingParams& hp, int grid, size_t smem, cudaStream_t s) {
+  auto kern = sweep_hamming_lpr_kernel<KP, LPR>;
+  if (smem > 48 * 1024) HDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kSweepThreads, smem, s>>>(hp);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int KP>
+static int launch_hamming_kp(const HammingParams& hp, int grid, size_t smem, cudaStream_t s) {
+  switch (hp.lpr) {
+    case 1: return launch_hamming_lpr<KP, 1>(hp, grid, smem, s);
+    case 2: return launch_hamming_lpr<KP, 2>(hp, grid, smem, s);
+    case 4: return launch_hamming_lpr<KP, 4>(hp, grid, smem, s);
+    case 8: return launch_hamming_lpr<KP, 8>(hp, grid, smem, s);
+    case 16: return launch_hamming_lpr<KP, 16>(hp, grid, smem, s);
+    default: return launch_hamming_lpr<KP, 32>(hp, grid, smem, s);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -448,6 +572,7 @@ int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t
     hp.f = f; hp.cand = out.cand; hp.tau = out.tau;
     size_t smem = list_smem(kp) + (size_t)hp.nvec * 16;
     if (smem > 200 * 1024) return fail("sweep: dimension too large for the fused hamming pass");
+    if (hp.nvec <= 32) return kp <= 32 ? launch_hamming_kp<32>(hp, out.grid, smem, s) : launch_hamming_kp<128>(hp, out.grid, smem, s);
     if (kp <= 32) {
       if (smem > 48 * 1024) HDB_CUDA(cudaFuncSetAttribute(sweep_hamming_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       sweep_hamming_kernel<32><<<out.grid, kSweepThreads, smem, s>>>(hp);

@@ -194,6 +194,26 @@ def test_fused_equals_exact(hb, vdt, metric, n, d, kind):
         assert fallbacks == 0, "fused pass should certify on well-separated data"
 
 
+@pytest.mark.parametrize("d", [130, 600, 1100, 2500, 4200])
+def test_hamming_wide_rows(hb, d):
+    """every lanes-per-row class of the bit-packed sweep (d <= 4096) and the generic form above it"""
+    rng = np.random.default_rng(d)
+    n = 40000
+    V = rng.standard_normal((n, d)).astype(np.float16)
+    q = rng.standard_normal(d).astype(np.float16)
+    keep = rng.random(n) < 0.8
+    m = hb.DeviceMatrix(V)
+    try:
+        for use_mask in (False, True):
+            m.set_mask(keep if use_mask else None)
+            idx, sc, cnt, flags = m.query(q, 16, "hamming_distance")
+            assert not (flags[0] & 1)
+            oi, os_ = K.rank(V, q, 16, "hamming_distance", keep=keep if use_mask else None)
+            assert list(idx[0]) == list(oi) and np.array_equal(sc[0], os_)
+    finally:
+        m.close()
+
+
 def test_range_and_batch(hb):
     rng = np.random.default_rng(5)
     V = rng.standard_normal((5000, 64)).astype(np.float32)
