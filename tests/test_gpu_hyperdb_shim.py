@@ -1,0 +1,53 @@
+"""The host shim `hyperdb_b200.hyperdb.HyperDB.query` against runs of the REAL HyperDB class
+(tests/golden/hyperdb_tail.npz: recency applied twice, skip_doc ranges, metadata masks, float64 query)."""
+import numpy as np
+import pytest
+
+import golden_io as G
+
+pytestmark = pytest.mark.gpu
+
+
+def test_query_matches_real_hyperdb(capsys):
+    from hyperdb_b200.hyperdb import HyperDB
+    z, specs = G.load_tail()
+    V, ts, queries, groups = z["V"], z["ts"], z["queries"], z["groups"]
+    docs = [{"id": i, "group": str(groups[i]), "timestamp": float(ts[i])} for i in range(len(V))]
+    db = HyperDB(documents=docs, vectors=V, metadata_keys=["group", "timestamp"], fp_precision="float32")
+    try:
+        for si, spec in enumerate(specs):
+            filters = [tuple(f) if f[0] == "skip_doc" else (f[0], f[1]) for f in spec["filters"]] if spec["filters"] else None
+            for qi in range(len(queries)):
+                res = db.query(queries[qi], top_k=spec["top_k"], filters=filters, recency_bias=spec["recency_bias"],
+                               timestamp_key="timestamp" if spec["recency_bias"] else None, metric=spec["metric"])
+                ids = [doc["id"] for doc, _s, _i in res]
+                sc = np.array([s for _d, s, _i in res])
+                assert ids == list(z[f"ids_{si}_{qi}"]), (si, qi)
+                blas = spec["metric"] in ("dot_product", "cosine_similarity")
+                np.testing.assert_allclose(sc, z[f"sc_{si}_{qi}"], rtol=1e-12 if blas else 1e-15)
+                assert all(i == d["id"] for d, _s, i in res)
+        assert "Bruteforce method used instead" in capsys.readouterr().out      # tests/test_hyperdb.py:619-626 greps this
+        assert [d["id"] for d in db.query(queries[0], top_k=3, return_similarities=False)] == list(z["ids_0_0"][:3])
+        assert db.query(query_vector=queries[0], top_k=2)[0][0]["id"] == z["ids_0_0"][0]
+        with pytest.raises(ValueError):
+            db.query(queries[0], metric="nope")
+        with pytest.raises(ValueError):
+            db.query(queries[0][:5])
+        with pytest.raises(ValueError):
+            db.query(queries[0], recency_bias=0.5, timestamp_key="missing")
+    finally:
+        db.close()
+
+
+def test_add_remove_roundtrip():
+    from hyperdb_b200.hyperdb import HyperDB
+    rng = np.random.default_rng(0)
+    V = rng.standard_normal((50, 16)).astype(np.float32)
+    docs = [{"id": i} for i in range(50)]
+    db = HyperDB(documents=docs[:30], vectors=V[:30])
+    db.add(docs[30:], vectors=V[30:])
+    assert db.size() == 50
+    assert db.query(V[41], top_k=1)[0][0]["id"] == 41
+    db.remove_document(41)
+    assert db.size() == 49 and db.query(V[41], top_k=1)[0][0]["id"] != 41
+    db.close()
