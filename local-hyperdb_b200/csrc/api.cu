@@ -56,6 +56,9 @@ struct hdb_matrix {
   void* sort_scratch = nullptr; size_t sort_scratch_bytes = 0;
   unsigned long long* misc = nullptr;   // [2] ordered max bits, count
   float* stats = nullptr; int* nan_flag = nullptr;
+  // tensor-core batched path workspace
+  TcWorkspace tc{};
+  int64_t tc_nq = 0;
   // per-launch event pairs around the dominant kernel (hdb_profile_*)
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
@@ -138,7 +141,8 @@ int hdb_matrix_destroy(hdb_matrix* m) {
   if (m->owns_rows) cudaFree(m->rows);
   void* ptrs[] = {m->norms, m->inv_norms, m->bits, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
                   m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_block,
-                  m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag};
+                  m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag, m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand,
+                  m->tc.cand_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (m->h_block) cudaFreeHost(m->h_block);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
@@ -371,6 +375,54 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
   a.qb.qc += b0 * m->d; a.qb.qbits += b0 * m->words; a.qb.qnorm += b0; a.qb.qflags += b0;
   a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
   a.uncertified = m->uncertified;
+  a.cand_count = nullptr; a.cand_stride = 0; a.tau0 = nullptr; a.extra_flags = 0;
+  return launch_finalize(a, cnt, m->stream);
+}
+
+constexpr int64_t kTcChunk = 4096;       // queries per tensor-core batch (bounds the sample / candidate workspaces)
+
+static int ensure_tc_workspace(hdb_matrix* m, int64_t nq, int kp) {
+  const int64_t all_tiles = (m->n + 127) / 128;
+  int64_t sample_tiles = all_tiles / 8;
+  if (sample_tiles > 512) sample_tiles = 512;
+  if (sample_tiles < 1) sample_tiles = 1;
+  int64_t cap = 1024;
+  const int64_t expect = 2 * m->n * kp / (sample_tiles * 128);
+  while (cap < expect && cap < 65536) cap <<= 1;
+  if (m->tc_nq >= nq && m->tc.cap >= cap && m->tc.sample_tiles == sample_tiles) return 0;
+  void* ptrs[] = {m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand, m->tc.cand_count};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  m->tc = TcWorkspace{};
+  m->tc_nq = 0;
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.q16), (size_t)nq * m->d * 2));
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.dense), (size_t)nq * sample_tiles * 128 * 4));
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.tau0), (size_t)nq * 4));
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.cand), (size_t)nq * cap * 8));
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.cand_count), (size_t)nq * 4));
+  m->tc.cap = (int)cap;
+  m->tc.sample_tiles = sample_tiles;
+  m->tc_nq = nq;
+  return 0;
+}
+
+// Tensor-core batched path for queries [b0, b0+cnt): sample -> thresholds -> select, then the same finalize.
+static int run_tensor(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int64_t cnt, int64_t k, const RowFilter& f,
+                      int64_t* idx, double* score, int64_t* count, uint32_t* flags) {
+  MatrixView v = view_of(m);
+  HDB_TRY(ensure_tc_workspace(m, cnt < kTcChunk ? cnt : kTcChunk, kp));
+  const float* qa = reinterpret_cast<const float*>(m->qb.qa) + (size_t)b0 * m->d;
+  const bool prof = m->prof_used + 2 <= m->prof_ev.size();
+  if (prof) HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used], m->stream));
+  HDB_TRY(launch_batched_tc(v, metric, f, qa, cnt, kp, m->device, m->tc, m->stream));
+  if (prof) { HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used + 1], m->stream)); m->prof_used += 2; }
+  FinalizeArgs a;
+  a.m = v; a.f = f; a.metric = metric; a.rdt = rdt; a.kp = kp; a.k = (int)k; a.n_kept = m->n_kept; a.grid = 0;
+  a.cand = m->tc.cand; a.tau = nullptr;
+  a.qb = m->qb;
+  a.qb.qc += b0 * m->d; a.qb.qbits += b0 * m->words; a.qb.qnorm += b0; a.qb.qflags += b0;
+  a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
+  a.uncertified = m->uncertified;
+  a.cand_count = m->tc.cand_count; a.cand_stride = m->tc.cap; a.tau0 = m->tc.tau0; a.extra_flags = HDB_FLAG_TENSOR;
   return launch_finalize(a, cnt, m->stream);
 }
 
@@ -425,6 +477,12 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   if (k == 0) {
     HDB_CUDA(cudaMemsetAsync(count, 0, (size_t)nq * 8, m->stream));
     if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
+  } else if (kp && m->path_mode != 2 && batched_tc_supported(view_of(m), metric, q_dtype, nq)) {
+    HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
+    for (int64_t b0 = 0; b0 < nq; b0 += kTcChunk) {
+      const int64_t cnt = nq - b0 < kTcChunk ? nq - b0 : kTcChunk;
+      HDB_TRY(run_tensor(m, metric, rdt, kp, b0, cnt, k, f, idx, score, count, flags));
+    }
   } else if (kp) {
     HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
     for (int64_t b0 = 0; b0 < nq; b0 += kChunk) {

@@ -1,0 +1,445 @@
+// Batched dot / cosine as a tcgen05 tensor-core contraction with a fused threshold-select epilogue.
+//
+// Replaces B independent calls of np.dot(vectors, q) (hyperdb/ranking_algorithm.py:29,41; the reference has no
+// batched API) by S[row, b] = sum_d V[row, d] * Q[b, d] on the 5th-generation tensor cores:
+//   * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a 4-stage shared-memory ring,
+//   * tcgen05.mma (M = 128 rows x N = BN queries x K = 16) issued by one elected thread, fp32 accumulators in
+//     TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1,
+//   * epilogue warps read TMEM with tcgen05.ld (thread = row, registers = queries), apply the cosine inverse
+//     norm / time decay / keep mask, and either
+//       - DENSE mode: write the scores of a strided row SAMPLE query-major (coalesced) so that a per-query
+//         threshold tau0[b] = KP-th best of the sample can be selected, or
+//       - SELECT mode: append (score, row) keys with score >= tau0[b] to a per-query candidate buffer.
+//     The N x B score matrix is never written.  finalize.cu then re-scores the best KP candidates of every query
+//     in the reference's exact arithmetic and certifies the top-k exactly as for the streaming sweep.
+// Tile order: query tile fastest, so the CTAs running at the same time share the V row tile through L2 and the
+// matrix is read from HBM once; Q stays L2 resident.
+#include <cuda.h>
+
+#include "hdb_common.cuh"
+#include "hdb_internal.h"
+#include "../../include/hyperdb_b200.h"
+
+namespace hdb {
+
+constexpr int kTcEpiWarps = 8;           // two epilogue warps per TMEM lane quarter, each takes half of the columns
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, rest: epilogue
+constexpr int kTcStages = 4;
+constexpr int kTileM = 128;
+constexpr int kTileKBytes = 128;         // one 128-byte swizzle span of K per stage row
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);      // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// kind::f16 / kind::tf32 instruction descriptor: fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool tf32) {
+  return (1u << 4) | ((tf32 ? 2u : 0u) << 7) | ((tf32 ? 2u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+  int64_t n, d;                 // shard rows, dim
+  int64_t nq;                   // queries in this batch (padded to BN by TMA zero fill)
+  int64_t n_tiles_m, n_tiles_q; // row tiles visited (all, or the sample), query tiles
+  int64_t sample_stride;        // DENSE mode: visited row tile i is matrix row tile i * sample_stride
+  const char* rows;             // matrix base (for the L2 prefetch)
+  const float* inv_norms;       // cosine or nullptr
+  RowFilter f;
+  // DENSE mode
+  float* dense;                 // [nq][n_tiles_m * 128] totals of the sample (dropped rows = -inf)
+  // SELECT mode
+  const float* tau0;            // [nq]
+  uint64_t* cand;               // [nq][cap]
+  unsigned* cand_count;         // [nq]
+  int cap;
+};
+
+template <int BN, bool TF32, bool DENSE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_q, TcParams p) {
+  constexpr int kABytes = kTileM * kTileKBytes;          // 16 KB
+  constexpr int kBBytes = BN * kTileKBytes;              // up to 32 KB
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kKPerStage = kTileKBytes / (TF32 ? 4 : 2);     // elements of K per stage
+  constexpr uint32_t kIdesc = make_idesc(kTileM, BN, TF32);
+  constexpr int kTmemCols = 2 * BN;                      // two accumulator buffers (power of two >= 32)
+
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  // the 128-byte swizzle atoms must start on 1024-byte boundaries
+  unsigned char* stage_base = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + kTcStages * kStageBytes);
+  uint64_t* empty = full + kTcStages;
+  uint64_t* acc_full = empty + kTcStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_tau = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full) + 128);   // [2][BN], 16-byte aligned
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (int)((p.d + kKPerStage - 1) / kKPerStage);
+  const int64_t total_tiles = p.n_tiles_m * p.n_tiles_q;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kTcEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int64_t row_bytes = p.d * (TF32 ? 4 : 2);
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int64_t mt = (t / p.n_tiles_q) * p.sample_stride;
+        const int64_t qt = t % p.n_tiles_q;
+        {
+          // The TMA boxes below gather 128-byte pieces of 128 rows (poor DRAM locality when they miss L2).  The
+          // row tile itself is ONE contiguous region, so stream it into L2 one tile ahead with a bulk prefetch; the
+          // CTAs that share the next row tile (one per query tile) each prefetch their slice of it.
+          const int64_t tn = t + gridDim.x;
+          if (tn < total_tiles) {
+            const int64_t mtn = (tn / p.n_tiles_q) * p.sample_stride, qtn = tn % p.n_tiles_q;
+            const int64_t rows_n = (p.n - mtn * kTileM) < kTileM ? (p.n - mtn * kTileM) : kTileM;
+            const int64_t region = rows_n * row_bytes;
+            int64_t slice = ((region / p.n_tiles_q) + 15) & ~int64_t(15);
+            int64_t off = qtn * slice;
+            if (off < region) {
+              if (off + slice > region) slice = (region - off) & ~int64_t(15);
+              if (slice > 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rows + mtn * kTileM * row_bytes + off), "r"((uint32_t)slice) : "memory");
+            }
+          }
+        }
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = stage_base + stage * kStageBytes;
+          mbar_expect_tx(&full[stage], kStageBytes);
+          tma_load_2d(sa, &map_v, &full[stage], kb * kKPerStage, (int)(mt * kTileM));
+          tma_load_2d(sa + kABytes, &map_q, &full[stage], kb * kKPerStage, (int)(qt * BN));
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kTileKBytes / 32; ++k)      // 32 bytes of K per MMA (16 halves / 8 tf32)
+            umma<TF32>(tmem_c, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) ? 1u : 0u);
+          tcgen05_commit(&empty[stage]);                   // frees the stage when these MMAs retire
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&acc_full[acc]);                    // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ep_tid = (warp - 2) * 32 + lane;             // 0..255 for cooperative loads
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int64_t mt_visit = t / p.n_tiles_q;
+      const int64_t mt = mt_visit * p.sample_stride;
+      const int64_t qt = t % p.n_tiles_q;
+      const int64_t row = mt * kTileM + quarter * 32 + lane;
+      // per-row side inputs; a dropped row gets dec = NaN so that every comparison below is false
+      bool kept = row < p.n && row >= p.f.lo && row < p.f.hi;
+      if (kept && p.f.mask) kept = (p.f.mask[row >> 5] >> (row & 31)) & 1u;
+      float inv = 0.f, dec = __int_as_float(0x7fc00000);
+      if (kept) {
+        inv = p.inv_norms ? p.inv_norms[row] : 1.f;
+        dec = p.f.decay ? (float)(p.f.bias * p.f.decay[row]) : 0.f;
+      }
+      const int64_t valid = (p.nq - qt * BN) < BN ? (p.nq - qt * BN) : BN;       // real queries in this tile
+      const int c_begin = half * (BN / 2);
+      const int c_end = (int)(valid < (half + 1) * (BN / 2) ? valid : (half + 1) * (BN / 2));
+      if (!DENSE) {
+        // thresholds of this query tile -> shared memory (double buffered with the accumulator)
+        for (int c = ep_tid; c < BN; c += 32 * kTcEpiWarps) {
+          const int64_t b = qt * BN + c;
+          s_tau[acc * BN + c] = b < p.nq ? p.tau0[b] : INFINITY;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kTcEpiWarps) : "memory");     // epilogue warps only
+      }
+      mbar_wait(&acc_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        if (DENSE) {
+          const int64_t ld = p.n_tiles_m * kTileM;
+          const int64_t col = mt_visit * kTileM + quarter * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t b = qt * BN + c0 + j;
+            if (b < p.nq) {
+              float s = fmaf(__uint_as_float(r[j]), inv, dec);
+              p.dense[b * ld + col] = (s == s) ? s : -INFINITY;
+            }
+          }
+        } else {
+          const float4* tq = reinterpret_cast<const float4*>(&s_tau[acc * BN + c0]);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 tv = tq[j4];
+            const float th[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float s = fmaf(__uint_as_float(r[j4 * 4 + u]), inv, dec);
+              if (s >= th[u]) {
+                const int64_t b = qt * BN + c0 + j4 * 4 + u;
+                const unsigned pos = atomicAdd(&p.cand_count[b], 1u);
+                if (pos < (unsigned)p.cap) p.cand[b * p.cap + pos] = make_key(s, (uint32_t)row);
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tau0[b] = KP-th largest of the dense sample row of query b (8-bit radix select on the ordered bits);
+// fewer than KP finite values -> -inf (everything passes).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_threshold_kernel(const float* dense, int64_t ld, int kp, float* tau0) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned sel[2];
+  const float* v = dense + (int64_t)blockIdx.x * ld;
+  uint32_t prefix = 0, pmask = 0;
+  unsigned need = (unsigned)kp;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < ld; i += 256) {
+      const uint32_t o = order_f32(v[i]);
+      if ((o & pmask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned cum = 0;
+      int chosen = 0;
+      for (int bin = 255; bin >= 0; --bin) {
+        if (cum + hist[bin] >= need) { chosen = bin; break; }
+        if (bin > 0) cum += hist[bin];
+      }
+      sel[0] = (unsigned)chosen;
+      sel[1] = need - cum;
+    }
+    __syncthreads();
+    prefix |= sel[0] << shift;
+    pmask |= 0xffu << shift;
+    need = sel[1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tau0[blockIdx.x] = unorder_f32(prefix);
+}
+
+// fp16 copy of the prepared (accumulate-type) queries: the tensor-core B operand
+__global__ void queries_to_half_kernel(const float* qa, __half* q16, int64_t count) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    q16[i] = __float2half_rn(qa[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, bool tf32, int64_t rows, int64_t d, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  const int esz = tf32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(kTileKBytes / esz), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  return 0;
+}
+
+template <int BN, bool TF32, bool DENSE>
+static int launch_tc(const CUtensorMap& mv, const CUtensorMap& mq, const TcParams& p, int grid, cudaStream_t s) {
+  auto kern = batched_tc_kernel<BN, TF32, DENSE>;
+  const size_t smem = (size_t)kTcStages * (kTileM + BN) * kTileKBytes + 16 * 8 + 16 + 2 * BN * 4 + 1024;
+  HDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kTcThreads, smem, s>>>(mv, mq, p);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq) {
+  if (metric != HDB_DOT && metric != HDB_COSINE) return 0;
+  if (m.dtype != 0) return 0;                                  // fp16 storage (tf32 for fp32 storage: next)
+  if (q_dtype != 0) return 0;                                  // the B operand is fp16: only exact for fp16 queries
+  if ((m.d * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(m.rows) & 15)) return 0;
+  if (m.n < 8 * 65536 || nq < 16) return 0;                    // small problems: the sweep loop is fine
+  if (m.n >= (int64_t(1) << 31)) return 0;
+  return 1;
+}
+
+// Runs sample -> thresholds -> select for queries [0, nq) of the prepared batch.  Candidate keys land in
+// ws.cand[b][0..min(count, cap)).
+int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const float* qa, int64_t nq, int kp, int device,
+                      const TcWorkspace& ws, cudaStream_t s) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int64_t count = nq * m.d;
+  queries_to_half_kernel<<<(unsigned)((count + 255) / 256 > 4096 ? 4096 : (count + 255) / 256), 256, 0, s>>>(qa, ws.q16, count);
+  HDB_LAUNCHED();
+  CUtensorMap mv, mq;
+  HDB_TRY(make_map(&mv, m.rows, false, m.n, m.d, kTileM));
+  const int BN = nq <= 64 ? 64 : (nq <= 128 ? 128 : 256);
+  HDB_TRY(make_map(&mq, ws.q16, false, nq, m.d, BN));
+  TcParams p;
+  p.n = m.n; p.d = m.d; p.nq = nq;
+  p.n_tiles_q = (nq + BN - 1) / BN;
+  p.rows = reinterpret_cast<const char*>(m.rows);
+  p.inv_norms = metric == HDB_COSINE ? reinterpret_cast<const float*>(m.inv_norms) : nullptr;
+  p.f = f;
+  const int64_t all_tiles = (m.n + kTileM - 1) / kTileM;
+  // ---- dense sample
+  p.n_tiles_m = ws.sample_tiles;
+  p.sample_stride = all_tiles / ws.sample_tiles;
+  p.dense = ws.dense; p.tau0 = nullptr; p.cand = nullptr; p.cand_count = nullptr; p.cap = 0;
+  if (BN == 64) HDB_TRY((launch_tc<64, false, true>(mv, mq, p, sms, s)));
+  else if (BN == 128) HDB_TRY((launch_tc<128, false, true>(mv, mq, p, sms, s)));
+  else HDB_TRY((launch_tc<256, false, true>(mv, mq, p, sms, s)));
+  sample_threshold_kernel<<<(unsigned)nq, 256, 0, s>>>(ws.dense, ws.sample_tiles * kTileM, kp, ws.tau0);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  // ---- select over all rows
+  HDB_CUDA(cudaMemsetAsync(ws.cand_count, 0, (size_t)nq * 4, s));
+  p.n_tiles_m = all_tiles;
+  p.sample_stride = 1;
+  p.dense = nullptr; p.tau0 = ws.tau0; p.cand = ws.cand; p.cand_count = ws.cand_count; p.cap = ws.cap;
+  if (BN == 64) HDB_TRY((launch_tc<64, false, false>(mv, mq, p, sms, s)));
+  else if (BN == 128) HDB_TRY((launch_tc<128, false, false>(mv, mq, p, sms, s)));
+  else HDB_TRY((launch_tc<256, false, false>(mv, mq, p, sms, s)));
+  return 0;
+}
+
+}  // namespace hdb

@@ -50,7 +50,8 @@ __device__ __forceinline__ void load_batch<double>(const void* src, int64_t j0, 
 __device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) {
   const double D = (double)a.m.d + 8.0;
   const double uk = 1.1920928955078125e-7;                    // 2^-23: float32 key rounding (2x slack)
-  const double ua = (a.m.dtype == 2) ? 4.440892098500626e-16 : 1.1920928955078125e-7;   // sweep accumulate type
+  // accumulate type of the select pass; the tensor cores' fp32 accumulation is not IEEE round-to-nearest
+  const double ua = a.cand_count ? 1.9073486328125e-6 /*2^-19*/ : (a.m.dtype == 2) ? 4.440892098500626e-16 : 1.1920928955078125e-7;
   const double uR = unit_roundoff(a.rdt);
   const double uT = unit_roundoff(a.m.dtype);
   const bool decay = a.f.decay != nullptr;
@@ -190,9 +191,15 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   const uint32_t qflag = a.qb.qflags[b];
   if (tid == 0) s_count = 0;
   __syncthreads();
-  const unsigned long long tau = a.tau[b];
-  const uint64_t* cand = a.cand + b * (int64_t)a.grid * a.kp;
-  const int total = a.grid * a.kp;
+  const unsigned long long tau = a.cand_count ? 0ull : a.tau[b];
+  const uint64_t* cand = a.cand_count ? a.cand + b * a.cand_stride : a.cand + b * (int64_t)a.grid * a.kp;
+  bool overflow = false;
+  int total = a.grid * a.kp;
+  if (a.cand_count) {
+    const unsigned appended = a.cand_count[b];
+    overflow = appended > (unsigned)a.cand_stride;          // some qualifying rows were dropped: cannot certify
+    total = (int)(overflow ? (unsigned)a.cand_stride : appended);
+  }
   for (int i0 = tid; i0 < total; i0 += kFinThreads * 8) {       // 8 loads in flight per thread
     uint64_t key[8];
 #pragma unroll
@@ -325,12 +332,13 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   if (kk > 0 && a.n_kept > (int64_t)m && !exact_keys) {
     if (m < kk) certified = false;
     else {
-      const double s_edge = (double)key_score(surv[m - 1]);
+      // rows outside the candidates: key <= the KP-th key, or (batched pass, fewer than KP appended) below tau0
+      const double s_edge = (m >= a.kp || !a.tau0) ? (double)key_score(surv[m - 1]) : (double)a.tau0[b];
       const double bound = outsider_bound(s_edge, a, a.qb.qnorm[b]);
       certified = o_tot[kk - 1] > bound;
     }
   }
-  if (m < kk) certified = false;
+  if (m < kk || overflow) certified = false;
   for (int i = tid; i < a.k; i += kFinThreads) {
     const bool have = i < kk && i < m;
     a.out_idx[b * a.k + i] = have ? (int64_t)o_row[i] + a.m.row_offset : -1;
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   }
   if (tid == 0) {
     a.out_count[b] = kk;
-    if (a.out_flags) a.out_flags[b] = qflag | (certified ? 0u : kFlagUncertified);
+    if (a.out_flags) a.out_flags[b] = qflag | a.extra_flags | (certified ? 0u : kFlagUncertified);
     if (!certified) atomicAdd(a.uncertified, 1);
   }
 }

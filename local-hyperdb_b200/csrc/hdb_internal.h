@@ -1,6 +1,7 @@
 // Internal host-side declarations shared by the translation units of libhyperdb_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 
@@ -93,6 +94,11 @@ struct FinalizeArgs {
   int64_t* out_idx; double* out_score; int64_t* out_count; uint32_t* out_flags;   // device
   int* uncertified;              // device counter: queries that need the exact path
   int smem_bytes;                // dynamic shared memory of the finalize kernel (set by launch_finalize)
+  // tensor-core batched path: per-query candidate buffers instead of per-CTA lists
+  const unsigned* cand_count;    // [B] appended keys per query (may exceed cand_stride = overflow) or nullptr
+  int64_t cand_stride;           // keys per query buffer
+  const float* tau0;             // [B] select threshold of the batched pass (rows below it were never appended)
+  uint32_t extra_flags;          // OR-ed into out_flags (HDB_FLAG_TENSOR)
 };
 int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s);
 int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,
@@ -104,5 +110,19 @@ int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, 
                cudaStream_t s);
 int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, int64_t ls_rec, int64_t ls_cnt, const double* scores, const int64_t* ids,
                       const int64_t* counts, int64_t* out_idx, double* out_score, int64_t* out_count, cudaStream_t s);
+
+// ---- batched_tc.cu : tcgen05 batched contraction + threshold select
+struct TcWorkspace {
+  __half* q16;             // [nq][d] fp16 queries (B operand)
+  float* dense;            // [nq][sample_tiles*128] sample totals
+  float* tau0;             // [nq]
+  uint64_t* cand;          // [nq][cap]
+  unsigned* cand_count;    // [nq]
+  int cap;
+  int64_t sample_tiles;
+};
+int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq);
+int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const float* qa, int64_t nq, int kp, int device,
+                      const TcWorkspace& ws, cudaStream_t s);
 
 }  // namespace hdb
