@@ -38,6 +38,9 @@ WORKLOADS = {
     # name: rows, dim, dtype, metric, top_k, batch, decay/mask
     "c3_cosine_b1": dict(n=10_000_000, d=768, dtype="float16", metric="cosine_similarity", k=10, b=1),
     "c3_dot_b1": dict(n=10_000_000, d=768, dtype="float16", metric="dot_product", k=10, b=1),
+    "c3_cosine_b64": dict(n=10_000_000, d=768, dtype="float16", metric="cosine_similarity", k=10, b=64),
+    "c3_cosine_b4096": dict(n=10_000_000, d=768, dtype="float16", metric="cosine_similarity", k=10, b=4096),
+    "c3_dot_b4096": dict(n=10_000_000, d=768, dtype="float16", metric="dot_product", k=10, b=4096),
     "c2_cosine_b1": dict(n=1_000_000, d=384, dtype="float32", metric="cosine_similarity", k=10, b=1),
     "c5_euclid_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="euclidean_metric", k=10, b=1),
     "c5_manhattan_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="manhattan_distance", k=10, b=1),
@@ -243,10 +246,16 @@ def main():
         m.set_timestamps(ts)
         sm.refresh_decay()
         bias = 0.3
-    q_host = gen_queries(args.warmup + args.steps + 1, w["d"], w["dtype"])       # a different query every step
+    b, k = w["b"], w["k"]
+    # a different query (batch) every step; large batches cycle through a pool of 6 batches
+    pool = (args.warmup + args.steps + 1) if b == 1 else min(args.warmup + args.steps + 1, 6)
+    q_host = gen_queries(pool * b, w["d"], w["dtype"])
     q_dev = torch.as_tensor(q_host).to(dev)
     q_pin = torch.as_tensor(q_host).pin_memory()
-    b, k = w["b"], w["k"]
+
+    def qslice(t, i):
+        j = (i % pool) * b
+        return t[j:j + b]
 
     def barrier():
         if world > 1:
@@ -256,7 +265,7 @@ def main():
     # ---- device-resident arm (value) ------------------------------------------------------------
     outs = []
     for i in range(args.warmup):
-        outs.append(sm.query_async(q_dev[i:i + b], k, w["metric"], bias))
+        outs.append(sm.query_async(qslice(q_dev, i), k, w["metric"], bias))
     barrier()
     m.profile_enable(args.steps * b + 8)
     N.lib().hdb_launch_count(1)
@@ -267,7 +276,7 @@ def main():
     barrier()
     e0.record()
     for i in range(args.steps):
-        outs.append(sm.query_async(q_dev[args.warmup + i: args.warmup + i + b], k, w["metric"], bias))
+        outs.append(sm.query_async(qslice(q_dev, args.warmup + i), k, w["metric"], bias))
     e1.record()
     barrier()
     launches = N.lib().hdb_launch_count(0)
@@ -288,11 +297,11 @@ def main():
     host_query = (lambda q: m.query(q, k, w["metric"], bias)) if world == 1 else (lambda q: sm.query(q, k, w["metric"], bias))
     q_np = q_pin.numpy()
     for i in range(2):
-        host_query(q_np[i:i + b])
+        host_query(qslice(q_np, i))
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        host_query(q_np[args.warmup + i: args.warmup + i + b])
+        host_query(qslice(q_np, args.warmup + i))
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -304,6 +313,8 @@ def main():
         shard_bytes = algorithmic_bytes(w, hi - lo)
         sweep_avg_ms = sweep_ms / max(1, n_sweeps)
         achieved = shard_bytes / (sweep_avg_ms * 1e-3) / 1e9 if n_sweeps else None
+        tensor_bound = b >= 256 and any(int(f) & N.FLAG_TENSOR for o in outs[-1:] for f in o[3].flatten().tolist())
+        shard_flops = 2.0 * (hi - lo) * w["d"] * b
         line = {
             "metric": "queries/sec @top-%d" % k, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -319,10 +330,20 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None,
-                         "kernel": "sweep_kernel", "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
+                         "kernel": "sweep_kernel" if b < 16 else "batched_tc_kernel (sample + select passes)",
+                         "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
                          "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
         }
+        if tensor_bound and n_sweeps:
+            tf = shard_flops / (sweep_avg_ms * 1e-3) / 1e12
+            peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+            line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                                "traffic": None, "kernel": "batched_tc_kernel (sample + select passes)",
+                                "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
+                                "algorithmic_flops_per_launch": shard_flops,
+                                "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                                "frac_of_burst": tf / peaks.get("bf16_tflops", 1667.5), "frac_of_nominal_2250": tf / 2250.0}
         if not args.no_cpu_baseline and world == 1:
             sample = cpu_sample_rows(w)
             tq = cpu_time_per_query(w, sample)

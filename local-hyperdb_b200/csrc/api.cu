@@ -511,9 +511,23 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
     if (h_flags[b] & HDB_FLAG_QUERY_NAN) any_nan = true;
     if (h_flags[b] & HDB_FLAG_UNCERTIFIED) {
       if (m->path_mode == 2) return fail("hdb_query: fused path forced but the certificate failed");
-      HDB_TRY(run_exact(m, metric, rdt, b, k, f, idx, score, count));
       if (fixed.empty()) fixed.assign(h_flags, h_flags + nq);
-      fixed[b] = (fixed[b] & ~HDB_FLAG_UNCERTIFIED) | HDB_FLAG_FALLBACK;
+      bool done = false;
+      if ((h_flags[b] & HDB_FLAG_TENSOR) && k <= 100) {
+        // a query the batched pass could not certify: first retry with the streaming sweep and the wide
+        // candidate class (IEEE fp32 accumulation, 128 candidates), only then pay for the exact path
+        HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
+        HDB_TRY(run_fused(m, metric, rdt, 128, b, 1, k, f, idx, score, count, flags));
+        int bad = 0;
+        HDB_CUDA(cudaMemcpyAsync(&bad, m->uncertified, 4, cudaMemcpyDeviceToHost, m->stream));
+        HDB_CUDA(cudaStreamSynchronize(m->stream));
+        done = (bad == 0);
+        if (done) fixed[b] = (fixed[b] & ~(HDB_FLAG_UNCERTIFIED | HDB_FLAG_TENSOR));
+      }
+      if (!done) {
+        HDB_TRY(run_exact(m, metric, rdt, b, k, f, idx, score, count));
+        fixed[b] = (fixed[b] & ~HDB_FLAG_UNCERTIFIED) | HDB_FLAG_FALLBACK;
+      }
       repaired = true;
     }
   }

@@ -233,3 +233,46 @@ def test_range_and_batch(hb):
         assert list(idx[3]) == list(oi) and np.array_equal(sc[3], os_)
     finally:
         m.close()
+
+
+# ---- tensor-core batched path (tcgen05) == streaming sweep == oracle ------------------------------------------------
+@pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity"])
+@pytest.mark.parametrize("nq", [17, 64, 130, 300])
+def test_batched_tensor_path(hb, metric, nq):
+    import torch
+    n, d = 530_000, 136                      # d*2 bytes is a multiple of 16 but not of 128: exercises the K tail
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(nq)
+    V = torch.randn(n, d, generator=g, device=dev) * (0.5 + torch.rand(n, 1, generator=g, device=dev))
+    V = V.half()
+    Q = torch.randn(nq, d, generator=g, device=dev).half()
+    ts = 1.7e9 + 10 * torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+    keep_bits = torch.randint(-2**31, 2**31 - 1, ((n + 31) // 32,), generator=g, device=dev, dtype=torch.int32)
+    q_np = Q.cpu().numpy()
+    m = hb.DeviceMatrix(V)
+    try:
+        for use_ts, use_mask, k in ((False, False, 10), (True, True, 10), (False, True, 100)):
+            m.set_mask(keep_bits if use_mask else None)
+            m.set_timestamps(ts if use_ts else None)
+            if use_ts:
+                m.refresh_decay()
+            bias = 0.2 if use_ts else 0.0
+            m.set_path(2)                                       # streaming sweep, one launch per query
+            i0, s0, c0, f0 = m.query(q_np, k, metric, bias)
+            m.set_path(0)                                       # automatic: tensor cores for >= 16 queries
+            i1, s1, c1, f1 = m.query(q_np, k, metric, bias)
+            assert all(f & 4 for f in f1), "tensor-core path was not taken"
+            assert sum(1 for f in f1 if f & 1) <= nq // 8, "too many certificate failures on the tensor path"
+            assert np.array_equal(i0, i1) and np.array_equal(s0, s1) and np.array_equal(c0, c1)
+        # and against the oracle on a row subset small enough for it
+        m.set_mask(None)
+        m.set_timestamps(None)
+        m.set_range(1000, 41000)
+        i1, s1, _, f1 = m.query(q_np[:4], 10, metric)
+        sub = V[1000:41000].cpu().numpy()
+        for b in range(4):
+            oi, os_ = K.rank(sub, q_np[b], 10, metric)
+            assert list(i1[b] - 1000) == list(oi) and np.array_equal(s1[b], os_)
+    finally:
+        m.close()
