@@ -41,6 +41,7 @@ WORKLOADS = {
     "c3_cosine_b64": dict(n=10_000_000, d=768, dtype="float16", metric="cosine_similarity", k=10, b=64),
     "c3_cosine_b4096": dict(n=10_000_000, d=768, dtype="float16", metric="cosine_similarity", k=10, b=4096),
     "c3_dot_b4096": dict(n=10_000_000, d=768, dtype="float16", metric="dot_product", k=10, b=4096),
+    "c2_cosine_b1024": dict(n=1_000_000, d=384, dtype="float32", metric="cosine_similarity", k=10, b=1024),
     "c2_cosine_b1": dict(n=1_000_000, d=384, dtype="float32", metric="cosine_similarity", k=10, b=1),
     "c5_euclid_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="euclidean_metric", k=10, b=1),
     "c5_manhattan_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="manhattan_distance", k=10, b=1),

@@ -478,6 +478,8 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
     HDB_CUDA(cudaMemsetAsync(count, 0, (size_t)nq * 8, m->stream));
     if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
   } else if (kp && m->path_mode != 2 && batched_tc_supported(view_of(m), metric, q_dtype, nq)) {
+    if (m->dtype == 1) kp = 128;         // tf32 select: wider error band, so certify a wider candidate list
+    m->last.kp = kp;
     HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
     for (int64_t b0 = 0; b0 < nq; b0 += kTcChunk) {
       const int64_t cnt = nq - b0 < kTcChunk ? nq - b0 : kTcChunk;

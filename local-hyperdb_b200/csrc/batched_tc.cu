@@ -393,12 +393,24 @@ static int launch_tc(const CUtensorMap& mv, const CUtensorMap& mq, const TcParam
 
 int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq) {
   if (metric != HDB_DOT && metric != HDB_COSINE) return 0;
-  if (m.dtype != 0) return 0;                                  // fp16 storage (tf32 for fp32 storage: next)
-  if (q_dtype != 0) return 0;                                  // the B operand is fp16: only exact for fp16 queries
-  if ((m.d * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(m.rows) & 15)) return 0;
+  if (m.dtype == 2) return 0;                                  // no fp64 tensor path
+  if (q_dtype > m.dtype) return 0;                             // the B operand has the storage precision: exact only then
+  if ((m.d * dtype_size(m.dtype)) % 16 != 0 || (reinterpret_cast<uintptr_t>(m.rows) & 15)) return 0;
   if (m.n < 8 * 65536 || nq < 16) return 0;                    // small problems: the sweep loop is fine
   if (m.n >= (int64_t(1) << 31)) return 0;
   return 1;
+}
+
+template <bool TF32>
+static int launch_tc_bn(int BN, bool dense, const CUtensorMap& mv, const CUtensorMap& mq, const TcParams& p, int grid, cudaStream_t s) {
+  if (dense) {
+    if (BN == 64) return launch_tc<64, TF32, true>(mv, mq, p, grid, s);
+    if (BN == 128) return launch_tc<128, TF32, true>(mv, mq, p, grid, s);
+    return launch_tc<256, TF32, true>(mv, mq, p, grid, s);
+  }
+  if (BN == 64) return launch_tc<64, TF32, false>(mv, mq, p, grid, s);
+  if (BN == 128) return launch_tc<128, TF32, false>(mv, mq, p, grid, s);
+  return launch_tc<256, TF32, false>(mv, mq, p, grid, s);
 }
 
 // Runs sample -> thresholds -> select for queries [0, nq) of the prepared batch.  Candidate keys land in
@@ -407,13 +419,18 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
                       const TcWorkspace& ws, cudaStream_t s) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int64_t count = nq * m.d;
-  queries_to_half_kernel<<<(unsigned)((count + 255) / 256 > 4096 ? 4096 : (count + 255) / 256), 256, 0, s>>>(qa, ws.q16, count);
-  HDB_LAUNCHED();
+  const bool tf32 = (m.dtype == 1);      // fp32 storage: kind::tf32 reads the fp32 operands directly (10-bit mantissa)
+  const void* qop = qa;
+  if (!tf32) {
+    const int64_t count = nq * m.d;
+    queries_to_half_kernel<<<(unsigned)((count + 255) / 256 > 4096 ? 4096 : (count + 255) / 256), 256, 0, s>>>(qa, ws.q16, count);
+    HDB_LAUNCHED();
+    qop = ws.q16;
+  }
   CUtensorMap mv, mq;
-  HDB_TRY(make_map(&mv, m.rows, false, m.n, m.d, kTileM));
+  HDB_TRY(make_map(&mv, m.rows, tf32, m.n, m.d, kTileM));
   const int BN = nq <= 64 ? 64 : (nq <= 128 ? 128 : 256);
-  HDB_TRY(make_map(&mq, ws.q16, false, nq, m.d, BN));
+  HDB_TRY(make_map(&mq, qop, tf32, nq, m.d, BN));
   TcParams p;
   p.n = m.n; p.d = m.d; p.nq = nq;
   p.n_tiles_q = (nq + BN - 1) / BN;
@@ -425,9 +442,7 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
   p.n_tiles_m = ws.sample_tiles;
   p.sample_stride = all_tiles / ws.sample_tiles;
   p.dense = ws.dense; p.tau0 = nullptr; p.cand = nullptr; p.cand_count = nullptr; p.cap = 0;
-  if (BN == 64) HDB_TRY((launch_tc<64, false, true>(mv, mq, p, sms, s)));
-  else if (BN == 128) HDB_TRY((launch_tc<128, false, true>(mv, mq, p, sms, s)));
-  else HDB_TRY((launch_tc<256, false, true>(mv, mq, p, sms, s)));
+  HDB_TRY(tf32 ? launch_tc_bn<true>(BN, true, mv, mq, p, sms, s) : launch_tc_bn<false>(BN, true, mv, mq, p, sms, s));
   sample_threshold_kernel<<<(unsigned)nq, 256, 0, s>>>(ws.dense, ws.sample_tiles * kTileM, kp, ws.tau0);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
@@ -436,9 +451,7 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
   p.n_tiles_m = all_tiles;
   p.sample_stride = 1;
   p.dense = nullptr; p.tau0 = ws.tau0; p.cand = ws.cand; p.cand_count = ws.cand_count; p.cap = ws.cap;
-  if (BN == 64) HDB_TRY((launch_tc<64, false, false>(mv, mq, p, sms, s)));
-  else if (BN == 128) HDB_TRY((launch_tc<128, false, false>(mv, mq, p, sms, s)));
-  else HDB_TRY((launch_tc<256, false, false>(mv, mq, p, sms, s)));
+  HDB_TRY(tf32 ? launch_tc_bn<true>(BN, false, mv, mq, p, sms, s) : launch_tc_bn<false>(BN, false, mv, mq, p, sms, s));
   return 0;
 }
 

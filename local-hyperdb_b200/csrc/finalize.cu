@@ -60,6 +60,7 @@ __device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) 
   if (a.metric == HDB_DOT || a.metric == HDB_COSINE) {
     const double A = (double)(a.metric == HDB_DOT ? a.m.max_norm : a.m.max_ratio) * qnorm;   // >= sum |v_i q_i|
     double e = D * ua + chain16;
+    if (a.cand_count && a.m.dtype == 1) e += 3.90625e-3;       // kind::tf32 keeps 10 mantissa bits of each fp32 operand (2 * 2^-9)
     if (a.metric == HDB_COSINE) e += 3.0 * uT + (a.m.dtype == 0 ? sqrt(D) * 5.9604644775390625e-8 : 0.0);
     const double b = s + fabs(s) * uk + A * e;
     return decay ? b + 2.0 * uR * A + fabs(b) * 1e-15 : b + 2.0 * uR * fabs(b);
