@@ -142,7 +142,7 @@ int hdb_matrix_destroy(hdb_matrix* m) {
   void* ptrs[] = {m->norms, m->inv_norms, m->bits, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
                   m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_block,
                   m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag, m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand,
-                  m->tc.cand_count};
+                  m->tc.cand_count, m->tc.rec, m->tc.rec_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (m->h_block) cudaFreeHost(m->h_block);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
@@ -389,8 +389,14 @@ static int ensure_tc_workspace(hdb_matrix* m, int64_t nq, int kp) {
   int64_t cap = 1024;
   const int64_t expect = 2 * m->n * kp / (sample_tiles * 128);
   while (cap < expect && cap < 65536) cap <<= 1;
-  if (m->tc_nq >= nq && m->tc.cap >= cap && m->tc.sample_tiles == sample_tiles) return 0;
-  void* ptrs[] = {m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand, m->tc.cand_count};
+  // CTA-private record buffers: expected records = n * nq * kp / sample_rows over all SMs; 3x slack
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  double expect_rec = (double)m->n * (double)nq * kp / (double)(sample_tiles * 128) / sms;
+  int64_t rec_cap = (int64_t)(3.0 * expect_rec) + 8192;
+  if (rec_cap > (int64_t)1 << 21) rec_cap = (int64_t)1 << 21;
+  if (m->tc_nq >= nq && m->tc.cap >= cap && m->tc.sample_tiles == sample_tiles && m->tc.rec_cap >= (unsigned)rec_cap) return 0;
+  void* ptrs[] = {m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand, m->tc.cand_count, m->tc.rec, m->tc.rec_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   m->tc = TcWorkspace{};
   m->tc_nq = 0;
@@ -399,6 +405,9 @@ static int ensure_tc_workspace(hdb_matrix* m, int64_t nq, int kp) {
   HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.tau0), (size_t)nq * 4));
   HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.cand), (size_t)nq * cap * 8));
   HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.cand_count), (size_t)nq * 4));
+  HDB_CUDA(cudaMalloc(&m->tc.rec, (size_t)sms * rec_cap * 16));
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.rec_count), (size_t)sms * 4));
+  m->tc.rec_cap = (unsigned)rec_cap;
   m->tc.cap = (int)cap;
   m->tc.sample_tiles = sample_tiles;
   m->tc_nq = nq;

@@ -15,6 +15,7 @@
 // Tile order: query tile fastest, so the CTAs running at the same time share the V row tile through L2 and the
 // matrix is read from HBM once; Q stays L2 resident.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "hdb_common.cuh"
 #include "hdb_internal.h"
@@ -22,7 +23,7 @@
 
 namespace hdb {
 
-constexpr int kTcEpiWarps = 8;           // two epilogue warps per TMEM lane quarter, each takes half of the columns
+constexpr int kTcEpiWarps = 16;          // four epilogue warps per TMEM lane quarter, each takes a quarter of the columns
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, rest: epilogue
 constexpr int kTcStages = 4;
 constexpr int kTileM = 128;
@@ -106,7 +107,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool tf32) {
 }
 
 // ---------------------------------------------------------------------------------------------
-struct TcParams {
+struct TcParamsBase {
   int64_t n, d;                 // shard rows, dim
   int64_t nq;                   // queries in this batch (padded to BN by TMA zero fill)
   int64_t n_tiles_m, n_tiles_q; // row tiles visited (all, or the sample), query tiles
@@ -114,6 +115,94 @@ struct TcParams {
   const char* rows;             // matrix base (for the L2 prefetch)
   const float* inv_norms;       // cosine or nullptr
   RowFilter f;
+};
+// ---------------------------------------------------------------------------------------------
+// SELECT epilogue of one accumulator tile for one warp: columns [c_begin, c_end) of this warp's 32 TMEM lanes.
+// Branch-free screening (FFMA + predicate-OR per element), the next chunk's tcgen05.ld in flight while the
+// current one is screened, and the append path only for lanes that actually hold a candidate.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Candidates found by the epilogue go to a CTA-private record buffer: the slot comes from a SHARED-memory counter
+// (tens of cycles) and the 16-byte record {key, query} is a fire-and-forget global store, so no global atomic
+// round trip ever sits on the epilogue's critical path.  bucket_records_kernel distributes the records to the
+// per-query candidate lists afterwards, where the atomics are throughput- not latency-bound.
+struct SelectSink {
+  uint4* rec;              // this CTA's records
+  unsigned* s_count;       // shared-memory counter
+  unsigned cap;
+};
+
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return v;
+}
+
+// Screen 32 columns of this warp's 32 rows.  Fast path: FFMA + compare per element into a per-lane bit mask (no
+// branches).  Slow path (some lane found a candidate): warp-uniform loop over the union of the masks, the column is
+// re-read from TMEM with a 1-column tcgen05.ld (registers cannot be indexed dynamically), the owners append.
+__device__ __forceinline__ void screen_chunk(const uint32_t (&r)[32], uint32_t taddr_chunk, const float* tau, float inv, float dec,
+                                             int64_t b0, uint32_t row, const SelectSink& sink) {
+  const float4* tq = reinterpret_cast<const float4*>(tau);
+  uint32_t mask = 0;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 tv = tq[j4];
+    mask |= (fmaf(__uint_as_float(r[j4 * 4 + 0]), inv, dec) >= tv.x ? 1u : 0u) << (j4 * 4 + 0);
+    mask |= (fmaf(__uint_as_float(r[j4 * 4 + 1]), inv, dec) >= tv.y ? 1u : 0u) << (j4 * 4 + 1);
+    mask |= (fmaf(__uint_as_float(r[j4 * 4 + 2]), inv, dec) >= tv.z ? 1u : 0u) << (j4 * 4 + 2);
+    mask |= (fmaf(__uint_as_float(r[j4 * 4 + 3]), inv, dec) >= tv.w ? 1u : 0u) << (j4 * 4 + 3);
+  }
+  uint32_t wmask = __reduce_or_sync(kFull, mask);
+  while (wmask) {
+    const int j = __ffs(wmask) - 1;
+    wmask &= wmask - 1;
+    const float s = fmaf(__uint_as_float(tmem_ld1(taddr_chunk + (uint32_t)j)), inv, dec);
+    if ((mask >> j) & 1u) {
+      const unsigned pos = atomicAdd(sink.s_count, 1u);
+      const uint64_t key = make_key(s, row);
+      if (pos < sink.cap) sink.rec[pos] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)(b0 + j), 0u);
+    }
+  }
+}
+
+// tau_tile: the BN thresholds of this query tile (shared memory); qbase = first query of the tile
+__device__ __forceinline__ void select_epilogue_tile(uint32_t taddr, int c_begin, int c_end, const float* tau_tile, float inv,
+                                                     float dec, int64_t qbase, uint32_t row, const SelectSink& sink, int debug) {
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + (uint32_t)c0, r);
+    if (debug != 1) screen_chunk(r, taddr + (uint32_t)c0, tau_tile + c0, inv, dec, qbase + c0, row, sink);
+  }
+}
+
+// per-row side inputs of the epilogue; a dropped row gets dec = NaN so that every comparison is false
+__device__ __forceinline__ void row_inputs(const TcParamsBase& p, int64_t row, float& inv, float& dec) {
+  bool kept = row < p.n && row >= p.f.lo && row < p.f.hi;
+  if (kept && p.f.mask) kept = (p.f.mask[row >> 5] >> (row & 31)) & 1u;
+  inv = 0.f;
+  dec = __int_as_float(0x7fc00000);
+  if (kept) {
+    inv = p.inv_norms ? p.inv_norms[row] : 1.f;
+    dec = p.f.decay ? (float)(p.f.bias * p.f.decay[row]) : 0.f;
+  }
+}
+
+struct TcParams : TcParamsBase {
   // DENSE mode
   float* dense;                 // [nq][n_tiles_m * 128] totals of the sample (dropped rows = -inf)
   // SELECT mode
@@ -121,6 +210,10 @@ struct TcParams {
   uint64_t* cand;               // [nq][cap]
   unsigned* cand_count;         // [nq]
   int cap;
+  uint4* rec;                   // [gridDim.x][rec_cap] CTA-private candidate records
+  unsigned* rec_count;          // [gridDim.x]
+  unsigned rec_cap;
+  int debug;                    // HDB_TC_DEBUG: 1 = epilogue drains TMEM but skips the compare/append (timing experiments)
 };
 
 template <int BN, bool TF32, bool DENSE>
@@ -141,11 +234,16 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
   uint64_t* acc_full = empty + kTcStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_tau = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full) + 128);   // [2][BN], 16-byte aligned
+  unsigned* s_rec_count = tmem_slot + 1;
+  float* s_tau = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full) + 128);   // [n_tiles_q * BN], 16-byte aligned
+  if (threadIdx.x == 0) *s_rec_count = 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = (int)((p.d + kKPerStage - 1) / kKPerStage);
   const int64_t total_tiles = p.n_tiles_m * p.n_tiles_q;
+  if (!DENSE) {      // every threshold of the batch lives in shared memory for the whole kernel (<= 16 KB)
+    for (int64_t i = threadIdx.x; i < p.n_tiles_q * BN; i += kTcThreads) s_tau[i] = i < p.nq ? p.tau0[i] : INFINITY;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -227,80 +325,274 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
   } else {
     // ===== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int ep_tid = (warp - 2) * 32 + lane;             // 0..255 for cooperative loads
+    const int part = (warp - 2) >> 2;                      // which quarter of the columns
     int acc = 0;
     uint32_t acc_phase = 0;
+    const SelectSink sink{p.rec + (size_t)blockIdx.x * p.rec_cap, s_rec_count, p.rec_cap};
+    float inv = 0.f, dec = 0.f;
+    if ((int64_t)blockIdx.x < total_tiles)
+      row_inputs(p, (blockIdx.x / p.n_tiles_q) * p.sample_stride * kTileM + quarter * 32 + lane, inv, dec);
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int64_t mt_visit = t / p.n_tiles_q;
       const int64_t mt = mt_visit * p.sample_stride;
       const int64_t qt = t % p.n_tiles_q;
       const int64_t row = mt * kTileM + quarter * 32 + lane;
-      // per-row side inputs; a dropped row gets dec = NaN so that every comparison below is false
-      bool kept = row < p.n && row >= p.f.lo && row < p.f.hi;
-      if (kept && p.f.mask) kept = (p.f.mask[row >> 5] >> (row & 31)) & 1u;
-      float inv = 0.f, dec = __int_as_float(0x7fc00000);
-      if (kept) {
-        inv = p.inv_norms ? p.inv_norms[row] : 1.f;
-        dec = p.f.decay ? (float)(p.f.bias * p.f.decay[row]) : 0.f;
-      }
+      // side inputs of the NEXT tile: their global-load latency hides behind this tile
+      float ninv = 0.f, ndec = 0.f;
+      if (t + gridDim.x < total_tiles)
+        row_inputs(p, ((t + gridDim.x) / p.n_tiles_q) * p.sample_stride * kTileM + quarter * 32 + lane, ninv, ndec);
       const int64_t valid = (p.nq - qt * BN) < BN ? (p.nq - qt * BN) : BN;       // real queries in this tile
-      const int c_begin = half * (BN / 2);
-      const int c_end = (int)(valid < (half + 1) * (BN / 2) ? valid : (half + 1) * (BN / 2));
-      if (!DENSE) {
-        // thresholds of this query tile -> shared memory (double buffered with the accumulator)
-        for (int c = ep_tid; c < BN; c += 32 * kTcEpiWarps) {
-          const int64_t b = qt * BN + c;
-          s_tau[acc * BN + c] = b < p.nq ? p.tau0[b] : INFINITY;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kTcEpiWarps) : "memory");     // epilogue warps only
-      }
+      constexpr int kColsPerWarp = BN / 4 < 32 ? 32 : BN / 4;                     // 32-column chunks; BN = 64: two warps idle
+      const int c_begin = part * kColsPerWarp;
+      const int c_end = (int)(valid < (part + 1) * kColsPerWarp ? valid : (part + 1) * kColsPerWarp);
       mbar_wait(&acc_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      if (DENSE) {
+        const int64_t ld = p.n_tiles_m * kTileM;
+        const int64_t col = mt_visit * kTileM + quarter * 32 + lane;
 #pragma unroll 1
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
-        if (DENSE) {
-          const int64_t ld = p.n_tiles_m * kTileM;
-          const int64_t col = mt_visit * kTileM + quarter * 32 + lane;
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c0, r);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int64_t b = qt * BN + c0 + j;
             if (b < p.nq) {
-              float s = fmaf(__uint_as_float(r[j]), inv, dec);
+              const float s = fmaf(__uint_as_float(r[j]), inv, dec);
               p.dense[b * ld + col] = (s == s) ? s : -INFINITY;
             }
           }
-        } else {
-          const float4* tq = reinterpret_cast<const float4*>(&s_tau[acc * BN + c0]);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 tv = tq[j4];
-            const float th[4] = {tv.x, tv.y, tv.z, tv.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float s = fmaf(__uint_as_float(r[j4 * 4 + u]), inv, dec);
-              if (s >= th[u]) {
-                const int64_t b = qt * BN + c0 + j4 * 4 + u;
-                const unsigned pos = atomicAdd(&p.cand_count[b], 1u);
-                if (pos < (unsigned)p.cap) p.cand[b * p.cap + pos] = make_key(s, (uint32_t)row);
-              }
-            }
-          }
         }
+      } else {
+        select_epilogue_tile(taddr, c_begin, c_end, s_tau + qt * BN, inv, dec, qt * BN, (uint32_t)row, sink, p.debug);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      inv = ninv;
+      dec = ndec;
     }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (!DENSE && threadIdx.x == 0) p.rec_count[blockIdx.x] = *s_rec_count;      // may exceed rec_cap: overflow, seen by the bucket pass
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair form of the SELECT pass (cta_group::2): the two CTAs of a cluster contract one 256-row x 256-query
+// tile.  Each CTA stages its own 128 rows of V and its own 128 queries (32 KB per stage instead of 48 KB, six
+// stages instead of four, a third less L2 traffic per flop); the leader CTA issues tcgen05.mma.cta_group::2,
+// the accumulator is split by rows over the two CTAs' TMEM and each CTA's epilogue warps drain their half.
+// Barriers: every TMA of both CTAs completes on the LEADER's full barrier; tcgen05.commit multicasts the
+// empty / accumulator-full arrivals to both CTAs; the peer's epilogue releases the accumulator remotely.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTc2Stages = 6;
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+
+template <bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+batched_tc_pair_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_q, TcParams p) {
+  constexpr int BN = 256;                                // queries per pair tile (128 staged by each CTA)
+  constexpr int kABytes = kTileM * kTileKBytes;          // 16 KB: this CTA's 128 rows
+  constexpr int kBBytes = (BN / 2) * kTileKBytes;        // 16 KB: this CTA's 128 queries
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kKPerStage = kTileKBytes / (TF32 ? 4 : 2);
+  constexpr uint32_t kIdesc = make_idesc(2 * kTileM, BN, TF32);
+  constexpr int kTmemCols = 2 * BN;
+
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  unsigned char* stage_base = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + kTc2Stages * kStageBytes);
+  uint64_t* empty = full + kTc2Stages;
+  uint64_t* acc_full = empty + kTc2Stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  unsigned* s_rec_count = tmem_slot + 1;
+  float* s_tau = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(full) + 256);      // [n_tiles_q * BN]
+  if (threadIdx.x == 0) *s_rec_count = 0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t i = threadIdx.x; i < p.n_tiles_q * BN; i += kTcThreads) s_tau[i] = i < p.nq ? p.tau0[i] : INFINITY;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int kblocks = (int)((p.d + kKPerStage - 1) / kKPerStage);
+  const int64_t tiles_m2 = (p.n_tiles_m + 1) / 2;        // 256-row tiles
+  const int64_t total_tiles = tiles_m2 * p.n_tiles_q;
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTc2Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * kTcEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; all transactions complete on the leader's full barrier) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int64_t row_bytes = p.d * (TF32 ? 4 : 2);
+      for (int64_t t = pair; t < total_tiles; t += npairs) {
+        const int64_t mt = (t / p.n_tiles_q) * 2 + rank;          // this CTA's 128-row tile
+        const int64_t qt = t % p.n_tiles_q;
+        {
+          const int64_t tn = t + npairs;
+          if (tn < total_tiles) {                                  // L2 bulk prefetch of the next tile's rows (see above)
+            const int64_t mtn = (tn / p.n_tiles_q) * 2 + rank, qtn = tn % p.n_tiles_q;
+            const int64_t rows_n = (p.n - mtn * kTileM) < kTileM ? (p.n - mtn * kTileM) : kTileM;
+            const int64_t region = rows_n > 0 ? rows_n * row_bytes : 0;
+            int64_t slice = ((region / p.n_tiles_q) + 15) & ~int64_t(15);
+            const int64_t off = qtn * slice;
+            if (off < region) {
+              if (off + slice > region) slice = (region - off) & ~int64_t(15);
+              if (slice > 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rows + mtn * kTileM * row_bytes + off), "r"((uint32_t)slice) : "memory");
+            }
+          }
+        }
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = stage_base + stage * kStageBytes;
+          const uint32_t leader_full = map_to_cta(smem_u32(&full[stage]), 0);
+          if (leader) mbar_expect_tx(&full[stage], 2 * kStageBytes);
+          tma_load_2d_pair(sa, &map_v, leader_full, kb * kKPerStage, (int)(mt * kTileM));
+          tma_load_2d_pair(sa + kABytes, &map_q, leader_full, kb * kKPerStage, (int)(qt * BN + rank * (BN / 2)));
+          if (++stage == kTc2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = pair; t < total_tiles; t += npairs) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kTileKBytes / 32; ++k)
+            umma_pair<TF32>(tmem_c, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (kb | k) ? 1u : 0u);
+          tcgen05_commit_pair(&empty[stage]);
+          if (++stage == kTc2Stages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit_pair(&acc_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: this CTA's 128 rows x 256 queries =====
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const SelectSink sink{p.rec + (size_t)blockIdx.x * p.rec_cap, s_rec_count, p.rec_cap};
+    const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
+    float inv = 0.f, dec = 0.f;
+    if (pair < total_tiles) row_inputs(p, ((pair / p.n_tiles_q) * 2 + rank) * kTileM + quarter * 32 + lane, inv, dec);
+    for (int64_t t = pair; t < total_tiles; t += npairs) {
+      const int64_t mt = (t / p.n_tiles_q) * 2 + rank;
+      const int64_t qt = t % p.n_tiles_q;
+      const int64_t row = mt * kTileM + quarter * 32 + lane;
+      float ninv = 0.f, ndec = 0.f;
+      if (t + npairs < total_tiles)
+        row_inputs(p, (((t + npairs) / p.n_tiles_q) * 2 + rank) * kTileM + quarter * 32 + lane, ninv, ndec);
+      const int64_t valid = (p.nq - qt * BN) < BN ? (p.nq - qt * BN) : BN;
+      const int c_begin = part * (BN / 4);
+      const int c_end = (int)(valid < (part + 1) * (BN / 4) ? valid : (part + 1) * (BN / 4));
+      mbar_wait(&acc_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      select_epilogue_tile(taddr, c_begin, c_end, s_tau + qt * BN, inv, dec, qt * BN, (uint32_t)row, sink, p.debug);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(leader_acc_empty0 + (uint32_t)(acc * 8));       // the leader's MMA thread waits on it
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      inv = ninv;
+      dec = ndec;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                      // the peer may still read this CTA's smem / signal its barriers
+  if (threadIdx.x == 0) p.rec_count[blockIdx.x] = *s_rec_count;
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-private records -> per-query candidate lists.  One CTA per source CTA; a source buffer that overflowed
+// poisons every query (count = UINT_MAX -> finalize reports them uncertified and the host retries).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bucket_records_kernel(const uint4* rec, const unsigned* rec_count, unsigned rec_cap,
+                                                             uint64_t* cand, unsigned* cand_count, int cap, int64_t nq) {
+  const unsigned n = rec_count[blockIdx.x];
+  if (n > rec_cap) {
+    for (int64_t b = threadIdx.x; b < nq; b += 256) cand_count[b] = 0xffffffffu;
+    return;
+  }
+  const uint4* src = rec + (size_t)blockIdx.x * rec_cap;
+  for (unsigned i = threadIdx.x; i < n; i += 256) {
+    const uint4 r = src[i];
+    const unsigned pos = atomicAdd(&cand_count[r.z], 1u);
+    if (pos < (unsigned)cap) cand[(size_t)r.z * cap + pos] = ((uint64_t)r.y << 32) | r.x;
   }
 }
 
@@ -383,7 +675,7 @@ static int make_map(CUtensorMap* map, const void* base, bool tf32, int64_t rows,
 template <int BN, bool TF32, bool DENSE>
 static int launch_tc(const CUtensorMap& mv, const CUtensorMap& mq, const TcParams& p, int grid, cudaStream_t s) {
   auto kern = batched_tc_kernel<BN, TF32, DENSE>;
-  const size_t smem = (size_t)kTcStages * (kTileM + BN) * kTileKBytes + 16 * 8 + 16 + 2 * BN * 4 + 1024;
+  const size_t smem = (size_t)kTcStages * (kTileM + BN) * kTileKBytes + 128 + (DENSE ? 0 : (size_t)p.n_tiles_q * BN * 4) + 16 + 1024;
   HDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kTcThreads, smem, s>>>(mv, mq, p);
   HDB_LAUNCHED();
@@ -435,6 +727,7 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
   p.n = m.n; p.d = m.d; p.nq = nq;
   p.n_tiles_q = (nq + BN - 1) / BN;
   p.rows = reinterpret_cast<const char*>(m.rows);
+  p.debug = getenv("HDB_TC_DEBUG") ? atoi(getenv("HDB_TC_DEBUG")) : 0;
   p.inv_norms = metric == HDB_COSINE ? reinterpret_cast<const float*>(m.inv_norms) : nullptr;
   p.f = f;
   const int64_t all_tiles = (m.n + kTileM - 1) / kTileM;
@@ -442,6 +735,7 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
   p.n_tiles_m = ws.sample_tiles;
   p.sample_stride = all_tiles / ws.sample_tiles;
   p.dense = ws.dense; p.tau0 = nullptr; p.cand = nullptr; p.cand_count = nullptr; p.cap = 0;
+  p.rec = nullptr; p.rec_count = nullptr; p.rec_cap = 0;
   HDB_TRY(tf32 ? launch_tc_bn<true>(BN, true, mv, mq, p, sms, s) : launch_tc_bn<false>(BN, true, mv, mq, p, sms, s));
   sample_threshold_kernel<<<(unsigned)nq, 256, 0, s>>>(ws.dense, ws.sample_tiles * kTileM, kp, ws.tau0);
   HDB_LAUNCHED();
@@ -451,8 +745,32 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
   p.n_tiles_m = all_tiles;
   p.sample_stride = 1;
   p.dense = nullptr; p.tau0 = ws.tau0; p.cand = ws.cand; p.cand_count = ws.cand_count; p.cap = ws.cap;
+  p.rec = reinterpret_cast<uint4*>(ws.rec); p.rec_count = ws.rec_count; p.rec_cap = ws.rec_cap;
+  auto bucket = [&]() -> int {
+    bucket_records_kernel<<<sms, 256, 0, s>>>(reinterpret_cast<const uint4*>(ws.rec), ws.rec_count, ws.rec_cap, ws.cand, ws.cand_count,
+                                               ws.cap, nq);
+    HDB_LAUNCHED();
+    HDB_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if (BN == 256 && (sms % 2) == 0 && !ws.force_single) {
+    // CTA-pair contraction: each CTA's query box is 128 rows
+    CUtensorMap mq2;
+    HDB_TRY(make_map(&mq2, qop, tf32, nq, m.d, 128));
+    const size_t smem = (size_t)kTc2Stages * (kTileM + 128) * kTileKBytes + 256 + (size_t)p.n_tiles_q * 256 * 4 + 16 + 1024;
+    if (tf32) {
+      HDB_CUDA(cudaFuncSetAttribute(batched_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      batched_tc_pair_kernel<true><<<sms, kTcThreads, smem, s>>>(mv, mq2, p);
+    } else {
+      HDB_CUDA(cudaFuncSetAttribute(batched_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      batched_tc_pair_kernel<false><<<sms, kTcThreads, smem, s>>>(mv, mq2, p);
+    }
+    HDB_LAUNCHED();
+    HDB_CUDA(cudaGetLastError());
+    return bucket();
+  }
   HDB_TRY(tf32 ? launch_tc_bn<true>(BN, false, mv, mq, p, sms, s) : launch_tc_bn<false>(BN, false, mv, mq, p, sms, s));
-  return 0;
+  return bucket();
 }
 
 }  // namespace hdb

@@ -120,6 +120,10 @@ struct TcWorkspace {
   unsigned* cand_count;    // [nq]
   int cap;
   int64_t sample_tiles;
+  void* rec;               // [n_sm][rec_cap] 16-byte CTA-private candidate records
+  unsigned* rec_count;     // [n_sm]
+  unsigned rec_cap;
+  int force_single;        // testing: keep the single-CTA contraction even for wide batches
 };
 int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq);
 int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const float* qa, int64_t nq, int kp, int device,
