@@ -201,6 +201,24 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     overflow = appended > (unsigned)a.cand_stride;          // some qualifying rows were dropped: cannot certify
     total = (int)(overflow ? (unsigned)a.cand_stride : appended);
   }
+  // Tighten the threshold before gathering: every per-CTA list is sorted, so the KP-th largest of the lists' HEADS
+  // (KP distinct keys) is a lower bound of the KP-th key overall -- far better than the sweep's running threshold
+  // when the shard is small and each warp saw only a few hundred rows.  Keeps the gather below on its fast path.
+  __shared__ uint64_t s_heads[1024];
+  __shared__ unsigned long long s_tau_star;
+  if (tid == 0) s_tau_star = 0;
+  if (!a.cand_count && a.grid >= a.kp && a.grid <= 1024) {
+    for (int i = tid; i < a.grid; i += kFinThreads) s_heads[i] = cand[(int64_t)i * a.kp];
+    __syncthreads();
+    for (int i = tid; i < a.grid; i += kFinThreads) {
+      const uint64_t mine = s_heads[i];
+      int rank = 0;
+      for (int u = 0; u < a.grid; ++u) rank += s_heads[u] > mine;
+      if (rank == a.kp - 1 && mine != 0) s_tau_star = mine;          // keys are unique: exactly one thread matches
+    }
+  }
+  __syncthreads();
+  const unsigned long long tau_eff = tau > s_tau_star ? tau : (unsigned long long)s_tau_star;
   for (int i0 = tid; i0 < total; i0 += kFinThreads * 8) {       // 8 loads in flight per thread
     uint64_t key[8];
 #pragma unroll
@@ -210,7 +228,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      if (key[u] != 0 && key[u] >= tau) {
+      if (key[u] != 0 && key[u] >= tau_eff) {
         int pos = atomicAdd(&s_count, 1);
         if (pos < kSurvCap) surv[pos] = key[u];
       }
@@ -311,7 +329,21 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     if (a.metric == HDB_COSINE)
       nrm = a.m.dtype == 2 ? reinterpret_cast<const double*>(a.m.norms)[row] : (double)reinterpret_cast<const float*>(a.m.norms)[row];
     const char* rowp = reinterpret_cast<const char*>(a.m.rows) + (int64_t)row * a.m.d * dtype_size(a.m.dtype);
-    const double sim = canonical_similarity_rt(ca, a.rdt, rowp, bitrow, nrm);
+    double sim;
+    if (a.metric == HDB_HAMMING) {
+      // packed rows are whole 16-byte vectors: independent 128-bit loads instead of a word-by-word chain
+      const uint4* vr = reinterpret_cast<const uint4*>(bitrow);
+      const uint4* vq = reinterpret_cast<const uint4*>(ca.qbits);
+      int diff = 0;
+#pragma unroll 4
+      for (int v = 0; v < a.m.words / 4; ++v) {
+        const uint4 x = vr[v], q = vq[v];
+        diff += __popc(x.x ^ q.x) + __popc(x.y ^ q.y) + __popc(x.z ^ q.z) + __popc(x.w ^ q.w);
+      }
+      sim = (double)((int)a.m.d - diff);
+    } else {
+      sim = canonical_similarity_rt(ca, a.rdt, rowp, bitrow, nrm);
+    }
     c_tot[tid] = total_score(sim, a.f.decay, a.f.bias, row);
     c_row[tid] = row;
   }

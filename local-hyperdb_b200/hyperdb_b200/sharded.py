@@ -153,3 +153,37 @@ class ShardedMatrix:
             return (blk[: b * k].view(b, k).numpy(), blk[b * k: 2 * b * k].view(torch.float64).view(b, k).numpy(),
                     blk[2 * b * k:].numpy())
         return idx.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+
+
+class GraphedQuery:
+    """A captured CUDA graph of one query step (prepare -> sweep/contraction -> certify -> all-gather -> merge) for a
+    fixed (batch, top_k, metric, recency_bias): replaying it costs one launch instead of a dozen host calls, which is
+    what bounds the latency-dominated configurations (small shards at 8 GPUs, bit-packed hamming).
+
+    The query is copied into a static device buffer before each replay; the outputs are static device tensors that the
+    next replay overwrites."""
+
+    def __init__(self, sharded, queries_like, top_k, metric, recency_bias=0.0):
+        import torch
+        self.sm = sharded
+        eng = sharded.engine
+        self.q_static = queries_like.clone()
+        side = torch.cuda.Stream(device=eng.device)
+        side.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(side):
+            eng.m.set_stream(side.cuda_stream)
+            for _ in range(2):                                   # warm-up: workspaces, NCCL channels, allocator
+                sharded.query_async(self.q_static, top_k, metric, recency_bias)
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                eng.m.set_stream(torch.cuda.current_stream(eng.device).cuda_stream)
+                self.out = sharded.query_async(self.q_static, top_k, metric, recency_bias)
+        eng.m.set_stream(0)
+        torch.cuda.current_stream(eng.device).wait_stream(side)
+
+    def replay(self, queries):
+        """Enqueue one step on the current stream; returns the static output tensors (idx, score, count, flags)."""
+        self.q_static.copy_(queries, non_blocking=True)
+        self.graph.replay()
+        return self.out
