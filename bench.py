@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debugging only; invalidates the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph (single GPU only)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.rows:
@@ -268,7 +268,7 @@ def main():
     # ---- device-resident arm (value) ------------------------------------------------------------
     # one captured CUDA graph per step when the step is short enough for host launch overhead to matter
     graphed = None
-    if not args.no_graph and b <= 64:
+    if args.graph and world == 1 and b <= 64:      # opt-in: NCCL collectives captured in a graph stalled at teardown here
         from hyperdb_b200.sharded import GraphedQuery
         graphed = GraphedQuery(sm, qslice(q_dev, 0), k, w["metric"], bias)
     step = (lambda q: graphed.replay(q)) if graphed else (lambda q: sm.query_async(q, k, w["metric"], bias))
