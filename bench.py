@@ -165,27 +165,37 @@ def cpu_sample_rows(w):
 
 
 def run_reference_arm(args, w):
+    """`--impl reference`: the reference's CPU path (NumPy port) on this box's host cores, EXACTLY --steps timed steps
+    after --warmup untimed ones; each step ranks one query against a row sample sized so the whole run takes ~2 min,
+    and the per-step time is scaled linearly to the full row count (rows are independent in the reference)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = cpu_sample_rows(w)
-    times = []
-    for _ in range(max(1, args.warmup)):
-        cpu_time_per_query(w, min(sample, 20_000))
-    steps = max(1, min(args.steps, 3))
-    for _ in range(steps):
-        times.append(cpu_time_per_query(w, sample))
-    t_full = float(np.mean(times)) * (w["n"] / sample) * w["b"]
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    per_row_s = cpu_time_per_query(w, 20_000) / 20_000                 # calibration, untimed
+    sample = int(max(2_000, min(w["n"], 120.0 / (steps + warm) / per_row_s)))
+    v = gen_rows_numpy(sample, w["d"], w["dtype"], seed=0)
+    qs = gen_queries(steps + warm, w["d"], w["dtype"])
+    ts = 1.7e9 + np.random.default_rng(2).uniform(0, 3600, sample) if w.get("decay") else None
+    from oracle import reference_port as P
+    for i in range(warm):
+        P.rank(v, qs[i], w["k"], w["metric"], ts, 0.3 if ts is not None else 0, canonical=False)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        P.rank(v, qs[warm + i], w["k"], w["metric"], ts, 0.3 if ts is not None else 0, canonical=False)
+    t_step = (time.perf_counter() - t0) / steps
+    t_full = t_step * (w["n"] / sample) * w["b"]                       # a batch is B independent calls in the reference
     qps = w["b"] / t_full
     cores = len(os.sched_getaffinity(0))
     line = {
         "impl": "reference", "metric": "queries/sec @top-%d" % w["k"], "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "strong",
+        "steps": steps, "warmup": warm, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
         "config": {"workload": args.workload, "rows": w["n"], "dim": w["d"], "metric": w["metric"], "top_k": w["k"], "batch": w["b"]},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {w['n']} rows per step, time scaled linearly by {w['n'] / sample:.1f}x; "
-                                   f"oracle/reference_port.rank (the reference's NumPy calls), NumPy {np.__version__}"},
+                         "sample": f"each step = 1 query on {sample} of {w['n']} rows ({t_step * 1e3:.1f} ms), scaled linearly by "
+                                   f"{w['n'] / sample:.1f}x (and by the batch size); oracle/reference_port.rank = the reference's NumPy "
+                                   f"calls, NumPy {np.__version__}, all threads NumPy/OpenBLAS chooses to use"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
