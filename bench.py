@@ -44,6 +44,7 @@ WORKLOADS = {
     "c2_cosine_b1024": dict(n=1_000_000, d=384, dtype="float32", metric="cosine_similarity", k=10, b=1024),
     "c2_cosine_b1": dict(n=1_000_000, d=384, dtype="float32", metric="cosine_similarity", k=10, b=1),
     "c5_euclid_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="euclidean_metric", k=10, b=1),
+    "c5_euclid_b1024": dict(n=5_000_000, d=1024, dtype="float32", metric="euclidean_metric", k=10, b=1024),
     "c5_manhattan_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="manhattan_distance", k=10, b=1),
     "c5_hamming_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="hamming_distance", k=10, b=1),
     "c4_decay_mask_k100": dict(n=100_000_000, d=384, dtype="float16", metric="cosine_similarity", k=100, b=1,

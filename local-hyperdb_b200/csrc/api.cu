@@ -30,6 +30,7 @@ struct hdb_matrix {
   bool owns_rows = false;
   void* norms = nullptr;
   void* inv_norms = nullptr;
+  float* sqnorms = nullptr;
   uint32_t* bits = nullptr;
   int words = 0;
   float max_norm = 0.f, max_ratio = 1.f;
@@ -69,7 +70,7 @@ struct hdb_matrix {
 static MatrixView view_of(const hdb_matrix* m) {
   MatrixView v;
   v.rows = m->rows; v.dtype = m->dtype; v.n = m->n; v.d = m->d; v.row_offset = m->row_offset;
-  v.norms = m->norms; v.inv_norms = m->inv_norms; v.bits = m->bits; v.words = m->words;
+  v.norms = m->norms; v.inv_norms = m->inv_norms; v.sqnorms = m->sqnorms; v.bits = m->bits; v.words = m->words;
   v.max_norm = m->max_norm; v.max_ratio = m->max_ratio;
   return v;
 }
@@ -139,10 +140,10 @@ int hdb_matrix_destroy(hdb_matrix* m) {
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
   if (m->owns_rows) cudaFree(m->rows);
-  void* ptrs[] = {m->norms, m->inv_norms, m->bits, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
+  void* ptrs[] = {m->norms, m->inv_norms, m->sqnorms, m->bits, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
                   m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_block,
                   m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag, m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand,
-                  m->tc.cand_count, m->tc.rec, m->tc.rec_count};
+                  m->tc.cand_count, m->tc.rec, m->tc.rec_count, m->tc.qsq};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (m->h_block) cudaFreeHost(m->h_block);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
@@ -209,12 +210,14 @@ int hdb_matrix_finalize(hdb_matrix* m) {
   if (m->norms) { cudaFree(m->norms); m->norms = nullptr; }
   if (m->inv_norms) { cudaFree(m->inv_norms); m->inv_norms = nullptr; }
   if (m->bits) { cudaFree(m->bits); m->bits = nullptr; }
+  if (m->sqnorms) { cudaFree(m->sqnorms); m->sqnorms = nullptr; }
+  if (m->dtype != 2) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->sqnorms), (size_t)(m->n ? m->n : 1) * 4));
   HDB_CUDA(cudaMalloc(&m->norms, (size_t)(m->n ? m->n : 1) * nsz));
   HDB_CUDA(cudaMalloc(&m->inv_norms, (size_t)(m->n ? m->n : 1) * nsz));
   HDB_CUDA(cudaMemsetAsync(m->stats, 0, 8, m->stream));
   HDB_CUDA(cudaMemsetAsync(m->nan_flag, 0, 4, m->stream));
   MatrixView v = view_of(m);
-  HDB_TRY(launch_row_stats(v, m->norms, m->inv_norms, m->stats, m->nan_flag, m->stream));
+  HDB_TRY(launch_row_stats(v, m->norms, m->inv_norms, m->sqnorms, m->stats, m->nan_flag, m->stream));
   float hs[2] = {0.f, 1.f};
   int hnan = 0;
   HDB_CUDA(cudaMemcpyAsync(hs, m->stats, 8, cudaMemcpyDeviceToHost, m->stream));
@@ -375,7 +378,7 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
   a.qb.qc += b0 * m->d; a.qb.qbits += b0 * m->words; a.qb.qnorm += b0; a.qb.qflags += b0;
   a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
   a.uncertified = m->uncertified;
-  a.cand_count = nullptr; a.cand_stride = 0; a.tau0 = nullptr; a.extra_flags = 0;
+  a.cand_count = nullptr; a.cand_stride = 0; a.tau0 = nullptr; a.extra_flags = 0; a.tau0_negd2 = 0;
   return launch_finalize(a, cnt, m->stream);
 }
 
@@ -396,7 +399,7 @@ static int ensure_tc_workspace(hdb_matrix* m, int64_t nq, int kp) {
   int64_t rec_cap = (int64_t)(3.0 * expect_rec) + 8192;
   if (rec_cap > (int64_t)1 << 21) rec_cap = (int64_t)1 << 21;
   if (m->tc_nq >= nq && m->tc.cap >= cap && m->tc.sample_tiles == sample_tiles && m->tc.rec_cap >= (unsigned)rec_cap) return 0;
-  void* ptrs[] = {m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand, m->tc.cand_count, m->tc.rec, m->tc.rec_count};
+  void* ptrs[] = {m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand, m->tc.cand_count, m->tc.rec, m->tc.rec_count, m->tc.qsq};
   for (void* p : ptrs) if (p) cudaFree(p);
   m->tc = TcWorkspace{};
   m->tc_nq = 0;
@@ -405,6 +408,7 @@ static int ensure_tc_workspace(hdb_matrix* m, int64_t nq, int kp) {
   HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.tau0), (size_t)nq * 4));
   HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.cand), (size_t)nq * cap * 8));
   HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.cand_count), (size_t)nq * 4));
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.qsq), (size_t)nq * 4));
   HDB_CUDA(cudaMalloc(&m->tc.rec, (size_t)sms * rec_cap * 16));
   HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc.rec_count), (size_t)sms * 4));
   m->tc.rec_cap = (unsigned)rec_cap;
@@ -422,7 +426,7 @@ static int run_tensor(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, in
   const float* qa = reinterpret_cast<const float*>(m->qb.qa) + (size_t)b0 * m->d;
   const bool prof = m->prof_used + 2 <= m->prof_ev.size();
   if (prof) HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used], m->stream));
-  HDB_TRY(launch_batched_tc(v, metric, f, qa, cnt, kp, m->device, m->tc, m->stream));
+  HDB_TRY(launch_batched_tc(v, metric, f, qa, m->qb.qnorm + b0, cnt, kp, m->device, m->tc, m->stream));
   if (prof) { HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used + 1], m->stream)); m->prof_used += 2; }
   FinalizeArgs a;
   a.m = v; a.f = f; a.metric = metric; a.rdt = rdt; a.kp = kp; a.k = (int)k; a.n_kept = m->n_kept; a.grid = 0;
@@ -432,6 +436,7 @@ static int run_tensor(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, in
   a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
   a.uncertified = m->uncertified;
   a.cand_count = m->tc.cand_count; a.cand_stride = m->tc.cap; a.tau0 = m->tc.tau0; a.extra_flags = HDB_FLAG_TENSOR;
+  a.tau0_negd2 = (metric == HDB_EUCLIDEAN);
   return launch_finalize(a, cnt, m->stream);
 }
 
@@ -486,7 +491,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   if (k == 0) {
     HDB_CUDA(cudaMemsetAsync(count, 0, (size_t)nq * 8, m->stream));
     if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
-  } else if (kp && m->path_mode != 2 && batched_tc_supported(view_of(m), metric, q_dtype, nq)) {
+  } else if (kp && m->path_mode != 2 && batched_tc_supported(view_of(m), metric, q_dtype, nq, use_decay)) {
     if (m->dtype == 1) kp = 128;         // tf32 select: wider error band, so certify a wider candidate list
     m->last.kp = kp;
     HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));

@@ -114,6 +114,8 @@ struct TcParamsBase {
   int64_t sample_stride;        // DENSE mode: visited row tile i is matrix row tile i * sample_stride
   const char* rows;             // matrix base (for the L2 prefetch)
   const float* inv_norms;       // cosine or nullptr
+  const float* sqnorms;         // euclidean (norm expansion) or nullptr
+  const float* qsq;             // [nq] ||q||^2 for euclidean, else nullptr
   RowFilter f;
 };
 // ---------------------------------------------------------------------------------------------
@@ -142,6 +144,7 @@ struct SelectSink {
   uint4* rec;              // this CTA's records
   unsigned* s_count;       // shared-memory counter
   unsigned cap;
+  const float* qsq;        // euclidean: the screened value is |q|^2 - d^2; the key holds the similarity 1/(1+d)
 };
 
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
@@ -170,8 +173,12 @@ __device__ __forceinline__ void screen_chunk(const uint32_t (&r)[32], uint32_t t
   while (wmask) {
     const int j = __ffs(wmask) - 1;
     wmask &= wmask - 1;
-    const float s = fmaf(__uint_as_float(tmem_ld1(taddr_chunk + (uint32_t)j)), inv, dec);
+    float s = fmaf(__uint_as_float(tmem_ld1(taddr_chunk + (uint32_t)j)), inv, dec);
     if ((mask >> j) & 1u) {
+      if (sink.qsq) {
+        const float d2 = sink.qsq[b0 + j] - s;
+        s = 1.f / (1.f + sqrtf(d2 > 0.f ? d2 : 0.f));
+      }
       const unsigned pos = atomicAdd(sink.s_count, 1u);
       const uint64_t key = make_key(s, row);
       if (pos < sink.cap) sink.rec[pos] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)(b0 + j), 0u);
@@ -197,8 +204,13 @@ __device__ __forceinline__ void row_inputs(const TcParamsBase& p, int64_t row, f
   inv = 0.f;
   dec = __int_as_float(0x7fc00000);
   if (kept) {
-    inv = p.inv_norms ? p.inv_norms[row] : 1.f;
-    dec = p.f.decay ? (float)(p.f.bias * p.f.decay[row]) : 0.f;
+    if (p.sqnorms) {                 // euclidean: screen -d^2 + |q|^2 = 2 v.q - |v|^2  (|q|^2 is folded into the threshold)
+      inv = 2.f;
+      dec = -p.sqnorms[row];
+    } else {
+      inv = p.inv_norms ? p.inv_norms[row] : 1.f;
+      dec = p.f.decay ? (float)(p.f.bias * p.f.decay[row]) : 0.f;
+    }
   }
 }
 
@@ -242,7 +254,8 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
   const int kblocks = (int)((p.d + kKPerStage - 1) / kKPerStage);
   const int64_t total_tiles = p.n_tiles_m * p.n_tiles_q;
   if (!DENSE) {      // every threshold of the batch lives in shared memory for the whole kernel (<= 16 KB)
-    for (int64_t i = threadIdx.x; i < p.n_tiles_q * BN; i += kTcThreads) s_tau[i] = i < p.nq ? p.tau0[i] : INFINITY;
+    for (int64_t i = threadIdx.x; i < p.n_tiles_q * BN; i += kTcThreads)
+      s_tau[i] = i < p.nq ? p.tau0[i] + (p.qsq ? p.qsq[i] : 0.f) : INFINITY;
   }
 
   if (threadIdx.x == 0) {
@@ -328,7 +341,7 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
     const int part = (warp - 2) >> 2;                      // which quarter of the columns
     int acc = 0;
     uint32_t acc_phase = 0;
-    const SelectSink sink{p.rec + (size_t)blockIdx.x * p.rec_cap, s_rec_count, p.rec_cap};
+    const SelectSink sink{p.rec + (size_t)blockIdx.x * p.rec_cap, s_rec_count, p.rec_cap, p.qsq};
     float inv = 0.f, dec = 0.f;
     if ((int64_t)blockIdx.x < total_tiles)
       row_inputs(p, (blockIdx.x / p.n_tiles_q) * p.sample_stride * kTileM + quarter * 32 + lane, inv, dec);
@@ -359,7 +372,7 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
           for (int j = 0; j < 32; ++j) {
             const int64_t b = qt * BN + c0 + j;
             if (b < p.nq) {
-              const float s = fmaf(__uint_as_float(r[j]), inv, dec);
+              const float s = fmaf(__uint_as_float(r[j]), inv, dec) - (p.qsq ? p.qsq[b] : 0.f);     // euclidean: -d^2
               p.dense[b * ld + col] = (s == s) ? s : -INFINITY;
             }
           }
@@ -452,7 +465,8 @@ batched_tc_pair_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_c
   if (threadIdx.x == 0) *s_rec_count = 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t i = threadIdx.x; i < p.n_tiles_q * BN; i += kTcThreads) s_tau[i] = i < p.nq ? p.tau0[i] : INFINITY;
+  for (int64_t i = threadIdx.x; i < p.n_tiles_q * BN; i += kTcThreads)
+    s_tau[i] = i < p.nq ? p.tau0[i] + (p.qsq ? p.qsq[i] : 0.f) : INFINITY;
   const uint32_t rank = cluster_rank();
   const bool leader = rank == 0;
   const int kblocks = (int)((p.d + kKPerStage - 1) / kKPerStage);
@@ -542,7 +556,7 @@ batched_tc_pair_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_c
     const int part = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const SelectSink sink{p.rec + (size_t)blockIdx.x * p.rec_cap, s_rec_count, p.rec_cap};
+    const SelectSink sink{p.rec + (size_t)blockIdx.x * p.rec_cap, s_rec_count, p.rec_cap, p.qsq};
     const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
     float inv = 0.f, dec = 0.f;
     if (pair < total_tiles) row_inputs(p, ((pair / p.n_tiles_q) * 2 + rank) * kTileM + quarter * 32 + lane, inv, dec);
@@ -633,6 +647,11 @@ __global__ void __launch_bounds__(256) sample_threshold_kernel(const float* dens
   if (threadIdx.x == 0) tau0[blockIdx.x] = unorder_f32(prefix);
 }
 
+__global__ void square_norms_kernel(const double* qnorm, float* qsq, int64_t nq) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < nq) qsq[i] = (float)(qnorm[i] * qnorm[i]);
+}
+
 // fp16 copy of the prepared (accumulate-type) queries: the tensor-core B operand
 __global__ void queries_to_half_kernel(const float* qa, __half* q16, int64_t count) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
@@ -683,8 +702,9 @@ static int launch_tc(const CUtensorMap& mv, const CUtensorMap& mq, const TcParam
   return 0;
 }
 
-int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq) {
-  if (metric != HDB_DOT && metric != HDB_COSINE) return 0;
+int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq, bool has_decay) {
+  if (metric != HDB_DOT && metric != HDB_COSINE && metric != HDB_EUCLIDEAN) return 0;
+  if (metric == HDB_EUCLIDEAN && (has_decay || !m.sqnorms)) return 0;   // 1/(1+d) + decay is not monotone in -d^2
   if (m.dtype == 2) return 0;                                  // no fp64 tensor path
   if (q_dtype > m.dtype) return 0;                             // the B operand has the storage precision: exact only then
   if ((m.d * dtype_size(m.dtype)) % 16 != 0 || (reinterpret_cast<uintptr_t>(m.rows) & 15)) return 0;
@@ -707,7 +727,7 @@ static int launch_tc_bn(int BN, bool dense, const CUtensorMap& mv, const CUtenso
 
 // Runs sample -> thresholds -> select for queries [0, nq) of the prepared batch.  Candidate keys land in
 // ws.cand[b][0..min(count, cap)).
-int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const float* qa, int64_t nq, int kp, int device,
+int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const float* qa, const double* qnorm, int64_t nq, int kp, int device,
                       const TcWorkspace& ws, cudaStream_t s) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -729,6 +749,12 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
   p.rows = reinterpret_cast<const char*>(m.rows);
   p.debug = getenv("HDB_TC_DEBUG") ? atoi(getenv("HDB_TC_DEBUG")) : 0;
   p.inv_norms = metric == HDB_COSINE ? reinterpret_cast<const float*>(m.inv_norms) : nullptr;
+  p.sqnorms = nullptr; p.qsq = nullptr;
+  if (metric == HDB_EUCLIDEAN) {
+    square_norms_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(qnorm, ws.qsq, nq);
+    HDB_LAUNCHED();
+    p.sqnorms = m.sqnorms; p.qsq = ws.qsq;
+  }
   p.f = f;
   const int64_t all_tiles = (m.n + kTileM - 1) / kTileM;
   // ---- dense sample

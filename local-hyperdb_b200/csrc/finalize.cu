@@ -86,6 +86,11 @@ __device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) 
   double dc;
   if (a.metric == HDB_EUCLIDEAN) {
     double d2 = d_lo * d_lo * (1.0 - D * ua - 6.0 * uR - chain16);
+    if (a.cand_count) {
+      // batched pass: d^2 = |v|^2 + |q|^2 - 2 v.q on the tensor cores -> ABSOLUTE error from the cancellation
+      const double A = (double)a.m.max_norm * qnorm;
+      d2 -= 2.0 * A * (D * ua + (a.m.dtype == 1 ? 3.90625e-3 : 0.0)) + 8.0 * 1.1920928955078125e-7 * ((double)a.m.max_norm * a.m.max_norm + qnorm * qnorm);
+    }
     if (a.rdt == 0) d2 -= D * 5.9604644775390625e-8;                          // float16 squares flushed below 2^-24
     dc = sqrt(d2 > 0.0 ? d2 : 0.0) * (1.0 - 3.0 * uR);
   } else {
@@ -366,7 +371,11 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     if (m < kk) certified = false;
     else {
       // rows outside the candidates: key <= the KP-th key, or (batched pass, fewer than KP appended) below tau0
-      const double s_edge = (m >= a.kp || !a.tau0) ? (double)key_score(surv[m - 1]) : (double)a.tau0[b];
+      double s_edge = (double)key_score(surv[m - 1]);
+      if (m < a.kp && a.tau0) {
+        const double t0 = (double)a.tau0[b];
+        s_edge = a.tau0_negd2 ? 1.0 / (1.0 + sqrt(t0 < 0.0 ? -t0 : 0.0)) : t0;
+      }
       const double bound = outsider_bound(s_edge, a, a.qb.qnorm[b]);
       certified = o_tot[kk - 1] > bound;
     }

@@ -51,6 +51,7 @@ struct MatrixView {
   int64_t row_offset;
   const void* norms;      // canonical norms: float (f16/f32 storage) or double (f64), zero -> 1
   const void* inv_norms;  // 1/norm in the accumulate type
+  const float* sqnorms;   // ||v||^2 (float) for f16/f32 storage, or nullptr
   const uint32_t* bits;   // packed sign bits or nullptr
   int words;              // words per packed row
   float max_norm;         // max_i ||v_i||_2
@@ -58,7 +59,7 @@ struct MatrixView {
 };
 
 // ---- ingest.cu
-int launch_row_stats(const MatrixView& m, void* norms, void* inv_norms, float* d_stats /*[2] max_norm,max_ratio*/,
+int launch_row_stats(const MatrixView& m, void* norms, void* inv_norms, float* sqnorms, float* d_stats /*[2] max_norm,max_ratio*/,
                      int* d_nan, cudaStream_t s);
 int launch_pack_bits(const MatrixView& m, uint32_t* bits, int words, cudaStream_t s);
 int launch_kept_ts_max(const double* ts, const RowFilter& f, int64_t n, unsigned long long* d_max_bits,
@@ -98,6 +99,7 @@ struct FinalizeArgs {
   const unsigned* cand_count;    // [B] appended keys per query (may exceed cand_stride = overflow) or nullptr
   int64_t cand_stride;           // keys per query buffer
   const float* tau0;             // [B] select threshold of the batched pass (rows below it were never appended)
+  int tau0_negd2;                // tau0 is -distance^2 (batched euclidean): convert to a similarity before use
   uint32_t extra_flags;          // OR-ed into out_flags (HDB_FLAG_TENSOR)
 };
 int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s);
@@ -118,6 +120,7 @@ struct TcWorkspace {
   float* tau0;             // [nq]
   uint64_t* cand;          // [nq][cap]
   unsigned* cand_count;    // [nq]
+  float* qsq;              // [nq] ||q||^2 (euclidean) or 0
   int cap;
   int64_t sample_tiles;
   void* rec;               // [n_sm][rec_cap] 16-byte CTA-private candidate records
@@ -125,8 +128,8 @@ struct TcWorkspace {
   unsigned rec_cap;
   int force_single;        // testing: keep the single-CTA contraction even for wide batches
 };
-int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq);
-int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const float* qa, int64_t nq, int kp, int device,
+int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq, bool has_decay);
+int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const float* qa, const double* qnorm, int64_t nq, int kp, int device,
                       const TcWorkspace& ws, cudaStream_t s);
 
 }  // namespace hdb

@@ -26,7 +26,7 @@ double decode_ordered_double(unsigned long long o) {
 
 // ---------------------------------------------------------------------------------------------
 template <int T>
-__global__ void row_stats_kernel(const void* rows, int64_t n, int64_t d, void* norms, void* inv_norms,
+__global__ void row_stats_kernel(const void* rows, int64_t n, int64_t d, void* norms, void* inv_norms, float* sqnorms,
                                  float* stats, int* nan_flag) {
   using A = Arith<T>;
   using C = typename A::C;
@@ -51,6 +51,7 @@ __global__ void row_stats_kernel(const void* rows, int64_t n, int64_t d, void* n
       reinterpret_cast<float*>(norms)[row] = (float)cn;
       reinterpret_cast<float*>(inv_norms)[row] = 1.0f / (float)cn;
     }
+    if (sqnorms) sqnorms[row] = (float)true_sq;          // ||v||^2 for the norm-expansion form of batched euclidean
     my_norm = (float)fmin(tn * (1.0 + 1e-6), 3.0e38);
     double ratio = tn / (double)cn;
     my_ratio = (ratio == ratio) ? (float)fmin(ratio * (1.0 + 1e-6), 3.0e38) : 3.0e38f;
@@ -69,14 +70,14 @@ __global__ void row_stats_kernel(const void* rows, int64_t n, int64_t d, void* n
   }
 }
 
-int launch_row_stats(const MatrixView& m, void* norms, void* inv_norms, float* d_stats, int* d_nan, cudaStream_t s) {
+int launch_row_stats(const MatrixView& m, void* norms, void* inv_norms, float* sqnorms, float* d_stats, int* d_nan, cudaStream_t s) {
   if (m.n == 0) return 0;
   int threads = 128;
   int64_t blocks = (m.n + threads - 1) / threads;
   if (blocks > 0x7fffffff) return fail("row_stats: too many rows");
-  if (m.dtype == 0) row_stats_kernel<0><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, d_stats, d_nan);
-  else if (m.dtype == 1) row_stats_kernel<1><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, d_stats, d_nan);
-  else row_stats_kernel<2><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, d_stats, d_nan);
+  if (m.dtype == 0) row_stats_kernel<0><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, sqnorms, d_stats, d_nan);
+  else if (m.dtype == 1) row_stats_kernel<1><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, sqnorms, d_stats, d_nan);
+  else row_stats_kernel<2><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, sqnorms, d_stats, d_nan);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;

@@ -237,7 +237,7 @@ def test_range_and_batch(hb):
 
 # ---- tensor-core batched path (tcgen05) == streaming sweep == oracle ------------------------------------------------
 @pytest.mark.parametrize("sdt", ["float16", "float32"])
-@pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity"])
+@pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity", "euclidean_metric"])
 @pytest.mark.parametrize("nq", [17, 64, 130, 300])
 def test_batched_tensor_path(hb, metric, nq, sdt):
     import torch
@@ -246,8 +246,14 @@ def test_batched_tensor_path(hb, metric, nq, sdt):
     g = torch.Generator(device=dev)
     g.manual_seed(nq)
     V = torch.randn(n, d, generator=g, device=dev) * (0.5 + torch.rand(n, 1, generator=g, device=dev))
+    if metric == "euclidean_metric":
+        # the norm expansion |v|^2 + |q|^2 - 2 v.q cancels: its certificate only holds on embedding-like (unit-norm) data;
+        # anything else is still answered exactly, by the sweep or the exact path (checked below through the equality)
+        V = V / V.norm(dim=1, keepdim=True)
     V = V.half() if sdt == "float16" else V.float()
     Q = torch.randn(nq, d, generator=g, device=dev)
+    if metric == "euclidean_metric":
+        Q = Q / Q.norm(dim=1, keepdim=True)
     Q = Q.half() if sdt == "float16" else Q.float()
     ts = 1.7e9 + 10 * torch.rand(n, generator=g, device=dev, dtype=torch.float64)
     keep_bits = torch.randint(-2**31, 2**31 - 1, ((n + 31) // 32,), generator=g, device=dev, dtype=torch.int32)
@@ -260,14 +266,22 @@ def test_batched_tensor_path(hb, metric, nq, sdt):
             if use_ts:
                 m.refresh_decay()
             bias = 0.2 if use_ts else 0.0
-            m.set_path(2)                                       # streaming sweep, one launch per query
-            i0, s0, c0, f0 = m.query(q_np, k, metric, bias)
+            # reference: the streaming sweep (forced), or for euclidean -- whose float16 scores tie so densely on
+            # this data that the sweep's own certificate may refuse -- the exact path on the first queries
+            nref = nq if metric != "euclidean_metric" else min(nq, 24)
+            m.set_path(2 if metric != "euclidean_metric" else 1)
+            i0, s0, c0, f0 = m.query(q_np[:nref], k, metric, bias)
             m.set_path(0)                                       # automatic: tensor cores for >= 16 queries
             i1, s1, c1, f1 = m.query(q_np, k, metric, bias)
+            i1c, s1c, c1c = i1[:nref], s1[:nref], c1[:nref]
             # bit 4 = answered by the tensor-core pass; queries its certificate rejected are re-run by the sweep
-            assert sum(1 for f in f1 if f & 4) >= 0.7 * nq, ("tensor-core path was not taken", f1.tolist())
-            assert sum(1 for f in f1 if f & 1) <= nq // 8, "too many exact-path fallbacks on the tensor path"
-            assert np.array_equal(i0, i1) and np.array_equal(s0, s1) and np.array_equal(c0, c1)
+            if not (metric == "euclidean_metric" and use_ts):     # 1/(1+d) + decay is not monotone in -d^2: sweeps
+                assert sum(1 for f in f1 if f & 4) >= 0.7 * nq, ("tensor-core path was not taken", f1.tolist())
+            if not (metric == "euclidean_metric" and sdt == "float16"):
+                # (float16 euclidean scores are so coarse -- ulp 2.4e-4 at 0.44 -- that with k = 100 of 128 candidates the
+                #  worst-case certificate legitimately refuses and the exact path answers; equality below still holds)
+                assert sum(1 for f in f1 if f & 1) <= nq // 8, "too many exact-path fallbacks on the tensor path"
+            assert np.array_equal(i0, i1c) and np.array_equal(s0, s1c) and np.array_equal(c0, c1c)
         # and against the oracle on a row subset small enough for it
         m.set_mask(None)
         m.set_timestamps(None)
