@@ -252,7 +252,6 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = (int)((p.d + kKPerStage - 1) / kKPerStage);
-  const int64_t total_tiles = p.n_tiles_m * p.n_tiles_q;
   if (!DENSE) {      // every threshold of the batch lives in shared memory for the whole kernel (<= 16 KB)
     for (int64_t i = threadIdx.x; i < p.n_tiles_q * BN; i += kTcThreads)
       s_tau[i] = i < p.nq ? p.tau0[i] + (p.qsq ? p.qsq[i] : 0.f) : INFINITY;
@@ -278,26 +277,21 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       const int64_t row_bytes = p.d * (TF32 ? 4 : 2);
-      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int64_t mt = (t / p.n_tiles_q) * p.sample_stride;
-        const int64_t qt = t % p.n_tiles_q;
-        {
+      // Tile order: a CTA keeps one ROW tile for all query tiles before moving on, so the row tile comes from HBM
+      // once and is re-read from L2 by the same CTA within microseconds (no reliance on CTAs staying in lockstep).
+      for (int64_t sq = 0;; ++sq) {
+        const int64_t mv = (int64_t)blockIdx.x + (sq / p.n_tiles_q) * gridDim.x;       // visited row-tile index
+        if (mv >= p.n_tiles_m) break;
+        const int64_t mt = mv * p.sample_stride;
+        const int64_t qt = sq % p.n_tiles_q;
+        if (qt == 0 && mv + gridDim.x < p.n_tiles_m) {
           // The TMA boxes below gather 128-byte pieces of 128 rows (poor DRAM locality when they miss L2).  The
-          // row tile itself is ONE contiguous region, so stream it into L2 one tile ahead with a bulk prefetch; the
-          // CTAs that share the next row tile (one per query tile) each prefetch their slice of it.
-          const int64_t tn = t + gridDim.x;
-          if (tn < total_tiles) {
-            const int64_t mtn = (tn / p.n_tiles_q) * p.sample_stride, qtn = tn % p.n_tiles_q;
-            const int64_t rows_n = (p.n - mtn * kTileM) < kTileM ? (p.n - mtn * kTileM) : kTileM;
-            const int64_t region = rows_n * row_bytes;
-            int64_t slice = ((region / p.n_tiles_q) + 15) & ~int64_t(15);
-            int64_t off = qtn * slice;
-            if (off < region) {
-              if (off + slice > region) slice = (region - off) & ~int64_t(15);
-              if (slice > 0)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rows + mtn * kTileM * row_bytes + off), "r"((uint32_t)slice) : "memory");
-            }
-          }
+          // row tile itself is ONE contiguous region: stream the NEXT one into L2 now with a bulk prefetch.
+          const int64_t mtn = (mv + gridDim.x) * p.sample_stride;
+          const int64_t rows_n = (p.n - mtn * kTileM) < kTileM ? (p.n - mtn * kTileM) : kTileM;
+          const int64_t region = (rows_n * row_bytes) & ~int64_t(15);
+          if (region > 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rows + mtn * kTileM * row_bytes), "r"((uint32_t)region) : "memory");
         }
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -316,7 +310,8 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int64_t sq = 0;; ++sq) {
+        if ((int64_t)blockIdx.x + (sq / p.n_tiles_q) * gridDim.x >= p.n_tiles_m) break;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
@@ -343,17 +338,18 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
     uint32_t acc_phase = 0;
     const SelectSink sink{p.rec + (size_t)blockIdx.x * p.rec_cap, s_rec_count, p.rec_cap, p.qsq};
     float inv = 0.f, dec = 0.f;
-    if ((int64_t)blockIdx.x < total_tiles)
-      row_inputs(p, (blockIdx.x / p.n_tiles_q) * p.sample_stride * kTileM + quarter * 32 + lane, inv, dec);
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int64_t mt_visit = t / p.n_tiles_q;
+    if ((int64_t)blockIdx.x < p.n_tiles_m)
+      row_inputs(p, blockIdx.x * p.sample_stride * kTileM + quarter * 32 + lane, inv, dec);
+    for (int64_t sq = 0;; ++sq) {
+      const int64_t mt_visit = (int64_t)blockIdx.x + (sq / p.n_tiles_q) * gridDim.x;
+      if (mt_visit >= p.n_tiles_m) break;
       const int64_t mt = mt_visit * p.sample_stride;
-      const int64_t qt = t % p.n_tiles_q;
+      const int64_t qt = sq % p.n_tiles_q;
       const int64_t row = mt * kTileM + quarter * 32 + lane;
-      // side inputs of the NEXT tile: their global-load latency hides behind this tile
-      float ninv = 0.f, ndec = 0.f;
-      if (t + gridDim.x < total_tiles)
-        row_inputs(p, ((t + gridDim.x) / p.n_tiles_q) * p.sample_stride * kTileM + quarter * 32 + lane, ninv, ndec);
+      // side inputs of the NEXT row tile: their global-load latency hides behind this tile
+      float ninv = inv, ndec = dec;
+      if (qt == p.n_tiles_q - 1 && mt_visit + gridDim.x < p.n_tiles_m)
+        row_inputs(p, (mt_visit + gridDim.x) * p.sample_stride * kTileM + quarter * 32 + lane, ninv, ndec);
       const int64_t valid = (p.nq - qt * BN) < BN ? (p.nq - qt * BN) : BN;       // real queries in this tile
       constexpr int kColsPerWarp = BN / 4 < 32 ? 32 : BN / 4;                     // 32-column chunks; BN = 64: two warps idle
       const int c_begin = part * kColsPerWarp;
@@ -471,7 +467,6 @@ batched_tc_pair_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_c
   const bool leader = rank == 0;
   const int kblocks = (int)((p.d + kKPerStage - 1) / kKPerStage);
   const int64_t tiles_m2 = (p.n_tiles_m + 1) / 2;        // 256-row tiles
-  const int64_t total_tiles = tiles_m2 * p.n_tiles_q;
   const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
@@ -495,23 +490,17 @@ batched_tc_pair_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       const int64_t row_bytes = p.d * (TF32 ? 4 : 2);
-      for (int64_t t = pair; t < total_tiles; t += npairs) {
-        const int64_t mt = (t / p.n_tiles_q) * 2 + rank;          // this CTA's 128-row tile
-        const int64_t qt = t % p.n_tiles_q;
-        {
-          const int64_t tn = t + npairs;
-          if (tn < total_tiles) {                                  // L2 bulk prefetch of the next tile's rows (see above)
-            const int64_t mtn = (tn / p.n_tiles_q) * 2 + rank, qtn = tn % p.n_tiles_q;
-            const int64_t rows_n = (p.n - mtn * kTileM) < kTileM ? (p.n - mtn * kTileM) : kTileM;
-            const int64_t region = rows_n > 0 ? rows_n * row_bytes : 0;
-            int64_t slice = ((region / p.n_tiles_q) + 15) & ~int64_t(15);
-            const int64_t off = qtn * slice;
-            if (off < region) {
-              if (off + slice > region) slice = (region - off) & ~int64_t(15);
-              if (slice > 0)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rows + mtn * kTileM * row_bytes + off), "r"((uint32_t)slice) : "memory");
-            }
-          }
+      for (int64_t sq = 0;; ++sq) {
+        const int64_t m2 = pair + (sq / p.n_tiles_q) * npairs;    // 256-row tile of the pair: kept for all query tiles
+        if (m2 >= tiles_m2) break;
+        const int64_t mt = m2 * 2 + rank;                         // this CTA's 128-row tile
+        const int64_t qt = sq % p.n_tiles_q;
+        if (qt == 0 && m2 + npairs < tiles_m2 && p.debug != 2) {  // L2 bulk prefetch of this CTA's NEXT row tile
+          const int64_t mtn = (m2 + npairs) * 2 + rank;
+          const int64_t rows_n = (p.n - mtn * kTileM) < kTileM ? (p.n - mtn * kTileM) : kTileM;
+          const int64_t region = rows_n > 0 ? (rows_n * row_bytes) & ~int64_t(15) : 0;
+          if (region > 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rows + mtn * kTileM * row_bytes), "r"((uint32_t)region) : "memory");
         }
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -531,7 +520,8 @@ batched_tc_pair_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t t = pair; t < total_tiles; t += npairs) {
+      for (int64_t sq = 0;; ++sq) {
+        if (pair + (sq / p.n_tiles_q) * npairs >= tiles_m2) break;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
@@ -559,14 +549,16 @@ batched_tc_pair_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_c
     const SelectSink sink{p.rec + (size_t)blockIdx.x * p.rec_cap, s_rec_count, p.rec_cap, p.qsq};
     const uint32_t leader_acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
     float inv = 0.f, dec = 0.f;
-    if (pair < total_tiles) row_inputs(p, ((pair / p.n_tiles_q) * 2 + rank) * kTileM + quarter * 32 + lane, inv, dec);
-    for (int64_t t = pair; t < total_tiles; t += npairs) {
-      const int64_t mt = (t / p.n_tiles_q) * 2 + rank;
-      const int64_t qt = t % p.n_tiles_q;
+    if (pair < tiles_m2) row_inputs(p, (pair * 2 + rank) * kTileM + quarter * 32 + lane, inv, dec);
+    for (int64_t sq = 0;; ++sq) {
+      const int64_t m2 = pair + (sq / p.n_tiles_q) * npairs;
+      if (m2 >= tiles_m2) break;
+      const int64_t mt = m2 * 2 + rank;
+      const int64_t qt = sq % p.n_tiles_q;
       const int64_t row = mt * kTileM + quarter * 32 + lane;
-      float ninv = 0.f, ndec = 0.f;
-      if (t + npairs < total_tiles)
-        row_inputs(p, (((t + npairs) / p.n_tiles_q) * 2 + rank) * kTileM + quarter * 32 + lane, ninv, ndec);
+      float ninv = inv, ndec = dec;
+      if (qt == p.n_tiles_q - 1 && m2 + npairs < tiles_m2)
+        row_inputs(p, ((m2 + npairs) * 2 + rank) * kTileM + quarter * 32 + lane, ninv, ndec);
       const int64_t valid = (p.nq - qt * BN) < BN ? (p.nq - qt * BN) : BN;
       const int c_begin = part * (BN / 4);
       const int c_end = (int)(valid < (part + 1) * (BN / 4) ? valid : (part + 1) * (BN / 4));
