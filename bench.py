@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debugging only; invalidates the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="keep every kernel of a query on one stream")
     ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph (single GPU only)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -252,6 +253,8 @@ def main():
         m.set_mask(keep_bits)
     eng = CudaEngine(m)
     sm = ShardedMatrix(eng, w["n"])
+    if not args.no_pipeline and w["b"] < 16:
+        eng.enable_pipeline()            # certify/exchange/merge of query i overlap the sweep of query i+1
     bias = 0.0
     if w.get("decay"):
         g = torch.Generator(device=dev)
@@ -279,7 +282,7 @@ def main():
     # ---- device-resident arm (value) ------------------------------------------------------------
     # one captured CUDA graph per step when the step is short enough for host launch overhead to matter
     graphed = None
-    if args.graph and world == 1 and b <= 64:      # opt-in: NCCL collectives captured in a graph stalled at teardown here
+    if args.graph and world == 1 and b <= 64 and eng.post is None:      # opt-in: NCCL collectives captured in a graph stalled at teardown here
         from hyperdb_b200.sharded import GraphedQuery
         graphed = GraphedQuery(sm, qslice(q_dev, 0), k, w["metric"], bias)
     step = (lambda q: graphed.replay(q)) if graphed else (lambda q: sm.query_async(q, k, w["metric"], bias))
@@ -302,6 +305,7 @@ def main():
             flag_log.append(o[3].clone())            # the static outputs are overwritten by the next replay
         else:
             outs.append(o)
+    sm.wait_results()                                # pipelined mode: the last certify/exchange/merge run on the post stream
     e1.record()
     barrier()
     launches = N.lib().hdb_launch_count(0)
@@ -363,7 +367,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "rows": w["n"], "dim": w["d"], "metric": w["metric"], "top_k": k, "batch": b,
                        "sharding": f"rows/{world}", "l2": "inputs larger than L2 (shard %.2f GB per GPU, a new query every step)"
-                       % (shard_bytes / 1e9), "uncertified_steps": uncertified, "cuda_graph": bool(graphed)},
+                       % (shard_bytes / 1e9), "uncertified_steps": uncertified, "cuda_graph": bool(graphed),
+                       "pipelined": eng.post is not None},
             "clocks": clocks,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(b * w["d"] * ITEM[w["dtype"]]),
                     "d2h_bytes_per_step": int(b * k * 16 + b * 8), "steps": e2e_steps},

@@ -66,6 +66,11 @@ int hdb_matrix_adopt(hdb_matrix* m, void* device_rows);
 int hdb_matrix_finalize(hdb_matrix* m);
 /* Run the handle's work on this cudaStream_t (NULL = legacy default stream). */
 int hdb_matrix_set_stream(hdb_matrix* m, void* cuda_stream);
+/* Query pipelining for device-output calls.  With a post stream set, hdb_query(..., HDB_DEVICE) enqueues the query
+ * preparation and the streaming sweep on the handle's stream and the certify step on `post_stream`, so that the
+ * certify (and whatever the caller enqueues after it on the post stream: the candidate exchange, the merge) of query i
+ * overlaps the sweep of query i+1.  Results are valid in POST-stream order.  NULL switches pipelining off. */
+int hdb_matrix_set_post_stream(hdb_matrix* m, void* post_stream);
 int hdb_matrix_info(const hdb_matrix* m, int* dtype, int64_t* n_rows, int64_t* dim, int64_t* row_offset,
                     int64_t* n_kept);
 

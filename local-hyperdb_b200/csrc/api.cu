@@ -57,6 +57,16 @@ struct hdb_matrix {
   void* sort_scratch = nullptr; size_t sort_scratch_bytes = 0;
   unsigned long long* misc = nullptr;   // [2] ordered max bits, count
   float* stats = nullptr; int* nan_flag = nullptr;
+  // query pipelining (hdb_matrix_set_post_stream): the per-query workspaces exist twice so that the certify step of
+  // query i (post stream) can overlap the sweep of query i+1 (main stream)
+  struct QuerySlot {
+    int64_t ws_q = 0; void* q_raw = nullptr; QueryBuffers qb{}; uint64_t* cand = nullptr; unsigned long long* tau = nullptr;
+    cudaEvent_t done = nullptr; bool pending = false;
+  } slots[2];
+  int cur_slot = 0;
+  cudaStream_t post_stream = nullptr;
+  cudaStream_t pre_stream = nullptr;     // pipelined mode: query preparation runs here, ahead of the main stream
+  cudaEvent_t ev_select = nullptr, ev_prep = nullptr;
   // tensor-core batched path workspace
   TcWorkspace tc{};
   int64_t tc_nq = 0;
@@ -66,6 +76,16 @@ struct hdb_matrix {
   // last query (for hdb_time_last_query)
   struct { bool valid = false; int metric = 0, rdt = 0, kp = 0; int64_t nq = 0, k = 0; double bias = 0; } last;
 };
+
+static void slot_store(hdb_matrix* m) {
+  hdb_matrix::QuerySlot& q = m->slots[m->cur_slot];
+  q.ws_q = m->ws_q; q.q_raw = m->q_raw; q.qb = m->qb; q.cand = m->cand; q.tau = m->tau;
+}
+static void slot_load(hdb_matrix* m, int s) {
+  m->cur_slot = s;
+  const hdb_matrix::QuerySlot& q = m->slots[s];
+  m->ws_q = q.ws_q; m->q_raw = q.q_raw; m->qb = q.qb; m->cand = q.cand; m->tau = q.tau;
+}
 
 static MatrixView view_of(const hdb_matrix* m) {
   MatrixView v;
@@ -140,6 +160,16 @@ int hdb_matrix_destroy(hdb_matrix* m) {
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
   if (m->owns_rows) cudaFree(m->rows);
+  slot_store(m);
+  {
+    hdb_matrix::QuerySlot& other = m->slots[m->cur_slot ^ 1];
+    void* extra[] = {other.q_raw, other.qb.qa, other.qb.qc, other.qb.qbits, other.qb.qnorm, other.qb.qflags, other.cand, other.tau};
+    for (void* p : extra) if (p) cudaFree(p);
+    for (auto& q : m->slots) if (q.done) cudaEventDestroy(q.done);
+    if (m->ev_select) cudaEventDestroy(m->ev_select);
+    if (m->ev_prep) cudaEventDestroy(m->ev_prep);
+    if (m->pre_stream) cudaStreamDestroy(m->pre_stream);
+  }
   void* ptrs[] = {m->norms, m->inv_norms, m->sqnorms, m->bits, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
                   m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_block,
                   m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag, m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand,
@@ -156,6 +186,29 @@ int hdb_matrix_set_stream(hdb_matrix* m, void* cuda_stream) {
   m->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   return 0;
 }
+int hdb_matrix_set_post_stream(hdb_matrix* m, void* cuda_stream) {
+  if (!m) return fail("null handle");
+  HDB_CUDA(cudaSetDevice(m->device));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->post_stream) HDB_CUDA(cudaStreamSynchronize(m->post_stream));
+  m->post_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (m->post_stream) {
+    if (!m->ev_select) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_select, cudaEventDisableTiming));
+    if (!m->ev_prep) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_prep, cudaEventDisableTiming));
+    if (!m->pre_stream) HDB_CUDA(cudaStreamCreateWithFlags(&m->pre_stream, cudaStreamNonBlocking));
+    for (auto& q : m->slots)
+      if (!q.done) HDB_CUDA(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+    m->grid = sweep_grid_size(m->device) - 2;     // leave room on one SM for the certify / exchange / merge kernels
+  } else {
+    m->grid = sweep_grid_size(m->device);
+  }
+  // the candidate buffers are sized by the grid: drop them so that they are re-allocated
+  slot_store(m);
+  for (auto& q : m->slots) { if (q.cand) { cudaFree(q.cand); q.cand = nullptr; } q.pending = false; }
+  slot_load(m, m->cur_slot);
+  return 0;
+}
+
 int hdb_matrix_set_path(hdb_matrix* m, int mode) {
   if (!m) return fail("null handle");
   if (mode < 0 || mode > 3) return fail("hdb_matrix_set_path: mode must be 0..3");
@@ -355,9 +408,9 @@ static int pick_kp(const hdb_matrix* m, int64_t k) {
 
 // Enqueue the fused path for queries [b0, b0+cnt) of the prepared batch; results go to (idx, score, count, flags).
 static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int64_t cnt, int64_t k, const RowFilter& f,
-                     int64_t* idx, double* score, int64_t* count, uint32_t* flags) {
+                     int64_t* idx, double* score, int64_t* count, uint32_t* flags, cudaStream_t fin_stream = nullptr) {
   MatrixView v = view_of(m);
-  HDB_CUDA(cudaMemsetAsync(m->tau + b0, 0, (size_t)cnt * 8, m->stream));
+  if (!(fin_stream && fin_stream != m->stream)) HDB_CUDA(cudaMemsetAsync(m->tau + b0, 0, (size_t)cnt * 8, m->stream));   // pipelined: prep zeroed it
   const int elt = (m->dtype == 2) ? 8 : 4;
   for (int64_t i = 0; i < cnt; ++i) {
     SweepOut so;
@@ -379,6 +432,12 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
   a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
   a.uncertified = m->uncertified;
   a.cand_count = nullptr; a.cand_stride = 0; a.tau0 = nullptr; a.extra_flags = 0; a.tau0_negd2 = 0;
+  if (fin_stream && fin_stream != m->stream) {
+    // pipelined: the certify step runs on the post stream, ordered after the sweeps by an event
+    HDB_CUDA(cudaEventRecord(m->ev_select, m->stream));
+    HDB_CUDA(cudaStreamWaitEvent(fin_stream, m->ev_select, 0));
+    return launch_finalize(a, cnt, fin_stream);
+  }
   return launch_finalize(a, cnt, m->stream);
 }
 
@@ -464,16 +523,33 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   const bool use_decay = m->ts != nullptr && m->decay_valid;
   if (m->ts && !m->decay_valid && recency_bias != 0.0)
     return fail("hdb_query: timestamps set but hdb_matrix_set_decay_reference was not called");
+  const bool pipelined = m->post_stream != nullptr && out_space == HDB_DEVICE;
+  if (pipelined) {
+    // rotate to the other workspace slot; its previous user (two queries ago) must have finished certifying
+    slot_store(m);
+    slot_load(m, m->cur_slot ^ 1);
+    hdb_matrix::QuerySlot& qs = m->slots[m->cur_slot];
+    if (qs.pending) HDB_CUDA(cudaStreamWaitEvent(m->pre_stream, qs.done, 0));
+  }
   HDB_TRY(ensure_workspace(m, nq, k));
   const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
   if (metric == HDB_HAMMING) HDB_TRY(ensure_bits(m));
 
   const void* q_dev = queries;
   if (q_space == HDB_HOST) {
-    HDB_CUDA(cudaMemcpyAsync(m->q_raw, queries, (size_t)nq * m->d * dtype_size(q_dtype), cudaMemcpyHostToDevice, m->stream));
+    HDB_CUDA(cudaMemcpyAsync(m->q_raw, queries, (size_t)nq * m->d * dtype_size(q_dtype), cudaMemcpyHostToDevice,
+                             pipelined ? m->pre_stream : m->stream));
     q_dev = m->q_raw;
   }
-  HDB_TRY(launch_prep_query(q_dev, q_dtype, nq, m->d, metric, m->dtype, m->words, m->qb, m->stream));
+  if (pipelined) {
+    // the preparation of THIS query runs on the internal pre stream, i.e. while the previous query's sweep still
+    // occupies the main stream (device queries must therefore be complete when hdb_query is called)
+    HDB_TRY(launch_prep_query(q_dev, q_dtype, nq, m->d, metric, m->dtype, m->words, m->qb, m->tau, m->pre_stream));
+    HDB_CUDA(cudaEventRecord(m->ev_prep, m->pre_stream));
+    HDB_CUDA(cudaStreamWaitEvent(m->stream, m->ev_prep, 0));
+  } else {
+    HDB_TRY(launch_prep_query(q_dev, q_dtype, nq, m->d, metric, m->dtype, m->words, m->qb, nullptr, m->stream));
+  }
   const RowFilter f = filter_of(m, recency_bias, use_decay);
   const bool dev_out = (out_space == HDB_DEVICE);
   int64_t* idx = dev_out ? out_idx : m->o_idx;
@@ -501,13 +577,30 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
     }
   } else if (kp) {
     HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
+    bool on_post = false;
     for (int64_t b0 = 0; b0 < nq; b0 += kChunk) {
       const int64_t cnt = nq - b0 < kChunk ? nq - b0 : kChunk;
-      HDB_TRY(run_fused(m, metric, rdt, kp, b0, cnt, k, f, idx, score, count, flags));
+      // only a single chunk can hand its certify step to the post stream (the candidate buffer is reused per chunk)
+      const bool hand_over = pipelined && nq <= kChunk;
+      HDB_TRY(run_fused(m, metric, rdt, kp, b0, cnt, k, f, idx, score, count, flags, hand_over ? m->post_stream : nullptr));
+      on_post = hand_over;
+    }
+    if (pipelined && on_post) {
+      hdb_matrix::QuerySlot& qs = m->slots[m->cur_slot];
+      HDB_CUDA(cudaEventRecord(qs.done, m->post_stream));
+      qs.pending = true;
+      slot_store(m);
+      return 0;
     }
   } else {
     for (int64_t b = 0; b < nq; ++b) HDB_TRY(run_exact(m, metric, rdt, b, k, f, idx, score, count));
     if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
+  }
+  if (pipelined) {
+    // paths that ran entirely on the main stream: results must still become visible in post-stream order
+    HDB_CUDA(cudaEventRecord(m->ev_select, m->stream));
+    HDB_CUDA(cudaStreamWaitEvent(m->post_stream, m->ev_select, 0));
+    slot_store(m);
   }
   if (dev_out) return 0;
 
@@ -643,7 +736,7 @@ int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_
     HDB_CUDA(cudaMemcpyAsync(m->q_raw, query, (size_t)m->d * dtype_size(q_dtype), cudaMemcpyHostToDevice, m->stream));
     q_dev = m->q_raw;
   }
-  HDB_TRY(launch_prep_query(q_dev, q_dtype, 1, m->d, metric, m->dtype, m->words, m->qb, m->stream));
+  HDB_TRY(launch_prep_query(q_dev, q_dtype, 1, m->d, metric, m->dtype, m->words, m->qb, nullptr, m->stream));
   const size_t esz = (metric == HDB_HAMMING) ? 8 : (size_t)dtype_size(rdt);
   if (out_dtype) *out_dtype = (metric == HDB_HAMMING) ? 3 : rdt;
   void* dst = out;

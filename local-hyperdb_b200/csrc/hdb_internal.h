@@ -67,7 +67,7 @@ int launch_kept_ts_max(const double* ts, const RowFilter& f, int64_t n, unsigned
 int launch_decay(const double* ts, double* decay, int64_t n, double ts_max, cudaStream_t s);
 int launch_stage1(double* ts, int64_t n, double bias1, double ts_max, cudaStream_t s);
 int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int metric, int sdt, int words,
-                      const QueryBuffers& qb, cudaStream_t s);
+                      const QueryBuffers& qb, unsigned long long* tau /*zeroed per query, or nullptr*/, cudaStream_t s);
 int launch_normalize_rows(int dtype, int64_t n, int64_t d, const void* src, void* dst, cudaStream_t s);
 double decode_ordered_double(unsigned long long bits);
 

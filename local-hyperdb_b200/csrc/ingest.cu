@@ -213,13 +213,16 @@ __device__ double query_unit_norm(const void* q, int64_t d, void* s_sq, int tid,
 }
 
 __global__ void prep_query_kernel(const void* queries, int qdt, int64_t d, int metric, int sdt, int words,
-                                  QueryBuffers qb, int stage) {
+                                  QueryBuffers qb, int stage, unsigned long long* tau) {
   extern __shared__ __align__(16) unsigned char s_query[];
   __shared__ double s_red[32];
   __shared__ int s_nan;
   const int64_t b = blockIdx.x;
   const char* q = reinterpret_cast<const char*>(queries) + b * d * dtype_size(qdt);
-  if (threadIdx.x == 0) s_nan = 0;
+  if (threadIdx.x == 0) {
+    s_nan = 0;
+    if (tau) tau[b] = 0;               // running threshold of this query's sweep starts below every key
+  }
   double nrm = 1.0;
   if (metric == HDB_COSINE) {
     if (qdt == 0) nrm = query_unit_norm<0>(q, d, s_query, threadIdx.x, blockDim.x, stage);
@@ -261,11 +264,11 @@ __global__ void prep_query_kernel(const void* queries, int qdt, int64_t d, int m
 }
 
 int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int metric, int sdt, int words,
-                      const QueryBuffers& qb, cudaStream_t s) {
+                      const QueryBuffers& qb, unsigned long long* tau, cudaStream_t s) {
   if (nq == 0) return 0;
   const size_t bytes = (size_t)d * (q_dtype == 2 ? 8 : 4);          // squares in the carrier type
   const int stage = bytes <= 40 * 1024;
-  prep_query_kernel<<<(unsigned)nq, 128, stage ? bytes : 0, s>>>(q, q_dtype, d, metric, sdt, words, qb, stage);
+  prep_query_kernel<<<(unsigned)nq, 128, stage ? bytes : 0, s>>>(q, q_dtype, d, metric, sdt, words, qb, stage, tau);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;

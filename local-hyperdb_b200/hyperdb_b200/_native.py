@@ -34,6 +34,7 @@ SIGNATURES = {
     "hdb_matrix_adopt": (C.c_int, [vp, vp]),
     "hdb_matrix_finalize": (C.c_int, [vp]),
     "hdb_matrix_set_stream": (C.c_int, [vp, vp]),
+    "hdb_matrix_set_post_stream": (C.c_int, [vp, vp]),
     "hdb_matrix_info": (C.c_int, [vp, C.POINTER(C.c_int), i64p, i64p, i64p, i64p]),
     "hdb_matrix_set_mask": (C.c_int, [vp, vp, C.c_int]),
     "hdb_matrix_set_range": (C.c_int, [vp, i64, i64]),

@@ -163,6 +163,10 @@ class DeviceMatrix:
         """0 automatic, 1 exact full-vector path, 2 fused sweep only (error instead of fallback)."""
         N.check(N.lib().hdb_matrix_set_path(self._h, int(mode)))
 
+    def set_post_stream(self, cuda_stream_ptr):
+        """Pipelining of device-output queries: certify on this stream, overlapping the next query's sweep (0 = off)."""
+        N.check(N.lib().hdb_matrix_set_post_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
     def set_stream(self, cuda_stream_ptr):
         N.check(N.lib().hdb_matrix_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

@@ -39,6 +39,17 @@ class CudaEngine:
         self.m = matrix
         self.torch = torch
         self.device = torch.device("cuda", matrix.device)
+        self.post = None                      # torch stream of the pipelined certify / exchange / merge
+
+    def enable_pipeline(self, on=True):
+        """Run certify / exchange / merge of query i on a second stream while the sweep of query i+1 streams the matrix."""
+        if on and self.post is None:
+            self.post = self.torch.cuda.Stream(device=self.device)
+            self.m.set_post_stream(self.post.cuda_stream)
+        elif not on and self.post is not None:
+            self.torch.cuda.current_stream(self.device).wait_stream(self.post)
+            self.m.set_post_stream(0)
+            self.post = None
 
     def kept_ts_max(self):
         return self.m.kept_ts_max()
@@ -129,6 +140,16 @@ class ShardedMatrix:
         k = max(int(top_k), 0)
         b = 1 if getattr(queries, "ndim", 1) == 1 else queries.shape[0]
         mine = self.engine.local_topk(queries, k, metric, recency_bias, exact=exact)
+        post = getattr(self.engine, "post", None)
+        if post is not None:
+            # pipelined: `mine` is completed on the post stream; exchange and merge follow it there
+            mine.record_stream(post)
+            with torch.cuda.stream(post):
+                return self._exchange_and_merge(mine, b, k, post)
+        return self._exchange_and_merge(mine, b, k, None)
+
+    def _exchange_and_merge(self, mine, b, k, post):
+        import torch
         if self.world > 1:
             gathered = torch.empty(self.world * mine.numel(), dtype=mine.dtype, device=mine.device)
             self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
@@ -138,14 +159,23 @@ class ShardedMatrix:
             gathered = mine.view(1, -1)
         return self.engine.merge(gathered, b, k)
 
+    def wait_results(self):
+        """Make the current stream wait for everything enqueued on the pipelined post stream."""
+        post = getattr(self.engine, "post", None)
+        if post is not None:
+            import torch
+            torch.cuda.current_stream(self.engine.device).wait_stream(post)
+
     def query(self, queries, top_k, metric, recency_bias=0.0):
         """Host results, identical on every rank: (idx [B,k], scores [B,k], counts [B])."""
         idx, sc, cnt, flags = self.query_async(queries, top_k, metric, recency_bias)
+        self.wait_results()
         flags = flags.cpu().numpy()
         if (flags & N.FLAG_QUERY_NAN).any():
             raise ValueError("Vectors and query_vector should not contain NaN values.")
         if (flags & N.FLAG_UNCERTIFIED).any():      # every rank sees every flag after the all-gather: same branch everywhere
             idx, sc, cnt, flags = self.query_async(queries, top_k, metric, recency_bias, exact=True)
+            self.wait_results()
         b, k = idx.shape
         if idx.data_ptr() + 8 * b * k == sc.data_ptr():          # merged block [idx | score | count]: one copy
             import torch
