@@ -130,6 +130,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/r01_traffic.json); None if it was not captured."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(path)).get(workload)
+        return None if t is None else float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -374,7 +385,8 @@ def main():
                     "d2h_bytes_per_step": int(b * k * 16 + b * 8), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
+                         "traffic": ncu_traffic(args.workload) if world == 1 else None,
                          "kernel": "sweep_kernel" if b < 16 else "batched_tc_kernel (sample + select passes)",
                          "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
                          "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peak_src,
@@ -384,7 +396,7 @@ def main():
             tf = shard_flops / (sweep_avg_ms * 1e-3) / 1e12
             peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
             line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                                "traffic": None, "kernel": "batched_tc_kernel (sample + select passes)",
+                                "traffic": ncu_traffic(args.workload) if world == 1 else None, "kernel": "batched_tc_kernel (sample + select passes)",
                                 "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
                                 "algorithmic_flops_per_launch": shard_flops,
                                 "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
