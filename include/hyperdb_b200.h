@@ -35,7 +35,8 @@ enum {                                              /* metric dispatch, hyperdb/
   HDB_COSINE = 1,     /* cosine_similarity  :32-42  */
   HDB_EUCLIDEAN = 2,  /* euclidean_metric   :44-52  */
   HDB_MANHATTAN = 3,  /* manhattan_distance :54-61  */
-  HDB_HAMMING = 4     /* hamming_distance   :128-147 */
+  HDB_HAMMING = 4,    /* hamming_distance   :128-147 */
+  HDB_JACCARD = 5     /* jaccard_similarity :63-76 (same packed sign bits as hamming) */
 };
 /* bits of the per-query flags word written by hdb_query */
 enum {
@@ -105,7 +106,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
 
 /* ---- full similarity vector: the metric functions themselves, ranking_algorithm.py:24-61,:128-147 */
 /* out holds n_rows values of the NumPy result dtype promote(matrix dtype, q_dtype)
- * (uint64 for HDB_HAMMING), reported through *out_dtype (HDB_F16/F32/F64; 3 = uint64). */
+ * (uint64 for HDB_HAMMING, float64 for HDB_JACCARD), reported through *out_dtype (HDB_F16/F32/F64; 3 = uint64). */
 int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_space,
                void* out, int out_space, int* out_dtype);
 /* L2-normalised copy of `n_rows` x `dim` values (get_norm_vector, ranking_algorithm.py:8-21). */

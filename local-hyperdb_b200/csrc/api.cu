@@ -512,7 +512,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
               int out_space) {
   if (!m) return fail("null handle");
   if (!m->finalized) return fail("hdb_query: call hdb_matrix_finalize first");
-  if (metric < 0 || metric > 4) return fail("Unknown metric");
+  if (metric < 0 || metric > 5) return fail("Unknown metric");
   if (q_dtype < 0 || q_dtype > 2) return fail("hdb_query: q_dtype must be HDB_F16/F32/F64");
   if (nq < 0) return fail("hdb_query: negative query count");
   if (nq == 0) return 0;
@@ -533,7 +533,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   }
   HDB_TRY(ensure_workspace(m, nq, k));
   const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
-  if (metric == HDB_HAMMING) HDB_TRY(ensure_bits(m));
+  if (metric == HDB_HAMMING || metric == HDB_JACCARD) HDB_TRY(ensure_bits(m));
 
   const void* q_dev = queries;
   if (q_space == HDB_HOST) {
@@ -724,21 +724,21 @@ int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_
                int* out_dtype) {
   if (!m) return fail("null handle");
   if (!m->finalized) return fail("hdb_scores: call hdb_matrix_finalize first");
-  if (metric < 0 || metric > 4) return fail("Unknown metric");
+  if (metric < 0 || metric > 5) return fail("Unknown metric");
   if (q_dtype < 0 || q_dtype > 2) return fail("hdb_scores: q_dtype must be HDB_F16/F32/F64");
   if (!query || !out) return fail("hdb_scores: NULL argument");
   HDB_CUDA(cudaSetDevice(m->device));
   HDB_TRY(ensure_workspace(m, 1, 1));
   const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
-  if (metric == HDB_HAMMING) HDB_TRY(ensure_bits(m));
+  if (metric == HDB_HAMMING || metric == HDB_JACCARD) HDB_TRY(ensure_bits(m));
   const void* q_dev = query;
   if (q_space == HDB_HOST) {
     HDB_CUDA(cudaMemcpyAsync(m->q_raw, query, (size_t)m->d * dtype_size(q_dtype), cudaMemcpyHostToDevice, m->stream));
     q_dev = m->q_raw;
   }
   HDB_TRY(launch_prep_query(q_dev, q_dtype, 1, m->d, metric, m->dtype, m->words, m->qb, nullptr, m->stream));
-  const size_t esz = (metric == HDB_HAMMING) ? 8 : (size_t)dtype_size(rdt);
-  if (out_dtype) *out_dtype = (metric == HDB_HAMMING) ? 3 : rdt;
+  const size_t esz = (metric == HDB_HAMMING || metric == HDB_JACCARD) ? 8 : (size_t)dtype_size(rdt);
+  if (out_dtype) *out_dtype = (metric == HDB_HAMMING) ? 3 : (metric == HDB_JACCARD ? 2 : rdt);
   void* dst = out;
   void* tmp = nullptr;
   if (out_space == HDB_HOST) {

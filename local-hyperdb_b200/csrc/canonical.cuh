@@ -264,6 +264,11 @@ __device__ double canonical_similarity(const CanonArgs& a, const void* rowp, con
     for (int w = 0; w < a.words; ++w) diff += __popc(bitrow[w] ^ a.qbits[w]);
     return (double)(d - diff);
   }
+  if (a.metric == 5) {          // jaccard: uint64 / uint64 -> float64 true division; 0/0 = NaN (ranking_algorithm.py:75)
+    int inter = 0, uni = 0;
+    for (int w = 0; w < a.words; ++w) { inter += __popc(bitrow[w] & a.qbits[w]); uni += __popc(bitrow[w] | a.qbits[w]); }
+    return __ddiv_rn((double)inter, (double)uni);
+  }
   auto gq = [&](int j) -> C { return A::from_double(a.qc[j]); };
   auto term = [&](int j) -> C { return canonical_term<RDT>(a.metric, load_as_double(rowp, a.sdt, j), a.qc[j], nrm, a.sdt); };
   return canonical_reduce<RDT>(a.metric, term, gq, d);

@@ -56,7 +56,7 @@ __device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) 
   const double uT = unit_roundoff(a.m.dtype);
   const bool decay = a.f.decay != nullptr;
   const double chain16 = (a.rdt == 0) ? D * 1.1920928955078125e-7 : 0.0;   // HALF_dot / f16 pairwise run in float32
-  if (a.metric == HDB_HAMMING) return s + fabs(s) * uk;
+  if (a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) return s + fabs(s) * uk;     // exact on both sides: only the key rounding
   if (a.metric == HDB_DOT || a.metric == HDB_COSINE) {
     const double A = (double)(a.metric == HDB_DOT ? a.m.max_norm : a.m.max_ratio) * qnorm;   // >= sum |v_i q_i|
     double e = D * ua + chain16;
@@ -335,17 +335,19 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
       nrm = a.m.dtype == 2 ? reinterpret_cast<const double*>(a.m.norms)[row] : (double)reinterpret_cast<const float*>(a.m.norms)[row];
     const char* rowp = reinterpret_cast<const char*>(a.m.rows) + (int64_t)row * a.m.d * dtype_size(a.m.dtype);
     double sim;
-    if (a.metric == HDB_HAMMING) {
+    if (a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) {
       // packed rows are whole 16-byte vectors: independent 128-bit loads instead of a word-by-word chain
       const uint4* vr = reinterpret_cast<const uint4*>(bitrow);
       const uint4* vq = reinterpret_cast<const uint4*>(ca.qbits);
-      int diff = 0;
+      int diff = 0, inter = 0, uni = 0;
 #pragma unroll 4
       for (int v = 0; v < a.m.words / 4; ++v) {
         const uint4 x = vr[v], q = vq[v];
         diff += __popc(x.x ^ q.x) + __popc(x.y ^ q.y) + __popc(x.z ^ q.z) + __popc(x.w ^ q.w);
+        inter += __popc(x.x & q.x) + __popc(x.y & q.y) + __popc(x.z & q.z) + __popc(x.w & q.w);
+        uni += __popc(x.x | q.x) + __popc(x.y | q.y) + __popc(x.z | q.z) + __popc(x.w | q.w);
       }
-      sim = (double)((int)a.m.d - diff);
+      sim = a.metric == HDB_HAMMING ? (double)((int)a.m.d - diff) : __ddiv_rn((double)inter, (double)uni);
     } else {
       sim = canonical_similarity_rt(ca, a.rdt, rowp, bitrow, nrm);
     }
@@ -401,7 +403,7 @@ int launch_finalize(const FinalizeArgs& a_in, int64_t nq, cudaStream_t s) {
   const int64_t qbytes = (a.m.d * (a.rdt == 2 ? 8 : 4) + 15) & ~int64_t(15);
   int64_t want = qbytes + row_pitch * a.kp;
   if (want > 160 * 1024) want = 160 * 1024;
-  if (want < qbytes + row_pitch || a.metric == HDB_HAMMING) want = 0;
+  if (want < qbytes + row_pitch || a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) want = 0;
   a.smem_bytes = (int)want;
   static bool attr_set = false;
   if (!attr_set) {
@@ -465,6 +467,7 @@ __global__ void scores_out_kernel(MatrixView m, int metric, int rdt, const doubl
   CanonArgs ca = canon_args(m, metric, qc, qbits);
   const double v = row_canonical(m, ca, rdt, row);
   if (metric == HDB_HAMMING) reinterpret_cast<unsigned long long*>(out)[row] = (unsigned long long)(long long)v;
+  else if (metric == HDB_JACCARD) reinterpret_cast<double*>(out)[row] = v;
   else if (rdt == 0) reinterpret_cast<__half*>(out)[row] = __float2half_rn((float)v);
   else if (rdt == 1) reinterpret_cast<float*>(out)[row] = (float)v;
   else reinterpret_cast<double*>(out)[row] = v;

@@ -301,6 +301,7 @@ struct HammingParams {
   const uint32_t* qbits;
   int64_t n, d;
   int nvec, lpr;
+  int jaccard;               // 0: score = d - popcount(xor); 1: score = popcount(and) / popcount(or)
   RowFilter f;
   uint64_t* cand;
   unsigned long long* tau;
@@ -367,7 +368,11 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_kernel(Hamming
 #pragma unroll
       for (int r = 0; r < kPasses; ++r) {
         const uint4 q = (kept[r] && sub < p.nvec) ? my_q : make_uint4(0, 0, 0, 0);
-        diff[r] = __popc(v[r].x ^ q.x) + __popc(v[r].y ^ q.y) + __popc(v[r].z ^ q.z) + __popc(v[r].w ^ q.w);
+        if (p.jaccard)
+          diff[r] = (__popc(v[r].x & q.x) + __popc(v[r].y & q.y) + __popc(v[r].z & q.z) + __popc(v[r].w & q.w)) +
+                    ((__popc(v[r].x | q.x) + __popc(v[r].y | q.y) + __popc(v[r].z | q.z) + __popc(v[r].w | q.w)) << 16);
+        else
+          diff[r] = __popc(v[r].x ^ q.x) + __popc(v[r].y ^ q.y) + __popc(v[r].z ^ q.z) + __popc(v[r].w ^ q.w);
       }
     } else {
 #pragma unroll
@@ -379,7 +384,11 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_kernel(Hamming
           for (int c = sub; c < p.nvec; c += lpr) {
             uint4 v = ld_stream16(rowp + c);
             uint4 q = s_q[c];
-            dsum += __popc(v.x ^ q.x) + __popc(v.y ^ q.y) + __popc(v.z ^ q.z) + __popc(v.w ^ q.w);
+            if (p.jaccard)      // low 16 bits: popcount(and), high 16 bits: popcount(or)  (d <= 32768 per the smem limit)
+              dsum += (__popc(v.x & q.x) + __popc(v.y & q.y) + __popc(v.z & q.z) + __popc(v.w & q.w)) +
+                      ((__popc(v.x | q.x) + __popc(v.y | q.y) + __popc(v.z | q.z) + __popc(v.w | q.w)) << 16);
+            else
+              dsum += __popc(v.x ^ q.x) + __popc(v.y ^ q.y) + __popc(v.z ^ q.z) + __popc(v.w ^ q.w);
           }
         }
         diff[r] = dsum;
@@ -390,8 +399,9 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_kernel(Hamming
       int dsum = diff[r];
       for (int o = lpr >> 1; o; o >>= 1) dsum += __shfl_xor_sync(kFull, dsum, o);
       const int64_t row = row0 + (int64_t)r * rpp + slot;
-      float score = (float)((int)p.d - dsum);
-      if (p.f.decay && kept[r] && sub == 0) score = (float)((double)score + p.f.bias * p.f.decay[row]);
+      double exact = p.jaccard ? (double)(dsum & 0xffff) / (double)(dsum >> 16) : (double)((int)p.d - dsum);
+      if (p.f.decay && kept[r] && sub == 0) exact += p.f.bias * p.f.decay[row];
+      const float score = (float)exact;
       const uint64_t key = make_key(score, (uint32_t)row);
       wl.push(sub == 0 && kept[r] && key > wl.tau, key, lane, s_tau, p.tau);
     }
@@ -428,7 +438,7 @@ __device__ __forceinline__ int transpose_reduce(int (&v)[PPR], int sub) {
   return v[0];                       // total of pass (sub & (PPR-1))
 }
 
-template <int KP, int LPR>
+template <int KP, int LPR, bool JAC>
 __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_lpr_kernel(HammingParams p) {
   constexpr int kCap = ListCfg<KP>::kCap;
   constexpr int PPR = LPR < 8 ? LPR : 8;       // passes per round = loads in flight per lane
@@ -490,11 +500,17 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_lpr_kernel(Ham
       }
       int cnt[PPR];
 #pragma unroll
-      for (int r = 0; r < PPR; ++r)
-        cnt[r] = __popc(v[r].x ^ my_q.x) + __popc(v[r].y ^ my_q.y) + __popc(v[r].z ^ my_q.z) + __popc(v[r].w ^ my_q.w);
+      for (int r = 0; r < PPR; ++r) {
+        if (JAC)          // both popcounts packed in one int (16 bits each: d <= 4096 here), reduced together
+          cnt[r] = (__popc(v[r].x & my_q.x) + __popc(v[r].y & my_q.y) + __popc(v[r].z & my_q.z) + __popc(v[r].w & my_q.w)) +
+                   ((__popc(v[r].x | my_q.x) + __popc(v[r].y | my_q.y) + __popc(v[r].z | my_q.z) + __popc(v[r].w | my_q.w)) << 16);
+        else
+          cnt[r] = __popc(v[r].x ^ my_q.x) + __popc(v[r].y ^ my_q.y) + __popc(v[r].z ^ my_q.z) + __popc(v[r].w ^ my_q.w);
+      }
       const int diff = transpose_reduce<PPR, LPR>(cnt, sub);
-      float score = (float)((int)p.d - diff);
-      if (p.f.decay) score = (float)((double)score + p.f.bias * my_decay);
+      double exact = JAC ? (double)(diff & 0xffff) / (double)(diff >> 16) : (double)((int)p.d - diff);
+      if (p.f.decay) exact += p.f.bias * my_decay;
+      const float score = (float)exact;
       const uint64_t key = make_key(score, (uint32_t)(row0 + my_loc));
       wl.push(rep && my_kept && key > wl.tau, key, lane, s_tau, p.tau);
     }
@@ -502,14 +518,18 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_lpr_kernel(Ham
   cta_merge_and_store<KP>(s_lists, wl, lane, warp, s_tau, p.tau, p.cand + (int64_t)blockIdx.x * KP);
 }
 
-template <int KP, int LPR>
-static int launch_hamming_lpr(const HammingParams& hp, int grid, size_t smem, cudaStream_t s) {
-  auto kern = sweep_hamming_lpr_kernel<KP, LPR>;
+template <int KP, int LPR, bool JAC>
+static int launch_hamming_lpr2(const HammingParams& hp, int grid, size_t smem, cudaStream_t s) {
+  auto kern = sweep_hamming_lpr_kernel<KP, LPR, JAC>;
   if (smem > 48 * 1024) HDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kSweepThreads, smem, s>>>(hp);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;
+}
+template <int KP, int LPR>
+static int launch_hamming_lpr(const HammingParams& hp, int grid, size_t smem, cudaStream_t s) {
+  return hp.jaccard ? launch_hamming_lpr2<KP, LPR, true>(hp, grid, smem, s) : launch_hamming_lpr2<KP, LPR, false>(hp, grid, smem, s);
 }
 template <int KP>
 static int launch_hamming_kp(const HammingParams& hp, int grid, size_t smem, cudaStream_t s) {
@@ -562,8 +582,9 @@ int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t
                  const SweepOut& out, cudaStream_t s) {
   if (m.n >= (int64_t(1) << 32)) return fail("sweep: more than 2^32 rows per shard");
   if (kp != 32 && kp != 128) return fail("sweep: unsupported candidate class");
-  if (metric == HDB_HAMMING) {
+  if (metric == HDB_HAMMING || metric == HDB_JACCARD) {
     HammingParams hp;
+    hp.jaccard = metric == HDB_JACCARD;
     hp.bits = m.bits; hp.qbits = qbits; hp.n = m.n; hp.d = m.d;
     hp.nvec = m.words / 4;
     int lpr = 1;

@@ -16,11 +16,12 @@ from .ranking_algorithm import (  # noqa: F401
     get_norm_vector,
     hamming_distance,
     hyperDB_ranking_algorithm_sort,
+    jaccard_similarity,
     manhattan_distance,
 )
 
 __all__ = [
     "DeviceMatrix", "ranking_algorithm", "cosine_similarity", "dot_product", "euclidean_metric",
-    "manhattan_distance", "hamming_distance", "get_norm_vector", "hyperDB_ranking_algorithm_sort",
+    "manhattan_distance", "hamming_distance", "jaccard_similarity", "get_norm_vector", "hyperDB_ranking_algorithm_sort",
     "custom_ranking_algorithm_sort",
 ]

@@ -15,6 +15,7 @@ METRIC_IDS = {
     "euclidean_metric": 2,
     "manhattan_distance": 3,
     "hamming_distance": 4,
+    "jaccard_similarity": 5,
 }
 FLAG_FALLBACK, FLAG_QUERY_NAN, FLAG_TENSOR, FLAG_UNCERTIFIED = 1, 2, 4, 8
 

@@ -221,7 +221,7 @@ class DeviceMatrix:
         if q.shape[0] != self.shape[1]:
             raise ValueError(f"operands could not be broadcast together with shapes {self.shape} {q.shape}")
         rdt = np.promote_types(self.np_dtype, q.dtype)
-        out = np.empty(self.shape[0], np.uint64 if metric == "hamming_distance" else rdt)
+        out = np.empty(self.shape[0], np.uint64 if metric == "hamming_distance" else (np.float64 if metric == "jaccard_similarity" else rdt))
         got = C.c_int()
         N.check(N.lib().hdb_scores(self._h, mid, C.c_void_p(q.ctypes.data), _NP2HDB[q.dtype], N.HDB_HOST,
                                    C.c_void_p(out.ctypes.data), N.HDB_HOST, C.byref(got)))

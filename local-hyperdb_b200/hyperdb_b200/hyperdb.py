@@ -25,7 +25,8 @@ from .device_matrix import DeviceMatrix
 
 _METRICS = ['dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_distance', 'jaccard_similarity',
             'pearson_correlation', 'hamming_distance']
-_ON_DEVICE = ('dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_distance', 'hamming_distance')
+_ON_DEVICE = ('dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_distance', 'hamming_distance',
+              'jaccard_similarity')
 
 
 def _nested(document, dotted):

@@ -106,8 +106,14 @@ def hamming_distance(vectors, query_vector):
     return _scores(vectors, query_vector, "hamming_distance")
 
 
-_SUPPORTED = ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance")
-_REFERENCE_ONLY = ("jaccard_similarity", "pearson_correlation")      # next round
+def jaccard_similarity(vectors, query_vector):
+    """hyperdb/ranking_algorithm.py:63-76 -- popcount(v & q) / popcount(v | q) on the sign bits, float64 (0/0 = NaN)."""
+    return _scores(vectors, query_vector, "jaccard_similarity")
+
+
+_SUPPORTED = ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance",
+              "jaccard_similarity")
+_REFERENCE_ONLY = ("pearson_correlation",)      # SURVEY.md section 8(f) rank 2: not on the B200 path yet
 
 
 def hyperDB_ranking_algorithm_sort(vectors, query_vector, top_k=5, metric='cosine_similarity', timestamps=None,

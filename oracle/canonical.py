@@ -121,6 +121,12 @@ def scores(vectors, query, metric):
     if metric == "hamming_distance":
         vb, qb = v > 0, q > 0
         return (v.shape[1] - np.sum(vb != qb[None, :], axis=1)).astype(np.uint64)
+    if metric == "jaccard_similarity":
+        vb, qb = v > 0, q > 0
+        inter = np.sum(vb & qb[None, :], axis=1).astype(np.float64)
+        union = np.sum(vb | qb[None, :], axis=1).astype(np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return inter / union
     R = _F[np.dtype(result_dtype(v, q))]
     if metric == "cosine_similarity":
         # each operand is normalised in ITS OWN dtype (ranking_algorithm.py:37-38); np.dot promotes after

@@ -23,6 +23,7 @@ METRICS = (
     "euclidean_metric",
     "manhattan_distance",
     "hamming_distance",
+    "jaccard_similarity",
 )
 
 
@@ -81,12 +82,21 @@ def hamming_scores(vectors, query):
     return np.asarray(vectors).shape[-1] - differing
 
 
+def jaccard_scores(vectors, query):
+    """hyperdb/ranking_algorithm.py:63-76 (jaccard_similarity): popcount(v & q) / popcount(v | q) on the sign bits,
+    float64; an empty union gives 0/0 = NaN (ranked last by the sort, :174)."""
+    vb, qb = sign_bits(vectors), sign_bits(query)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.sum(np.bitwise_and(vb, qb), axis=1) / np.sum(np.bitwise_or(vb, qb), axis=1)
+
+
 _DISPATCH = {
     "dot_product": dot_scores,
     "cosine_similarity": cosine_scores,
     "euclidean_metric": euclidean_scores,
     "manhattan_distance": manhattan_scores,
     "hamming_distance": hamming_scores,
+    "jaccard_similarity": jaccard_scores,
 }
 
 

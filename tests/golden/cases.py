@@ -11,7 +11,8 @@ import itertools
 
 import numpy as np
 
-METRICS = ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance")
+METRICS = ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance",
+           "jaccard_similarity")
 DT = {"f16": np.float16, "f32": np.float32, "f64": np.float64}
 
 
@@ -73,9 +74,13 @@ def sort_cases():
                           ts=False, bias=0.0))
     # binary data for hamming, big-k, k > n, k <= 0
     for vdt in ("f16", "f32", "f64"):
-        seed += 1
-        cases.append(dict(seed=seed, n=500, d=256, vdt=vdt, qdt=vdt, kind="binary", metric="hamming_distance",
-                          k=10, ts=False, bias=0.0))
+        for metric in ("hamming_distance", "jaccard_similarity"):
+            seed += 1
+            cases.append(dict(seed=seed, n=500, d=256, vdt=vdt, qdt=vdt, kind="binary", metric=metric,
+                              k=10, ts=False, bias=0.0))
+    # an all-non-positive row and query: empty union -> 0/0 -> NaN -> ranked last
+    seed += 1
+    cases.append(dict(seed=seed, n=60, d=9, vdt="f32", qdt="f32", kind="coarse", metric="jaccard_similarity", k=60, ts=False, bias=0.0))
     for k in (0, -1, 50, 1000):
         seed += 1
         cases.append(dict(seed=seed, n=40, d=16, vdt="f32", qdt="f32", kind="gauss", metric="cosine_similarity",

@@ -15,7 +15,7 @@ TOL = {"float16": 1e-3, "float32": 1e-5, "float64": 1e-12, "uint64": 0, "int64":
 
 
 def exact_expected(case, dtype):
-    return dtype == "float16" or case["metric"] in ("euclidean_metric", "manhattan_distance", "hamming_distance")
+    return dtype == "float16" or case["metric"] in ("euclidean_metric", "manhattan_distance", "hamming_distance", "jaccard_similarity")
 
 
 @pytest.mark.parametrize("entry", GOLDEN, ids=[G.case_id(e[0]) for e in GOLDEN])

@@ -9,7 +9,7 @@ from oracle import reference_port as P
 
 GOLDEN = G.load_sort_golden()
 FN = {"dot_product": P.dot_scores, "cosine_similarity": P.cosine_scores, "euclidean_metric": P.euclidean_scores,
-      "manhattan_distance": P.manhattan_scores, "hamming_distance": P.hamming_scores}
+      "manhattan_distance": P.manhattan_scores, "hamming_distance": P.hamming_scores, "jaccard_similarity": P.jaccard_scores}
 
 
 @pytest.mark.parametrize("entry", GOLDEN, ids=[G.case_id(e[0]) for e in GOLDEN])
