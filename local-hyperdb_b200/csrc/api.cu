@@ -531,6 +531,11 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
     hdb_matrix::QuerySlot& qs = m->slots[m->cur_slot];
     if (qs.pending) HDB_CUDA(cudaStreamWaitEvent(m->pre_stream, qs.done, 0));
   }
+  if (!pipelined && m->post_stream) {
+    // a host-output call while pipelining is on: order it after every certify step still in flight on the post stream
+    for (auto& qs : m->slots)
+      if (qs.pending) { HDB_CUDA(cudaStreamWaitEvent(m->stream, qs.done, 0)); }
+  }
   HDB_TRY(ensure_workspace(m, nq, k));
   const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
   if (metric == HDB_HAMMING || metric == HDB_JACCARD) HDB_TRY(ensure_bits(m));
