@@ -264,7 +264,7 @@ def main():
         m.set_mask(keep_bits)
     eng = CudaEngine(m)
     sm = ShardedMatrix(eng, w["n"])
-    if not args.no_pipeline and w["b"] < 16:
+    if not args.no_pipeline and w["b"] < 2:
         eng.enable_pipeline()            # certify/exchange/merge of query i overlap the sweep of query i+1
     bias = 0.0
     if w.get("decay"):
@@ -387,7 +387,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
                          "traffic": ncu_traffic(args.workload) if world == 1 else None,
-                         "kernel": "sweep_kernel" if b < 16 else "batched_tc_kernel (sample + select passes)",
+                         "kernel": "sweep_kernel" if b < 2 else "batched_tc_kernel (sample + select passes)",
                          "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
                          "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
