@@ -36,7 +36,8 @@ enum {                                              /* metric dispatch, hyperdb/
   HDB_EUCLIDEAN = 2,  /* euclidean_metric   :44-52  */
   HDB_MANHATTAN = 3,  /* manhattan_distance :54-61  */
   HDB_HAMMING = 4,    /* hamming_distance   :128-147 */
-  HDB_JACCARD = 5     /* jaccard_similarity :63-76 (same packed sign bits as hamming) */
+  HDB_JACCARD = 5,    /* jaccard_similarity :63-76 (same packed sign bits as hamming) */
+  HDB_PEARSON = 6     /* pearson_correlation :78-113 (per-row np.mean / np.std columns, built on first use) */
 };
 /* bits of the per-query flags word written by hdb_query */
 enum {
@@ -74,6 +75,20 @@ int hdb_matrix_set_stream(hdb_matrix* m, void* cuda_stream);
 int hdb_matrix_set_post_stream(hdb_matrix* m, void* post_stream);
 int hdb_matrix_info(const hdb_matrix* m, int* dtype, int64_t* n_rows, int64_t* dim, int64_t* row_offset,
                     int64_t* n_kept);
+
+/* ---- mutation of a resident shard: replaces np.concatenate on add (hyperdb/hyperdb.py:504-509) and the
+ *      np.vstack / boolean-mask copies of remove_document (:718-728).  Owning shards only (not adopted memory).
+ *      The row mask, the kept range, the decay column and (append only) the timestamps are reset: set them again. */
+/* Make room for `capacity_rows` rows in the matrix and every per-row column (amortises appends). */
+int hdb_matrix_reserve(hdb_matrix* m, int64_t capacity_rows);
+/* Append n_rows rows (same dtype, row-major, host or device memory) after the last row.  Norms, sign bits and pearson
+ * statistics are computed for the NEW rows only.  Fails, leaving the shard unchanged, if the new rows hold a NaN. */
+int hdb_matrix_append(hdb_matrix* m, int64_t n_rows, const void* src, int src_space);
+/* Remove the listed LOCAL rows (any order, duplicates allowed); the remaining rows keep their relative order
+ * (stable in-place compaction on the device), so local row i of the result is the i-th surviving row. */
+int hdb_matrix_remove_rows(hdb_matrix* m, const int64_t* local_rows, int64_t count, int src_space);
+/* Global row id of the shard's first row (changes when an earlier shard grows or shrinks). */
+int hdb_matrix_set_row_offset(hdb_matrix* m, int64_t row_offset);
 
 /* ---- row subset: replaces the filters' output (hyperdb/hyperdb.py:1119-1134, :1218-1308) ---- */
 /* Keep only rows whose bit is set (bit i of word i/32, LSB first, local row ids); NULL keeps all. */

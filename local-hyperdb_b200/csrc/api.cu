@@ -26,6 +26,7 @@ constexpr int64_t kChunk = 64;     // queries per fused batch chunk (bounds the 
 struct hdb_matrix {
   int device = 0, dtype = 0;
   int64_t n = 0, d = 0, row_offset = 0;
+  int64_t cap = 0;                  // row capacity of `rows` (when owned) and of every per-row column (>= n)
   void* rows = nullptr;
   bool owns_rows = false;
   void* norms = nullptr;
@@ -34,6 +35,8 @@ struct hdb_matrix {
   uint32_t* bits = nullptr;
   int words = 0;
   float max_norm = 0.f, max_ratio = 1.f;
+  void* pmean = nullptr; void* pstd = nullptr; void* pscale = nullptr;    // pearson columns, built on first use
+  float max_pratio = 0.f, max_cratio = 0.f, min_pstd = 0.f;
   bool finalized = false;
   uint32_t* mask = nullptr;
   int64_t lo = 0, hi = 0, n_kept = 0;
@@ -55,6 +58,7 @@ struct hdb_matrix {
   int64_t* o_idx = nullptr; double* o_score = nullptr; int64_t* o_count = nullptr; uint32_t* o_flags = nullptr;
   double* totals = nullptr;
   void* sort_scratch = nullptr; size_t sort_scratch_bytes = 0;
+  void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;      // row removal
   unsigned long long* misc = nullptr;   // [2] ordered max bits, count
   float* stats = nullptr; int* nan_flag = nullptr;
   // query pipelining (hdb_matrix_set_post_stream): the per-query workspaces exist twice so that the certify step of
@@ -92,6 +96,7 @@ static MatrixView view_of(const hdb_matrix* m) {
   v.rows = m->rows; v.dtype = m->dtype; v.n = m->n; v.d = m->d; v.row_offset = m->row_offset;
   v.norms = m->norms; v.inv_norms = m->inv_norms; v.sqnorms = m->sqnorms; v.bits = m->bits; v.words = m->words;
   v.max_norm = m->max_norm; v.max_ratio = m->max_ratio;
+  v.pmean = m->pmean; v.pstd = m->pstd; v.pscale = m->pscale; v.max_pratio = m->max_pratio; v.max_cratio = m->max_cratio; v.min_pstd = m->min_pstd;
   return v;
 }
 static RowFilter filter_of(const hdb_matrix* m, double bias, bool use_decay) {
@@ -108,6 +113,11 @@ static int dev_alloc(T** p, size_t count) {
   if (count == 0) count = 1;
   HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
   return 0;
+}
+
+static size_t cap_rows(const hdb_matrix* m) {
+  const int64_t c = m->cap > m->n ? m->cap : m->n;
+  return (size_t)(c > 0 ? c : 1);
 }
 
 static int refresh_kept(hdb_matrix* m) {
@@ -144,10 +154,11 @@ int hdb_matrix_create(int device, int dtype, int64_t n_rows, int64_t dim, int64_
   HDB_CUDA(cudaSetDevice(device));
   hdb_matrix* m = new hdb_matrix();
   m->device = device; m->dtype = dtype; m->n = n_rows; m->d = dim; m->row_offset = row_offset;
+  m->cap = n_rows;
   m->lo = 0; m->hi = n_rows; m->n_kept = n_rows;
   m->grid = sweep_grid_size(device);
   int rc = dev_alloc(&m->misc, 2);
-  if (!rc) rc = dev_alloc(&m->stats, 2);
+  if (!rc) rc = dev_alloc(&m->stats, 4);
   if (!rc) rc = dev_alloc(&m->nan_flag, 1);
   if (!rc) rc = dev_alloc(&m->uncertified, 1);
   if (rc) { delete m; return rc; }
@@ -163,16 +174,16 @@ int hdb_matrix_destroy(hdb_matrix* m) {
   slot_store(m);
   {
     hdb_matrix::QuerySlot& other = m->slots[m->cur_slot ^ 1];
-    void* extra[] = {other.q_raw, other.qb.qa, other.qb.qc, other.qb.qbits, other.qb.qnorm, other.qb.qflags, other.cand, other.tau};
+    void* extra[] = {other.q_raw, other.qb.qa, other.qb.qc, other.qb.qbits, other.qb.qnorm, other.qb.qflags, other.qb.qaux, other.cand, other.tau};
     for (void* p : extra) if (p) cudaFree(p);
     for (auto& q : m->slots) if (q.done) cudaEventDestroy(q.done);
     if (m->ev_select) cudaEventDestroy(m->ev_select);
     if (m->ev_prep) cudaEventDestroy(m->ev_prep);
     if (m->pre_stream) cudaStreamDestroy(m->pre_stream);
   }
-  void* ptrs[] = {m->norms, m->inv_norms, m->sqnorms, m->bits, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
-                  m->qb.qnorm, m->qb.qflags, m->cand, m->tau, m->uncertified, m->o_block,
-                  m->totals, m->sort_scratch, m->misc, m->stats, m->nan_flag, m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand,
+  void* ptrs[] = {m->norms, m->inv_norms, m->sqnorms, m->bits, m->pmean, m->pstd, m->pscale, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
+                  m->qb.qnorm, m->qb.qflags, m->qb.qaux, m->cand, m->tau, m->uncertified, m->o_block,
+                  m->totals, m->sort_scratch, m->scan_tmp, m->misc, m->stats, m->nan_flag, m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand,
                   m->tc.cand_count, m->tc.rec, m->tc.rec_count, m->tc.qsq};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (m->h_block) cudaFreeHost(m->h_block);
@@ -231,7 +242,7 @@ int hdb_matrix_upload(hdb_matrix* m, int64_t row_start, int64_t n_rows, const vo
   HDB_CUDA(cudaSetDevice(m->device));
   const size_t row_bytes = (size_t)m->d * dtype_size(m->dtype);
   if (!m->rows) {
-    HDB_CUDA(cudaMalloc(&m->rows, (size_t)(m->n ? m->n : 1) * row_bytes));
+    HDB_CUDA(cudaMalloc(&m->rows, cap_rows(m) * row_bytes));
     m->owns_rows = true;
   } else if (!m->owns_rows) {
     return fail("hdb_matrix_upload: the shard uses adopted memory");
@@ -264,9 +275,10 @@ int hdb_matrix_finalize(hdb_matrix* m) {
   if (m->inv_norms) { cudaFree(m->inv_norms); m->inv_norms = nullptr; }
   if (m->bits) { cudaFree(m->bits); m->bits = nullptr; }
   if (m->sqnorms) { cudaFree(m->sqnorms); m->sqnorms = nullptr; }
-  if (m->dtype != 2) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->sqnorms), (size_t)(m->n ? m->n : 1) * 4));
-  HDB_CUDA(cudaMalloc(&m->norms, (size_t)(m->n ? m->n : 1) * nsz));
-  HDB_CUDA(cudaMalloc(&m->inv_norms, (size_t)(m->n ? m->n : 1) * nsz));
+  for (void** p : {&m->pmean, &m->pstd, &m->pscale}) if (*p) { cudaFree(*p); *p = nullptr; }
+  if (m->dtype != 2) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->sqnorms), cap_rows(m) * 4));
+  HDB_CUDA(cudaMalloc(&m->norms, cap_rows(m) * nsz));
+  HDB_CUDA(cudaMalloc(&m->inv_norms, cap_rows(m) * nsz));
   HDB_CUDA(cudaMemsetAsync(m->stats, 0, 8, m->stream));
   HDB_CUDA(cudaMemsetAsync(m->nan_flag, 0, 4, m->stream));
   MatrixView v = view_of(m);
@@ -287,8 +299,45 @@ int hdb_matrix_finalize(hdb_matrix* m) {
 
 static int ensure_bits(hdb_matrix* m) {
   if (m->bits) return 0;
-  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->bits), (size_t)(m->n ? m->n : 1) * m->words * 4));
+  HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->bits), cap_rows(m) * m->words * 4));
   return launch_pack_bits(view_of(m), m->bits, m->words, m->stream);
+}
+
+// np.mean / np.std columns and certificate statistics of rows [r0, r0+cnt); the statistics are merged into the running ones
+static int pearson_stats_rows(hdb_matrix* m, int64_t r0, int64_t cnt) {
+  if (cnt == 0) return 0;
+  const size_t nsz = (m->dtype == 2) ? 8 : 4;
+  uint32_t init[4] = {0u, 0xffffffffu, 0u, 0u};
+  memcpy(&init[0], &m->max_pratio, 4);
+  memcpy(&init[2], &m->max_cratio, 4);
+  if (m->min_pstd > 0.f) { const float neg = -m->min_pstd; memcpy(&init[1], &neg, 4); }
+  HDB_CUDA(cudaMemcpyAsync(m->stats, init, 16, cudaMemcpyHostToDevice, m->stream));
+  MatrixView v = view_of(m);
+  v.rows = reinterpret_cast<const char*>(m->rows) + (size_t)r0 * m->d * dtype_size(m->dtype);
+  v.n = cnt;
+  HDB_TRY(launch_pearson_stats(v, reinterpret_cast<char*>(m->pmean) + r0 * nsz, reinterpret_cast<char*>(m->pstd) + r0 * nsz,
+                               reinterpret_cast<char*>(m->pscale) + r0 * nsz, m->stats, m->stream));
+  uint32_t got[4];
+  HDB_CUDA(cudaMemcpyAsync(got, m->stats, 16, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  float negstd;
+  memcpy(&m->max_pratio, &got[0], 4);
+  memcpy(&m->max_cratio, &got[2], 4);
+  memcpy(&negstd, &got[1], 4);
+  m->min_pstd = (got[1] == 0xffffffffu || negstd < -1.0e38f) ? 0.f : -negstd;     // 0: every row is constant
+  return 0;
+}
+
+// pearson_correlation's np.mean / np.std per row (ranking_algorithm.py:91,94), once per matrix instead of once per query
+static int ensure_pearson(hdb_matrix* m) {
+  if (m->pmean) return 0;
+  const size_t nsz = (m->dtype == 2) ? 8 : 4;
+  const size_t cnt = cap_rows(m);
+  HDB_CUDA(cudaMalloc(&m->pmean, cnt * nsz));
+  HDB_CUDA(cudaMalloc(&m->pstd, cnt * nsz));
+  HDB_CUDA(cudaMalloc(&m->pscale, cnt * nsz));
+  m->max_pratio = 0.f; m->max_cratio = 0.f; m->min_pstd = 0.f;
+  return pearson_stats_rows(m, 0, m->n);
 }
 
 int hdb_matrix_set_mask(hdb_matrix* m, const uint32_t* bits, int src_space) {
@@ -298,7 +347,7 @@ int hdb_matrix_set_mask(hdb_matrix* m, const uint32_t* bits, int src_space) {
     if (m->mask) { cudaStreamSynchronize(m->stream); cudaFree(m->mask); m->mask = nullptr; }
   } else {
     const size_t words = (size_t)((m->n + 31) / 32);
-    if (!m->mask) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->mask), (words ? words : 1) * 4));
+    if (!m->mask) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->mask), ((cap_rows(m) + 31) / 32) * 4));
     HDB_CUDA(cudaMemcpyAsync(m->mask, bits, words * 4, src_space == HDB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                              m->stream));
   }
@@ -326,8 +375,8 @@ int hdb_matrix_set_timestamps(hdb_matrix* m, const double* ts, int src_space) {
     if (m->decay) { cudaFree(m->decay); m->decay = nullptr; }
     return 0;
   }
-  if (!m->ts) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->ts), (size_t)(m->n ? m->n : 1) * 8));
-  if (!m->decay) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->decay), (size_t)(m->n ? m->n : 1) * 8));
+  if (!m->ts) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->ts), cap_rows(m) * 8));
+  if (!m->decay) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->decay), cap_rows(m) * 8));
   HDB_CUDA(cudaMemcpyAsync(m->ts, ts, (size_t)m->n * 8, src_space == HDB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                            m->stream));
   HDB_CUDA(cudaStreamSynchronize(m->stream));
@@ -353,6 +402,7 @@ int hdb_matrix_set_decay_reference(hdb_matrix* m, double ts_max) {
   if (!m) return fail("null handle");
   if (!m->ts) return fail("hdb_matrix_set_decay_reference: no timestamps set");
   HDB_CUDA(cudaSetDevice(m->device));
+  if (!m->decay) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->decay), cap_rows(m) * 8));     // dropped by a mutation
   HDB_TRY(launch_decay(m->ts, m->decay, m->n, ts_max, m->stream));
   m->decay_valid = true;
   return 0;
@@ -366,6 +416,185 @@ int hdb_matrix_stage1_recency(hdb_matrix* m, double bias1, double ts_max) {
   return launch_stage1(m->ts, m->n, bias1, ts_max, m->stream);
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Mutation of a resident shard: the reference re-materialises the whole matrix on every
+// add (np.concatenate, hyperdb/hyperdb.py:504-509) and every remove_document (np.vstack / mask copy, :718-728).
+// ---------------------------------------------------------------------------------------------
+static int quiesce(hdb_matrix* m) {
+  HDB_CUDA(cudaSetDevice(m->device));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->post_stream) HDB_CUDA(cudaStreamSynchronize(m->post_stream));
+  if (m->pre_stream) HDB_CUDA(cudaStreamSynchronize(m->pre_stream));
+  for (auto& q : m->slots) q.pending = false;
+  return 0;
+}
+
+// the per-query row subset / decay state does not survive a change of the row set
+static void drop_row_state(hdb_matrix* m) {
+  if (m->mask) { cudaFree(m->mask); m->mask = nullptr; }
+  if (m->decay) { cudaFree(m->decay); m->decay = nullptr; }
+  m->decay_valid = false;
+  if (m->totals) { cudaFree(m->totals); m->totals = nullptr; }
+}
+
+static int grow_column(void** p, size_t row_bytes, int64_t n_used, int64_t new_cap, cudaStream_t s) {
+  if (!*p) return 0;
+  void* fresh = nullptr;
+  HDB_CUDA(cudaMalloc(&fresh, (size_t)(new_cap > 0 ? new_cap : 1) * row_bytes));
+  if (n_used > 0) HDB_CUDA(cudaMemcpyAsync(fresh, *p, (size_t)n_used * row_bytes, cudaMemcpyDeviceToDevice, s));
+  HDB_CUDA(cudaStreamSynchronize(s));
+  cudaFree(*p);
+  *p = fresh;
+  return 0;
+}
+
+extern "C" int hdb_matrix_reserve(hdb_matrix* m, int64_t capacity_rows) {
+  if (!m) return fail("null handle");
+  if (m->rows && !m->owns_rows) return fail("hdb_matrix_reserve: the shard uses adopted memory");
+  if (capacity_rows <= m->cap) return 0;
+  HDB_TRY(quiesce(m));
+  const size_t row_bytes = (size_t)m->d * dtype_size(m->dtype);
+  const size_t nsz = (m->dtype == 2) ? 8 : 4;
+  if (!m->rows) {
+    HDB_CUDA(cudaMalloc(&m->rows, (size_t)capacity_rows * row_bytes));
+    m->owns_rows = true;
+  } else {
+    HDB_TRY(grow_column(&m->rows, row_bytes, m->n, capacity_rows, m->stream));
+  }
+  HDB_TRY(grow_column(&m->norms, nsz, m->n, capacity_rows, m->stream));
+  HDB_TRY(grow_column(&m->inv_norms, nsz, m->n, capacity_rows, m->stream));
+  HDB_TRY(grow_column(reinterpret_cast<void**>(&m->sqnorms), 4, m->n, capacity_rows, m->stream));
+  HDB_TRY(grow_column(reinterpret_cast<void**>(&m->bits), (size_t)m->words * 4, m->n, capacity_rows, m->stream));
+  HDB_TRY(grow_column(&m->pmean, nsz, m->n, capacity_rows, m->stream));
+  HDB_TRY(grow_column(&m->pstd, nsz, m->n, capacity_rows, m->stream));
+  HDB_TRY(grow_column(&m->pscale, nsz, m->n, capacity_rows, m->stream));
+  HDB_TRY(grow_column(reinterpret_cast<void**>(&m->ts), 8, m->n, capacity_rows, m->stream));
+  HDB_TRY(grow_column(reinterpret_cast<void**>(&m->decay), 8, m->n, capacity_rows, m->stream));
+  if (m->mask) {          // one bit per row, whole words
+    uint32_t* fresh = nullptr;
+    HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&fresh), (size_t)((capacity_rows + 31) / 32) * 4));
+    HDB_CUDA(cudaMemcpy(fresh, m->mask, (size_t)((m->n + 31) / 32) * 4, cudaMemcpyDeviceToDevice));
+    cudaFree(m->mask);
+    m->mask = fresh;
+  }
+  if (m->totals) { cudaFree(m->totals); m->totals = nullptr; }
+  m->cap = capacity_rows;
+  return 0;
+}
+
+extern "C" int hdb_matrix_append(hdb_matrix* m, int64_t n_rows, const void* src, int src_space) {
+  if (!m) return fail("null handle");
+  if (!m->finalized) return fail("hdb_matrix_append: call hdb_matrix_finalize first");
+  if (m->rows && !m->owns_rows) return fail("hdb_matrix_append: the shard uses adopted memory");
+  if (n_rows < 0) return fail("hdb_matrix_append: negative row count");
+  if (n_rows == 0) return 0;
+  if (!src) return fail("hdb_matrix_append: src is NULL");
+  if (m->n + n_rows >= (int64_t(1) << 32)) return fail("hdb_matrix_append: more than 2^32 rows per shard");
+  HDB_TRY(quiesce(m));
+  if (m->n + n_rows > m->cap || !m->rows) {
+    int64_t want = m->cap + m->cap / 2;                       // geometric growth: amortised O(1) copies per appended row
+    if (want < m->n + n_rows) want = m->n + n_rows;
+    HDB_TRY(hdb_matrix_reserve(m, want));
+  }
+  const size_t row_bytes = (size_t)m->d * dtype_size(m->dtype);
+  const size_t nsz = (m->dtype == 2) ? 8 : 4;
+  const int64_t r0 = m->n;
+  HDB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m->rows) + (size_t)r0 * row_bytes, src, (size_t)n_rows * row_bytes,
+                           src_space == HDB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m->stream));
+  // ingest statistics of the new rows only, merged into the running maxima
+  float hs[2] = {m->max_norm, m->max_ratio};
+  HDB_CUDA(cudaMemcpyAsync(m->stats, hs, 8, cudaMemcpyHostToDevice, m->stream));
+  HDB_CUDA(cudaMemsetAsync(m->nan_flag, 0, 4, m->stream));
+  MatrixView sub = view_of(m);
+  sub.rows = reinterpret_cast<const char*>(m->rows) + (size_t)r0 * row_bytes;
+  sub.n = n_rows;
+  HDB_TRY(launch_row_stats(sub, reinterpret_cast<char*>(m->norms) + r0 * nsz, reinterpret_cast<char*>(m->inv_norms) + r0 * nsz,
+                           m->sqnorms ? m->sqnorms + r0 : nullptr, m->stats, m->nan_flag, m->stream));
+  int hnan = 0;
+  HDB_CUDA(cudaMemcpyAsync(hs, m->stats, 8, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaMemcpyAsync(&hnan, m->nan_flag, 4, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  if (hnan) return fail("Vectors and query_vector should not contain NaN values.");       // the shard is unchanged
+  m->max_norm = hs[0];
+  m->max_ratio = hs[1] > 0.f ? hs[1] : 1.f;
+  if (m->bits) HDB_TRY(launch_pack_bits(sub, m->bits + (size_t)r0 * m->words, m->words, m->stream));
+  if (m->pmean) HDB_TRY(pearson_stats_rows(m, r0, n_rows));
+  if (m->ts) { cudaFree(m->ts); m->ts = nullptr; }          // timestamps of the new rows are unknown: set them again
+  drop_row_state(m);
+  m->n += n_rows;
+  m->lo = 0; m->hi = m->n;
+  return refresh_kept(m);
+}
+
+extern "C" int hdb_matrix_remove_rows(hdb_matrix* m, const int64_t* local_rows, int64_t count, int src_space) {
+  if (!m) return fail("null handle");
+  if (!m->finalized) return fail("hdb_matrix_remove_rows: call hdb_matrix_finalize first");
+  if (m->rows && !m->owns_rows) return fail("hdb_matrix_remove_rows: the shard uses adopted memory");
+  if (count < 0) return fail("hdb_matrix_remove_rows: negative count");
+  if (count == 0 || m->n == 0) return count == 0 ? 0 : fail("hdb_matrix_remove_rows: row index out of range");
+  if (!local_rows) return fail("hdb_matrix_remove_rows: NULL rows");
+  HDB_TRY(quiesce(m));
+  const int64_t n = m->n;
+  int64_t* d_rows = nullptr;
+  uint32_t* plan = nullptr;            // keep | pos | src
+  void* bounce = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() { if (d_rows) cudaFree(d_rows); if (plan) cudaFree(plan); if (bounce) cudaFree(bounce); };
+  const int64_t* rows_dev = local_rows;
+  if (src_space != HDB_DEVICE) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_rows), (size_t)count * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, local_rows, (size_t)count * 8, cudaMemcpyHostToDevice, m->stream);
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "remove_rows staging"); }
+    rows_dev = d_rows;
+  }
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&plan), (size_t)n * 12);
+  if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "remove_rows plan"); }
+  cudaMemsetAsync(m->nan_flag, 0, 4, m->stream);
+  rc = launch_plan_removal(n, rows_dev, count, plan, plan + n, plan + 2 * n, m->misc, m->nan_flag, &m->scan_tmp, &m->scan_tmp_bytes, m->stream);
+  unsigned long long n_new = 0;
+  int bad = 0;
+  if (!rc) {
+    e = cudaMemcpyAsync(&n_new, m->misc, 8, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, m->nan_flag, 4, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "remove_rows plan readback");
+  }
+  if (!rc && bad) rc = fail("hdb_matrix_remove_rows: row index out of range");
+  if (!rc && (int64_t)n_new < n) {
+    const size_t row_bytes = (size_t)m->d * dtype_size(m->dtype);
+    const size_t nsz = (m->dtype == 2) ? 8 : 4;
+    size_t bounce_bytes = (size_t)64 << 20;
+    if (bounce_bytes < row_bytes) bounce_bytes = row_bytes;
+    e = cudaMalloc(&bounce, bounce_bytes);
+    if (e != cudaSuccess) rc = cuda_fail(e, "remove_rows bounce");
+    const uint32_t* src = plan + 2 * n;
+    struct Col { void* p; size_t rb; } cols[] = {{m->rows, row_bytes}, {m->norms, nsz}, {m->inv_norms, nsz}, {m->sqnorms, 4},
+                                                  {m->bits, (size_t)m->words * 4}, {m->pmean, nsz}, {m->pstd, nsz}, {m->pscale, nsz}, {m->ts, 8}};
+    for (const Col& c : cols)
+      if (!rc) rc = launch_compact_column(c.p, (int64_t)c.rb, (int64_t)n_new, src, bounce, bounce_bytes, m->stream);
+    if (!rc) { e = cudaStreamSynchronize(m->stream); if (e != cudaSuccess) rc = cuda_fail(e, "remove_rows compaction"); }
+    if (!rc) {
+      drop_row_state(m);                 // max_norm / max_ratio / pearson statistics stay valid as bounds over a subset
+      m->n = (int64_t)n_new;
+      m->lo = 0; m->hi = m->n;
+    }
+  }
+  cleanup();
+  if (rc) return rc;
+  return refresh_kept(m);
+}
+
+extern "C" int hdb_matrix_set_row_offset(hdb_matrix* m, int64_t row_offset) {
+  if (!m) return fail("null handle");
+  if (row_offset < 0) return fail("hdb_matrix_set_row_offset: negative offset");
+  m->row_offset = row_offset;
+  return 0;
+}
+
+extern "C" {
+
 // ---------------------------------------------------------------------------------------------
 static int ensure_workspace(hdb_matrix* m, int64_t nq, int64_t k) {
   const int64_t cq = nq < kChunk ? (nq < 1 ? 1 : nq) : kChunk;       // fused chunk capacity
@@ -376,6 +605,7 @@ static int ensure_workspace(hdb_matrix* m, int64_t nq, int64_t k) {
     HDB_TRY(dev_alloc(&m->qb.qbits, (size_t)nq * m->words));
     HDB_TRY(dev_alloc(&m->qb.qnorm, (size_t)nq));
     HDB_TRY(dev_alloc(&m->qb.qflags, (size_t)nq));
+    HDB_TRY(dev_alloc(&m->qb.qaux, (size_t)nq * 2));
     HDB_TRY(dev_alloc(&m->tau, (size_t)nq));
     m->ws_q = nq;
   }
@@ -395,7 +625,7 @@ static int ensure_workspace(hdb_matrix* m, int64_t nq, int64_t k) {
   m->o_score = reinterpret_cast<double*>(m->o_block + (size_t)nq * kk * 8);
   m->o_count = reinterpret_cast<int64_t*>(m->o_block + (size_t)nq * kk * 16);
   m->o_flags = reinterpret_cast<uint32_t*>(m->o_block + (size_t)nq * kk * 16 + (size_t)nq * 8);
-  if (!m->totals) HDB_TRY(dev_alloc(&m->totals, (size_t)(m->n ? m->n : 1)));
+  if (!m->totals) HDB_TRY(dev_alloc(&m->totals, cap_rows(m)));
   return 0;
 }
 
@@ -421,14 +651,14 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
     const uint32_t* qbits = m->qb.qbits + (size_t)(b0 + i) * m->words;
     const bool prof = m->prof_used + 2 <= m->prof_ev.size();
     if (prof) HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used], m->stream));
-    HDB_TRY(launch_sweep(v, metric, qa, qbits, f, kp, so, m->stream));
+    HDB_TRY(launch_sweep(v, metric, qa, qbits, m->qb.qaux + 2 * (b0 + i), f, kp, so, m->stream));
     if (prof) { HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used + 1], m->stream)); m->prof_used += 2; }
   }
   FinalizeArgs a;
   a.m = v; a.f = f; a.metric = metric; a.rdt = rdt; a.kp = kp; a.k = (int)k; a.n_kept = m->n_kept; a.grid = m->grid;
   a.cand = m->cand; a.tau = m->tau + b0;
   a.qb = m->qb;
-  a.qb.qc += b0 * m->d; a.qb.qbits += b0 * m->words; a.qb.qnorm += b0; a.qb.qflags += b0;
+  a.qb.qc += b0 * m->d; a.qb.qbits += b0 * m->words; a.qb.qnorm += b0; a.qb.qflags += b0; a.qb.qaux += 2 * b0;
   a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
   a.uncertified = m->uncertified;
   a.cand_count = nullptr; a.cand_stride = 0; a.tau0 = nullptr; a.extra_flags = 0; a.tau0_negd2 = 0;
@@ -491,7 +721,7 @@ static int run_tensor(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, in
   a.m = v; a.f = f; a.metric = metric; a.rdt = rdt; a.kp = kp; a.k = (int)k; a.n_kept = m->n_kept; a.grid = 0;
   a.cand = m->tc.cand; a.tau = nullptr;
   a.qb = m->qb;
-  a.qb.qc += b0 * m->d; a.qb.qbits += b0 * m->words; a.qb.qnorm += b0; a.qb.qflags += b0;
+  a.qb.qc += b0 * m->d; a.qb.qbits += b0 * m->words; a.qb.qnorm += b0; a.qb.qflags += b0; a.qb.qaux += 2 * b0;
   a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
   a.uncertified = m->uncertified;
   a.cand_count = m->tc.cand_count; a.cand_stride = m->tc.cap; a.tau0 = m->tc.tau0; a.extra_flags = HDB_FLAG_TENSOR;
@@ -502,7 +732,7 @@ static int run_tensor(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, in
 static int run_exact(hdb_matrix* m, int metric, int rdt, int64_t b, int64_t k, const RowFilter& f, int64_t* idx, double* score,
                      int64_t* count) {
   MatrixView v = view_of(m);
-  HDB_TRY(launch_full_scores(v, f, metric, rdt, m->qb.qc + b * m->d, m->qb.qbits + b * m->words, m->totals, m->stream));
+  HDB_TRY(launch_full_scores(v, f, metric, rdt, m->qb.qc + b * m->d, m->qb.qbits + b * m->words, m->qb.qaux + 2 * b, m->totals, m->stream));
   return exact_topk(m->device, m->totals, m->n, m->row_offset, k, m->n_kept, idx + b * k, score + b * k, count + b,
                     &m->sort_scratch, &m->sort_scratch_bytes, m->stream);
 }
@@ -512,7 +742,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
               int out_space) {
   if (!m) return fail("null handle");
   if (!m->finalized) return fail("hdb_query: call hdb_matrix_finalize first");
-  if (metric < 0 || metric > 5) return fail("Unknown metric");
+  if (metric < 0 || metric > 6) return fail("Unknown metric");
   if (q_dtype < 0 || q_dtype > 2) return fail("hdb_query: q_dtype must be HDB_F16/F32/F64");
   if (nq < 0) return fail("hdb_query: negative query count");
   if (nq == 0) return 0;
@@ -539,6 +769,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   HDB_TRY(ensure_workspace(m, nq, k));
   const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
   if (metric == HDB_HAMMING || metric == HDB_JACCARD) HDB_TRY(ensure_bits(m));
+  if (metric == HDB_PEARSON) HDB_TRY(ensure_pearson(m));
 
   const void* q_dev = queries;
   if (q_space == HDB_HOST) {
@@ -709,7 +940,7 @@ int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter) 
       HDB_CUDA(cudaMemsetAsync(m->tau, 0, 8, m->stream));
       SweepOut so; so.cand = m->cand; so.tau = m->tau; so.grid = m->grid;
       (void)elt;
-      HDB_TRY(launch_sweep(v, m->last.metric, m->qb.qa, m->qb.qbits, f, m->last.kp, so, m->stream));
+      HDB_TRY(launch_sweep(v, m->last.metric, m->qb.qa, m->qb.qbits, m->qb.qaux, f, m->last.kp, so, m->stream));
     } else {
       HDB_TRY(run_fused(m, m->last.metric, m->last.rdt, m->last.kp, 0, nq, m->last.k, f, m->o_idx, m->o_score, m->o_count,
                         m->o_flags));
@@ -729,28 +960,30 @@ int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_
                int* out_dtype) {
   if (!m) return fail("null handle");
   if (!m->finalized) return fail("hdb_scores: call hdb_matrix_finalize first");
-  if (metric < 0 || metric > 5) return fail("Unknown metric");
+  if (metric < 0 || metric > 6) return fail("Unknown metric");
   if (q_dtype < 0 || q_dtype > 2) return fail("hdb_scores: q_dtype must be HDB_F16/F32/F64");
   if (!query || !out) return fail("hdb_scores: NULL argument");
   HDB_CUDA(cudaSetDevice(m->device));
   HDB_TRY(ensure_workspace(m, 1, 1));
   const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
   if (metric == HDB_HAMMING || metric == HDB_JACCARD) HDB_TRY(ensure_bits(m));
+  if (metric == HDB_PEARSON) HDB_TRY(ensure_pearson(m));
   const void* q_dev = query;
   if (q_space == HDB_HOST) {
     HDB_CUDA(cudaMemcpyAsync(m->q_raw, query, (size_t)m->d * dtype_size(q_dtype), cudaMemcpyHostToDevice, m->stream));
     q_dev = m->q_raw;
   }
   HDB_TRY(launch_prep_query(q_dev, q_dtype, 1, m->d, metric, m->dtype, m->words, m->qb, nullptr, m->stream));
-  const size_t esz = (metric == HDB_HAMMING || metric == HDB_JACCARD) ? 8 : (size_t)dtype_size(rdt);
-  if (out_dtype) *out_dtype = (metric == HDB_HAMMING) ? 3 : (metric == HDB_JACCARD ? 2 : rdt);
+  const bool f64_out = (metric == HDB_JACCARD || metric == HDB_PEARSON);
+  const size_t esz = (metric == HDB_HAMMING || f64_out) ? 8 : (size_t)dtype_size(rdt);
+  if (out_dtype) *out_dtype = (metric == HDB_HAMMING) ? 3 : (f64_out ? 2 : rdt);
   void* dst = out;
   void* tmp = nullptr;
   if (out_space == HDB_HOST) {
     HDB_CUDA(cudaMalloc(&tmp, (size_t)(m->n ? m->n : 1) * esz));
     dst = tmp;
   }
-  int rc = launch_scores_out(view_of(m), metric, rdt, m->qb.qc, m->qb.qbits, dst, m->stream);
+  int rc = launch_scores_out(view_of(m), metric, rdt, m->qb.qc, m->qb.qbits, m->qb.qaux, dst, m->stream);
   if (!rc && out_space == HDB_HOST) {
     cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)m->n * esz, cudaMemcpyDeviceToHost, m->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);

@@ -20,6 +20,7 @@ template <int RDT> struct Arith;
 template <> struct Arith<0> {                     // float16 result dtype
   using C = float;
   static __device__ __forceinline__ C rnd(float x) { return __half2float(__float2half_rn(x)); }
+  static __device__ __forceinline__ C rnd_c(C x) { return rnd(x); }
   static __device__ __forceinline__ C sub(C a, C b) { return rnd(__fsub_rn(a, b)); }
   static __device__ __forceinline__ C add(C a, C b) { return rnd(__fadd_rn(a, b)); }
   static __device__ __forceinline__ C mul(C a, C b) { return rnd(__fmul_rn(a, b)); }
@@ -31,6 +32,7 @@ template <> struct Arith<0> {                     // float16 result dtype
 };
 template <> struct Arith<1> {                     // float32
   using C = float;
+  static __device__ __forceinline__ C rnd_c(C x) { return x; }
   static __device__ __forceinline__ C sub(C a, C b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ C add(C a, C b) { return __fadd_rn(a, b); }
   static __device__ __forceinline__ C mul(C a, C b) { return __fmul_rn(a, b); }
@@ -42,6 +44,7 @@ template <> struct Arith<1> {                     // float32
 };
 template <> struct Arith<2> {                     // float64
   using C = double;
+  static __device__ __forceinline__ C rnd_c(C x) { return x; }
   static __device__ __forceinline__ C sub(C a, C b) { return __dsub_rn(a, b); }
   static __device__ __forceinline__ C add(C a, C b) { return __dadd_rn(a, b); }
   static __device__ __forceinline__ C mul(C a, C b) { return __dmul_rn(a, b); }
@@ -183,6 +186,67 @@ __device__ typename Arith<DT>::C canonical_norm(const void* x, int64_t d) {
   return A::sqrt(pairwise_sum<DT>(term, (int)d));
 }
 
+// float64 -> dtype DT in ONE rounding (a float64 ufunc result cast to the output array's dtype), carried in C
+template <int DT>
+__device__ __forceinline__ typename Arith<DT>::C round_to(double x) {
+  if (DT == 0) return (typename Arith<DT>::C)__half2float(__double2half(x));
+  if (DT == 1) return (typename Arith<DT>::C)(float)x;
+  return (typename Arith<DT>::C)x;
+}
+
+// np.mean / np.std of d values of dtype DT (numpy._core._methods._mean / _var / _std), `val(j)` = element j in C:
+//   mean: pairwise sum (float16: in float32, unrounded), / d formed in float64 (the count is a NumPy integer scalar),
+//         cast to DT -- through float32 first for a float16 ARRAY result, directly for a 1-D input (`scalar`);
+//   std : arrmean = DT(sum_DT / d), dev = (x - arrmean)^2 in DT, sqrt(DT(sum_DT(dev) / d)).
+// hyperdb/ranking_algorithm.py:90-94.  `sum` abstracts the pairwise summation (sequential or warp-cooperative).
+template <int DT, typename Val, typename Sum32, typename SumDT>
+__device__ void mean_std_core(Val val, int d, bool scalar, Sum32 sum_f32, SumDT sum_dt, typename Arith<DT>::C* mean,
+                              typename Arith<DT>::C* stdv) {
+  using A = Arith<DT>;
+  using C = typename A::C;
+  const double dd = (double)d;
+  C sum_rounded;
+  if (DT == 0) {
+    const float s32 = (float)sum_f32([&](int j) { return (float)val(j); });
+    const double qd = (double)s32 / dd;
+    *mean = scalar ? round_to<DT>(qd) : round_to<DT>((double)(float)qd);
+    sum_rounded = A::rnd_c((C)s32);
+  } else {
+    sum_rounded = sum_dt([&](int j) { return val(j); });
+    *mean = round_to<DT>((double)sum_rounded / dd);
+  }
+  const C arrmean = round_to<DT>((double)sum_rounded / dd);
+  const C ssq = sum_dt([&](int j) { const C df = A::sub(val(j), arrmean); return A::mul(df, df); });
+  *stdv = A::sqrt(round_to<DT>((double)ssq / dd));
+}
+
+template <int DT>
+__device__ void canonical_mean_std(const void* x, int64_t d, bool scalar, typename Arith<DT>::C* mean, typename Arith<DT>::C* stdv) {
+  using C = typename Arith<DT>::C;
+  auto val = [&](int j) -> C { return Arith<DT>::from_double(load_as_double(x, DT, j)); };
+  mean_std_core<DT>(val, (int)d, scalar,
+                    [&](auto term) { return pairwise_sum<1>(term, (int)d); },
+                    [&](auto term) { return pairwise_sum<DT>(term, (int)d); }, mean, stdv);
+}
+
+// x - y in dtype `dt`'s arithmetic (runtime switch)
+__device__ __forceinline__ double sub_in(double x, double y, int dt) {
+  if (dt == 0) return (double)Arith<0>::sub((float)x, (float)y);
+  if (dt == 1) return (double)Arith<1>::sub((float)x, (float)y);
+  return Arith<2>::sub(x, y);
+}
+
+// pearson_correlation's last lines (ranking_algorithm.py:100-111): denominator = std_v * std_q * d in R; quotient only where
+// the denominator is non-zero (np.zeros elsewhere); NaN whenever either side is constant.
+template <int RDT>
+__device__ __forceinline__ double pearson_quotient(typename Arith<RDT>::C num, double std_v, double std_q, int d) {
+  using A = Arith<RDT>;
+  using C = typename A::C;
+  if (std_v == 0.0 || std_q == 0.0) return __longlong_as_double(0x7ff8000000000000ll);
+  const C den = A::mul(A::mul(A::from_double(std_v), A::from_double(std_q)), round_to<RDT>((double)d));
+  return den != C(0) ? (double)A::div(num, den) : 0.0;
+}
+
 // v / norm in the STORAGE dtype's arithmetic (get_norm_vector runs in the array's own dtype).
 __device__ __forceinline__ double unit_elem(double v, double norm, int dt) {
   if (dt == 0) return (double)Arith<0>::div((float)v, (float)norm);
@@ -226,6 +290,7 @@ struct CanonArgs {
   const uint32_t* qbits; // packed sign bits of the query (hamming) or nullptr
   int words;             // 32-bit words per packed row
   int metric;
+  double qstd;           // pearson: np.std(query) (query dtype, widened)
 };
 
 // Element-wise half of a canonical score (parallelisable): the per-column term the reference feeds into
@@ -255,10 +320,16 @@ __device__ double canonical_reduce(int metric, GetTerm term, GetQ gq, int d) {
 // (hamming: the integer D - popcount).  `rowp` points at the row's d stored elements, `bitrow` at its
 // packed sign bits; nrm is the row's canonical norm (cosine only).
 template <int RDT>
-__device__ double canonical_similarity(const CanonArgs& a, const void* rowp, const uint32_t* bitrow, double nrm) {
+__device__ double canonical_similarity(const CanonArgs& a, const void* rowp, const uint32_t* bitrow, double nrm, double aux2 = 0.0) {
   using A = Arith<RDT>;
   using C = typename A::C;
   const int d = (int)a.d;
+  if (a.metric == 6) {          // pearson: nrm = np.mean(row), aux2 = np.std(row); qc = q - np.mean(q) in the query's dtype
+    auto pterm = [&](int j) -> C {
+      return A::mul(A::from_double(sub_in(load_as_double(rowp, a.sdt, j), nrm, a.sdt)), A::from_double(a.qc[j]));
+    };
+    return pearson_quotient<RDT>(pairwise_sum<RDT>(pterm, d), aux2, a.qstd, d);
+  }
   if (a.metric == 4) {
     int diff = 0;
     for (int w = 0; w < a.words; ++w) diff += __popc(bitrow[w] ^ a.qbits[w]);
@@ -275,10 +346,10 @@ __device__ double canonical_similarity(const CanonArgs& a, const void* rowp, con
 }
 
 __device__ __forceinline__ double canonical_similarity_rt(const CanonArgs& a, int rdt, const void* rowp,
-                                                          const uint32_t* bitrow, double nrm) {
-  if (rdt == 0) return canonical_similarity<0>(a, rowp, bitrow, nrm);
-  if (rdt == 1) return canonical_similarity<1>(a, rowp, bitrow, nrm);
-  return canonical_similarity<2>(a, rowp, bitrow, nrm);
+                                                          const uint32_t* bitrow, double nrm, double aux2 = 0.0) {
+  if (rdt == 0) return canonical_similarity<0>(a, rowp, bitrow, nrm, aux2);
+  if (rdt == 1) return canonical_similarity<1>(a, rowp, bitrow, nrm, aux2);
+  return canonical_similarity<2>(a, rowp, bitrow, nrm, aux2);
 }
 
 // ranking_algorithm.py:171-186: float64 score, NaN -> -inf, + recency_bias * exp(ts - max ts)

@@ -47,7 +47,7 @@ __device__ __forceinline__ void load_batch<double>(const void* src, int64_t j0, 
 
 // Upper bound of the CANONICAL total score of any row whose selection key is <= the KP-th key
 // (score part s).  See DESIGN.md "certificate"; every term is a worst-case rounding bound.
-__device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) {
+__device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm, double qstd) {
   const double D = (double)a.m.d + 8.0;
   const double uk = 1.1920928955078125e-7;                    // 2^-23: float32 key rounding (2x slack)
   // accumulate type of the select pass; the tensor cores' fp32 accumulation is not IEEE round-to-nearest
@@ -57,6 +57,26 @@ __device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm) 
   const bool decay = a.f.decay != nullptr;
   const double chain16 = (a.rdt == 0) ? D * 1.1920928955078125e-7 : 0.0;   // HALF_dot / f16 pairwise run in float32
   if (a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) return s + fabs(s) * uk;     // exact on both sides: only the key rounding
+  if (a.metric == HDB_PEARSON) {
+    // Both sides evaluate rho~ = sum_j (v_j - mean_v) b_j / (std_v std_q d) from the SAME rounded statistics (b = q - mean_q).
+    // Magnitudes: sum_j |v_j b_j| / (std_v std_q d) <= A := max_i ||v_i|| / (std_i sqrt d) * ||b|| / (std_q sqrt d)   (qnorm slot),
+    // and ||v - mean_v|| <= 2 ||v||, so |rho~| <= 2A.
+    //             sum_j |(v_j - mean_v) b_j| / (std_v std_q d) <= Ac := max_i ||v_i - mean_i|| / (std_i sqrt d) * (same query factor), ~1.
+    const double A = (double)a.m.max_pratio * qnorm, Ac = (double)a.m.max_cratio * qnorm;
+    const double uaccR = (a.rdt == 2) ? 1.1102230246251565e-16 : 5.9604644775390625e-8;
+    double b = s + fabs(s) * uk
+             + A * ((D + 16.0) * ua + 1.1920928955078125e-7)   // sweep: FMA chains, mean correction, scalings; query rounded to the accumulate type
+             + Ac * 1.05 * (uT + uR + D * uaccR);              // reference: (v - mean) rounded to S, products to R, pairwise sum
+    // reference: rounding of the sum, the denominator (3 roundings) and the quotient, relative to the similarity itself
+    b += 6.0 * uR * (decay ? Ac : fabs(b));
+    if (a.rdt == 0 || a.m.dtype == 0) {
+      // float16: differences / products are multiples of 2^-24 (absolute errors), and the denominator must stay normal and finite
+      const double smin = (double)a.m.min_pstd;
+      if (!(smin * qstd > 2.44140625e-4) || !((double)a.m.max_norm * sqrt(D) * qstd * fmax(1.0, 2.0 * A) < 3.0e4)) return INFINITY;
+      b += 2.98023223876953125e-8 * (qnorm / smin + 1.0 / (smin * qstd)) * 1.5;
+    }
+    return decay ? b + fabs(b) * 1e-15 : b;
+  }
   if (a.metric == HDB_DOT || a.metric == HDB_COSINE) {
     const double A = (double)(a.metric == HDB_DOT ? a.m.max_norm : a.m.max_ratio) * qnorm;   // >= sum |v_i q_i|
     double e = D * ua + chain16;
@@ -132,6 +152,8 @@ __device__ void rescore_smem(const FinalizeArgs& a, int64_t b, const uint64_t* s
       CS nrm = CS(1);
       if (metric == HDB_COSINE) nrm = SDT == 2 ? (CS) reinterpret_cast<const double*>(a.m.norms)[row]
                                                 : (CS) reinterpret_cast<const float*>(a.m.norms)[row];
+      if (metric == HDB_PEARSON) nrm = SDT == 2 ? (CS) reinterpret_cast<const double*>(a.m.pmean)[row]
+                                                 : (CS) reinterpret_cast<const float*>(a.m.pmean)[row];
       C* dst = s_terms + (size_t)r * pitch;
       for (int j0 = lane; j0 < d; j0 += 32 * 8) {
         T raw[8];
@@ -145,6 +167,7 @@ __device__ void rescore_smem(const FinalizeArgs& a, int64_t b, const uint64_t* s
             C term;
             if (metric == 0) term = (C)vs;
             else if (metric == 1) term = (nrm == CS(1)) ? (C)vs : (C)AS::div(vs, nrm);
+            else if (metric == HDB_PEARSON) term = AR::mul((C)AS::sub(vs, nrm), s_q[j]);     // (v - mean) in S, product in R
             else {
               const C df = AR::sub((C)vs, s_q[j]);
               term = metric == 2 ? AR::mul(df, df) : C(fabs(df));
@@ -170,8 +193,14 @@ __device__ void rescore_smem(const FinalizeArgs& a, int64_t b, const uint64_t* s
         const uint32_t row = key_row(surv[base + r]);
         const C* terms = s_terms + (size_t)r * pitch;
         C dist = pairwise_sum_warp<RDT>([&](int j) { return terms[j]; }, d, lane, &s_pw[warp]);
-        if (metric == 2) dist = AR::sqrt(dist);
-        const double sim = (double)AR::div(C(1), AR::add(C(1), dist));
+        double sim;
+        if (metric == HDB_PEARSON) {
+          const double sd = SDT == 2 ? reinterpret_cast<const double*>(a.m.pstd)[row] : (double)reinterpret_cast<const float*>(a.m.pstd)[row];
+          sim = pearson_quotient<RDT>(dist, sd, a.qb.qaux[2 * b], d);
+        } else {
+          if (metric == 2) dist = AR::sqrt(dist);
+          sim = (double)AR::div(C(1), AR::add(C(1), dist));
+        }
         if (lane == 0) {
           c_tot[base + r] = total_score(sim, a.f.decay, a.f.bias, row);
           c_row[base + r] = row;
@@ -328,11 +357,16 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     ca.qbits = a.qb.qbits ? a.qb.qbits + b * a.m.words : nullptr;
     ca.metric = a.metric;
     ca.qc = a.qb.qc + b * a.m.d;
+    ca.qstd = a.qb.qaux ? a.qb.qaux[2 * b] : 1.0;
     const uint32_t row = key_row(surv[tid]);
     const uint32_t* bitrow = a.m.bits ? a.m.bits + (int64_t)row * a.m.words : nullptr;
-    double nrm = 1.0;
+    double nrm = 1.0, aux2 = 0.0;
     if (a.metric == HDB_COSINE)
       nrm = a.m.dtype == 2 ? reinterpret_cast<const double*>(a.m.norms)[row] : (double)reinterpret_cast<const float*>(a.m.norms)[row];
+    if (a.metric == HDB_PEARSON) {
+      nrm = a.m.dtype == 2 ? reinterpret_cast<const double*>(a.m.pmean)[row] : (double)reinterpret_cast<const float*>(a.m.pmean)[row];
+      aux2 = a.m.dtype == 2 ? reinterpret_cast<const double*>(a.m.pstd)[row] : (double)reinterpret_cast<const float*>(a.m.pstd)[row];
+    }
     const char* rowp = reinterpret_cast<const char*>(a.m.rows) + (int64_t)row * a.m.d * dtype_size(a.m.dtype);
     double sim;
     if (a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) {
@@ -349,7 +383,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
       }
       sim = a.metric == HDB_HAMMING ? (double)((int)a.m.d - diff) : __ddiv_rn((double)inter, (double)uni);
     } else {
-      sim = canonical_similarity_rt(ca, a.rdt, rowp, bitrow, nrm);
+      sim = canonical_similarity_rt(ca, a.rdt, rowp, bitrow, nrm, aux2);
     }
     c_tot[tid] = total_score(sim, a.f.decay, a.f.bias, row);
     c_row[tid] = row;
@@ -378,7 +412,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
         const double t0 = (double)a.tau0[b];
         s_edge = a.tau0_negd2 ? 1.0 / (1.0 + sqrt(t0 < 0.0 ? -t0 : 0.0)) : t0;
       }
-      const double bound = outsider_bound(s_edge, a, a.qb.qnorm[b]);
+      const double bound = outsider_bound(s_edge, a, a.qb.qnorm[b], a.qb.qaux ? a.qb.qaux[2 * b] : 1.0);
       certified = o_tot[kk - 1] > bound;
     }
   }
@@ -425,10 +459,12 @@ __device__ __forceinline__ bool kept_row(const RowFilter& f, int64_t row) {
   return true;
 }
 
-__device__ __forceinline__ CanonArgs canon_args(const MatrixView& m, int metric, const double* qc, const uint32_t* qbits) {
+__device__ __forceinline__ CanonArgs canon_args(const MatrixView& m, int metric, const double* qc, const uint32_t* qbits,
+                                                const double* qaux) {
   CanonArgs ca;
   ca.sdt = m.dtype; ca.d = m.d; ca.qc = qc;
   ca.qbits = qbits; ca.words = m.words; ca.metric = metric;
+  ca.qstd = qaux ? qaux[0] : 1.0;
   return ca;
 }
 
@@ -436,48 +472,53 @@ __device__ __forceinline__ double row_canonical(const MatrixView& m, CanonArgs& 
   double nrm = 1.0;
   if (ca.metric == HDB_COSINE)
     nrm = m.dtype == 2 ? reinterpret_cast<const double*>(m.norms)[row] : (double)reinterpret_cast<const float*>(m.norms)[row];
+  double aux2 = 0.0;
+  if (ca.metric == HDB_PEARSON) {
+    nrm = m.dtype == 2 ? reinterpret_cast<const double*>(m.pmean)[row] : (double)reinterpret_cast<const float*>(m.pmean)[row];
+    aux2 = m.dtype == 2 ? reinterpret_cast<const double*>(m.pstd)[row] : (double)reinterpret_cast<const float*>(m.pstd)[row];
+  }
   const void* rowp = reinterpret_cast<const char*>(m.rows) + row * m.d * dtype_size(m.dtype);
   const uint32_t* bitrow = m.bits ? m.bits + row * (int64_t)m.words : nullptr;
-  return canonical_similarity_rt(ca, rdt, rowp, bitrow, nrm);
+  return canonical_similarity_rt(ca, rdt, rowp, bitrow, nrm, aux2);
 }
 
 __global__ void full_scores_kernel(MatrixView m, RowFilter f, int metric, int rdt, const double* qc,
-                                   const uint32_t* qbits, double* totals) {
+                                   const uint32_t* qbits, const double* qaux, double* totals) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= m.n) return;
   if (!kept_row(f, row)) { totals[row] = __longlong_as_double(-1ll); return; }   // -NaN sorts last (descending)
-  CanonArgs ca = canon_args(m, metric, qc, qbits);
+  CanonArgs ca = canon_args(m, metric, qc, qbits, qaux);
   totals[row] = total_score(row_canonical(m, ca, rdt, row), f.decay, f.bias, row);
 }
 
 int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,
-                       const uint32_t* qbits, double* totals, cudaStream_t s) {
+                       const uint32_t* qbits, const double* qaux, double* totals, cudaStream_t s) {
   if (m.n == 0) return 0;
   int64_t blocks = (m.n + 127) / 128;
-  full_scores_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, f, metric, rdt, qc, qbits, totals);
+  full_scores_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, f, metric, rdt, qc, qbits, qaux, totals);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;
 }
 
 // the metric function's own output: dtype R (uint64 for hamming)
-__global__ void scores_out_kernel(MatrixView m, int metric, int rdt, const double* qc, const uint32_t* qbits, void* out) {
+__global__ void scores_out_kernel(MatrixView m, int metric, int rdt, const double* qc, const uint32_t* qbits, const double* qaux, void* out) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= m.n) return;
-  CanonArgs ca = canon_args(m, metric, qc, qbits);
+  CanonArgs ca = canon_args(m, metric, qc, qbits, qaux);
   const double v = row_canonical(m, ca, rdt, row);
   if (metric == HDB_HAMMING) reinterpret_cast<unsigned long long*>(out)[row] = (unsigned long long)(long long)v;
-  else if (metric == HDB_JACCARD) reinterpret_cast<double*>(out)[row] = v;
+  else if (metric == HDB_JACCARD || metric == HDB_PEARSON) reinterpret_cast<double*>(out)[row] = v;      // np.zeros(N) receives the quotients
   else if (rdt == 0) reinterpret_cast<__half*>(out)[row] = __float2half_rn((float)v);
   else if (rdt == 1) reinterpret_cast<float*>(out)[row] = (float)v;
   else reinterpret_cast<double*>(out)[row] = v;
 }
 
-int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits, void* out,
+int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits, const double* qaux, void* out,
                       cudaStream_t s) {
   if (m.n == 0) return 0;
   int64_t blocks = (m.n + 127) / 128;
-  scores_out_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, metric, rdt, qc, qbits, out);
+  scores_out_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, metric, rdt, qc, qbits, qaux, out);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;

@@ -42,6 +42,7 @@ struct QueryBuffers {     // per-batch device buffers written by prep_query
   uint32_t* qbits;        // [B][words] sign bits
   double* qnorm;          // [B] ||qc||_2
   uint32_t* qflags;       // [B] HDB_FLAG_QUERY_NAN
+  double* qaux;           // [B][2] pearson: np.std(q), sum_j (q_j - np.mean(q))
 };
 
 struct MatrixView {
@@ -56,12 +57,26 @@ struct MatrixView {
   int words;              // words per packed row
   float max_norm;         // max_i ||v_i||_2
   float max_ratio;        // max_i ||v_i||_2 / canonical norm_i
+  // pearson columns (built on the first pearson query): np.mean / np.std per row in the storage dtype's carrier
+  // (float for f16/f32, double for f64), and 1/(std*d) in the sweep's accumulate type (NaN for a constant row)
+  const void* pmean;
+  const void* pstd;
+  const void* pscale;
+  float max_pratio;       // max_i ||v_i||_2 / (std_i * sqrt(d)) over non-constant rows (certificate: the sweep's error scale)
+  float max_cratio;       // max_i ||v_i - mean_i||_2 / (std_i * sqrt(d)), ~1 (certificate: the reference's error scale)
+  float min_pstd;         // min_i std_i over non-constant rows
 };
 
 // ---- ingest.cu
 int launch_row_stats(const MatrixView& m, void* norms, void* inv_norms, float* sqnorms, float* d_stats /*[2] max_norm,max_ratio*/,
                      int* d_nan, cudaStream_t s);
 int launch_pack_bits(const MatrixView& m, uint32_t* bits, int words, cudaStream_t s);
+int launch_pearson_stats(const MatrixView& m, void* pmean, void* pstd, void* pscale, float* d_stats /*[3] max_pratio, -min_pstd (ordered), max_cratio*/,
+                         cudaStream_t s);
+int launch_plan_removal(int64_t n, const int64_t* d_rows, int64_t count, uint32_t* keep /*[n]*/, uint32_t* pos /*[n]*/, uint32_t* src /*[n]*/,
+                        unsigned long long* d_n_new, int* d_err, void** scan_tmp, size_t* scan_tmp_bytes, cudaStream_t s);
+int launch_compact_column(void* column, int64_t row_bytes, int64_t n_new, const uint32_t* src, void* bounce, size_t bounce_bytes,
+                          cudaStream_t s);
 int launch_kept_ts_max(const double* ts, const RowFilter& f, int64_t n, unsigned long long* d_max_bits,
                        unsigned long long* d_count, cudaStream_t s);
 int launch_decay(const double* ts, double* decay, int64_t n, double ts_max, cudaStream_t s);
@@ -78,8 +93,8 @@ struct SweepOut {
   int grid;
 };
 int sweep_grid_size(int device);
-int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const RowFilter& f, int kp,
-                 const SweepOut& out, cudaStream_t s);
+int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const double* qaux /*pearson, this query*/,
+                 const RowFilter& f, int kp, const SweepOut& out, cudaStream_t s);
 
 // ---- finalize.cu : merge + canonical re-score + certification; exact full-vector path
 struct FinalizeArgs {
@@ -104,9 +119,9 @@ struct FinalizeArgs {
 };
 int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s);
 int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,
-                       const uint32_t* qbits, double* totals /*[n], masked rows = -NaN*/, cudaStream_t s);
-int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits,
-                      void* out /*dtype R or uint64*/, cudaStream_t s);
+                       const uint32_t* qbits, const double* qaux, double* totals /*[n], masked rows = -NaN*/, cudaStream_t s);
+int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits, const double* qaux,
+                      void* out /*dtype R, uint64 (hamming) or float64 (jaccard, pearson)*/, cudaStream_t s);
 int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
                int64_t* out_idx, double* out_score, int64_t* out_count, void** scratch, size_t* scratch_bytes,
                cudaStream_t s);

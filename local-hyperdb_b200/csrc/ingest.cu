@@ -7,6 +7,8 @@
 //  kept_ts_max / decay / stage1    the time-decay column of :179-183 and hyperdb.py:1334-1346.
 //  prep_query    canonical query (unit query for cosine, normalised in the QUERY's dtype, :38),
 //                accumulate-type copy for the sweep, sign bits, ||q||, NaN flag.
+#include <cub/device/device_scan.cuh>
+
 #include "canonical.cuh"
 #include "hdb_internal.h"
 #include "../../include/hyperdb_b200.h"
@@ -78,6 +80,71 @@ int launch_row_stats(const MatrixView& m, void* norms, void* inv_norms, float* s
   if (m.dtype == 0) row_stats_kernel<0><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, sqnorms, d_stats, d_nan);
   else if (m.dtype == 1) row_stats_kernel<1><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, sqnorms, d_stats, d_nan);
   else row_stats_kernel<2><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, norms, inv_norms, sqnorms, d_stats, d_nan);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pearson_correlation's per-row statistics (hyperdb/ranking_algorithm.py:91,94: np.mean / np.std along axis 1), computed
+// once per matrix in NumPy's arithmetic instead of once per query; plus the sweep's scale 1/(std*d) and the two
+// statistics of the certificate.  Thread per row (one-off pass).
+template <int T>
+__global__ void pearson_stats_kernel(const void* rows, int64_t n, int64_t d, void* pmean, void* pstd, void* pscale, float* stats) {
+  using A = Arith<T>;
+  using C = typename A::C;
+  int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float my_ratio = 0.f, my_cratio = 0.f, my_negstd = -3.0e38f;
+  if (row < n) {
+    const char* base = reinterpret_cast<const char*>(rows) + row * d * dtype_size(T);
+    C mean, sd;
+    canonical_mean_std<T>(base, d, false, &mean, &sd);
+    double true_sq = 0.0, cen_sq = 0.0;
+    for (int64_t j = 0; j < d; ++j) {
+      const double v = load_as_double(base, T, j);
+      true_sq += v * v;
+      cen_sq += (v - (double)mean) * (v - (double)mean);
+    }
+    const double scale = (sd == C(0)) ? __longlong_as_double(0x7ff8000000000000ll) : 1.0 / ((double)sd * (double)d);
+    if (T == 2) {
+      reinterpret_cast<double*>(pmean)[row] = (double)mean;
+      reinterpret_cast<double*>(pstd)[row] = (double)sd;
+      reinterpret_cast<double*>(pscale)[row] = scale;
+    } else {
+      reinterpret_cast<float*>(pmean)[row] = (float)mean;
+      reinterpret_cast<float*>(pstd)[row] = (float)sd;
+      reinterpret_cast<float*>(pscale)[row] = (float)scale;
+    }
+    if (sd != C(0) && sd == sd) {
+      const double ratio = sqrt(true_sq) / ((double)sd * sqrt((double)d));
+      my_ratio = (ratio == ratio) ? (float)fmin(ratio * (1.0 + 1e-6), 3.0e38) : 3.0e38f;
+      const double cratio = sqrt(cen_sq) / ((double)sd * sqrt((double)d));
+      my_cratio = (cratio == cratio) ? (float)fmin(cratio * (1.0 + 1e-6), 3.0e38) : 3.0e38f;
+      my_negstd = -(float)((double)sd * (1.0 - 1e-6));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    my_ratio = fmaxf(my_ratio, __shfl_xor_sync(kFull, my_ratio, o));
+    my_cratio = fmaxf(my_cratio, __shfl_xor_sync(kFull, my_cratio, o));
+    my_negstd = fmaxf(my_negstd, __shfl_xor_sync(kFull, my_negstd, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<int*>(stats), __float_as_int(my_ratio));                 // non-negative: bit order = value order
+    atomicMin(reinterpret_cast<unsigned*>(stats) + 1, __float_as_uint(my_negstd));      // non-positive: larger value = smaller bits
+    atomicMax(reinterpret_cast<int*>(stats) + 2, __float_as_int(my_cratio));
+  }
+}
+
+// d_stats[0], [2] start at the running maxima (0 at first), d_stats[1] at the bits of the running -min std (0xffffffff at first)
+int launch_pearson_stats(const MatrixView& m, void* pmean, void* pstd, void* pscale, float* d_stats, cudaStream_t s) {
+  if (m.n == 0) return 0;
+  int threads = 128;
+  int64_t blocks = (m.n + threads - 1) / threads;
+  if (blocks > 0x7fffffff) return fail("pearson_stats: too many rows");
+  if (m.dtype == 0) pearson_stats_kernel<0><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, pmean, pstd, pscale, d_stats);
+  else if (m.dtype == 1) pearson_stats_kernel<1><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, pmean, pstd, pscale, d_stats);
+  else pearson_stats_kernel<2><<<(unsigned)blocks, threads, 0, s>>>(m.rows, m.n, m.d, pmean, pstd, pscale, d_stats);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;
@@ -212,6 +279,36 @@ __device__ double query_unit_norm(const void* q, int64_t d, void* s_sq, int tid,
   return s_result;
 }
 
+// np.mean(q) / np.std(q) of the query in ITS dtype (hyperdb/ranking_algorithm.py:90,93; q is 1-D, so np.mean takes the
+// scalar branch).  Staged: values and squared deviations in shared memory, pairwise sums by warp 0.
+template <int QDT>
+__device__ void query_mean_std(const void* q, int64_t d, void* s_buf, int tid, int nthreads, bool staged, double* mean_out,
+                               double* std_out) {
+  using A = Arith<QDT>;
+  using C = typename A::C;
+  __shared__ double s_ms[2];
+  __shared__ PwScratch s_pw2;
+  if (staged) {
+    C* x = reinterpret_cast<C*>(s_buf);
+    for (int64_t j = tid; j < d; j += nthreads) x[j] = A::from_double(load_as_double(q, QDT, j));
+    __syncthreads();
+    if (tid < 32) {
+      C mean, sd;
+      mean_std_core<QDT>([&](int j) { return x[j]; }, (int)d, true,
+                         [&](auto term) { return pairwise_sum_warp<1>(term, (int)d, tid, &s_pw2); },
+                         [&](auto term) { return pairwise_sum_warp<QDT>(term, (int)d, tid, &s_pw2); }, &mean, &sd);
+      if (tid == 0) { s_ms[0] = (double)mean; s_ms[1] = (double)sd; }
+    }
+  } else if (tid == 0) {
+    C mean, sd;
+    canonical_mean_std<QDT>(q, d, true, &mean, &sd);
+    s_ms[0] = (double)mean; s_ms[1] = (double)sd;
+  }
+  __syncthreads();
+  *mean_out = s_ms[0];
+  *std_out = s_ms[1];
+}
+
 __global__ void prep_query_kernel(const void* queries, int qdt, int64_t d, int metric, int sdt, int words,
                                   QueryBuffers qb, int stage, unsigned long long* tau) {
   extern __shared__ __align__(16) unsigned char s_query[];
@@ -229,18 +326,25 @@ __global__ void prep_query_kernel(const void* queries, int qdt, int64_t d, int m
     else if (qdt == 1) nrm = query_unit_norm<1>(q, d, s_query, threadIdx.x, blockDim.x, stage);
     else nrm = query_unit_norm<2>(q, d, s_query, threadIdx.x, blockDim.x, stage);
   }
+  double qmean = 0.0, qstd = 1.0;
+  if (metric == HDB_PEARSON) {
+    if (qdt == 0) query_mean_std<0>(q, d, s_query, threadIdx.x, blockDim.x, stage, &qmean, &qstd);
+    else if (qdt == 1) query_mean_std<1>(q, d, s_query, threadIdx.x, blockDim.x, stage, &qmean, &qstd);
+    else query_mean_std<2>(q, d, s_query, threadIdx.x, blockDim.x, stage, &qmean, &qstd);
+  }
   __syncthreads();
   const bool acc_f64 = (sdt == 2);
-  double sq = 0.0;
+  double sq = 0.0, sb = 0.0;
   bool bad = false;
   for (int64_t j = threadIdx.x; j < d; j += blockDim.x) {
     double v = load_as_double(q, qdt, j);
     bad |= (v != v);
-    double c = (metric == HDB_COSINE) ? unit_elem(v, nrm, qdt) : v;
+    double c = (metric == HDB_COSINE) ? unit_elem(v, nrm, qdt) : (metric == HDB_PEARSON ? sub_in(v, qmean, qdt) : v);
     qb.qc[b * d + j] = c;
     if (acc_f64) reinterpret_cast<double*>(qb.qa)[b * d + j] = c;
     else reinterpret_cast<float*>(qb.qa)[b * d + j] = (float)c;
     sq += c * c;
+    sb += acc_f64 ? c : (double)(float)c;          // the sweep's own view of sum_j (q_j - mean)
   }
   if (qb.qbits) {       // sign bits: one coalesced 32-element read + ballot per word
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -252,24 +356,117 @@ __global__ void prep_query_kernel(const void* queries, int qdt, int64_t d, int m
     }
   }
   sq = warp_sum(sq);
+  sb = warp_sum(sb);
   if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicOr(&s_nan, 1);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = sq; s_red[16 + (threadIdx.x >> 5)] = sb; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double tot = 0;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += s_red[w];
-    qb.qnorm[b] = sqrt(tot);
+    double tot = 0, tot_b = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { tot += s_red[w]; tot_b += s_red[16 + w]; }
+    // pearson: ||q - mean||_2 / (std_q sqrt(d)) -- the query's factor of the certificate's magnitude bound
+    qb.qnorm[b] = (metric == HDB_PEARSON) ? sqrt(tot) / (qstd * sqrt((double)d)) : sqrt(tot);
     qb.qflags[b] = s_nan ? HDB_FLAG_QUERY_NAN : 0u;
+    if (qb.qaux) { qb.qaux[2 * b] = qstd; qb.qaux[2 * b + 1] = tot_b; }
   }
 }
 
 int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int metric, int sdt, int words,
                       const QueryBuffers& qb, unsigned long long* tau, cudaStream_t s) {
   if (nq == 0) return 0;
-  const size_t bytes = (size_t)d * (q_dtype == 2 ? 8 : 4);          // squares in the carrier type
+  const size_t bytes = (size_t)d * (q_dtype == 2 ? 8 : 4);          // squares (cosine) / values (pearson) in the carrier type
   const int stage = bytes <= 40 * 1024;
   prep_query_kernel<<<(unsigned)nq, 128, stage ? bytes : 0, s>>>(q, q_dtype, d, metric, sdt, words, qb, stage, tau);
   HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row removal (hyperdb/hyperdb.py:718-728: np.vstack / boolean-mask copy of the whole matrix per remove_document):
+// stable in-place compaction of the matrix and of every per-row column.
+//   mark_removed:  keep[i] = 0 for every listed row          (keep[] starts as all ones)
+//   exclusive scan of keep[] -> destination of every kept row; build_src_index inverts it: src[dest] = row
+//   gather_rows:   bounce[j - j0] = column[src[j]] for one chunk of destinations [j0, j0+cnt); the caller then copies
+//                  the bounce buffer to column[j0 ...].  src[j] >= j, so a chunk only overwrites rows that later
+//                  chunks never read.
+__global__ void mark_removed_kernel(uint32_t* keep, int64_t n, const int64_t* rows, int64_t count, int* err) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = rows[i];
+    if (r < 0 || r >= n) atomicOr(err, 1);
+    else keep[r] = 0u;                                   // duplicates write the same value
+  }
+}
+__global__ void fill_u32_kernel(uint32_t* p, int64_t n, uint32_t v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void build_src_index_kernel(const uint32_t* keep, const uint32_t* pos, int64_t n, uint32_t* src, unsigned long long* n_new) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (keep[i]) src[pos[i]] = (uint32_t)i;
+    if (i == n - 1) *n_new = (unsigned long long)pos[i] + keep[i];
+  }
+}
+// One warp per destination row; VEC = 16-byte pieces, otherwise 2-byte pieces (every stored dtype is >= 2 bytes wide).
+template <bool VEC>
+__global__ void gather_rows_kernel(const char* col, char* bounce, int64_t row_bytes, const uint32_t* src, int64_t j0, int64_t cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < cnt; j += nwarps) {
+    const char* from = col + (int64_t)src[j0 + j] * row_bytes;
+    char* to = bounce + j * row_bytes;
+    if (VEC) {
+      for (int64_t c = lane; c < row_bytes / 16; c += 32) reinterpret_cast<uint4*>(to)[c] = reinterpret_cast<const uint4*>(from)[c];
+    } else {
+      for (int64_t c = lane; c < row_bytes / 2; c += 32) reinterpret_cast<uint16_t*>(to)[c] = reinterpret_cast<const uint16_t*>(from)[c];
+    }
+  }
+}
+
+int launch_plan_removal(int64_t n, const int64_t* d_rows, int64_t count, uint32_t* keep, uint32_t* pos, uint32_t* src,
+                        unsigned long long* d_n_new, int* d_err, void** scan_tmp, size_t* scan_tmp_bytes, cudaStream_t s) {
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fill_u32_kernel<<<(unsigned)blocks, 256, 0, s>>>(keep, n, 1u);
+  HDB_LAUNCHED();
+  if (count > 0) {
+    int64_t b2 = (count + 255) / 256;
+    if (b2 > 148 * 16) b2 = 148 * 16;
+    mark_removed_kernel<<<(unsigned)b2, 256, 0, s>>>(keep, n, d_rows, count, d_err);
+    HDB_LAUNCHED();
+  }
+  size_t need = 0;
+  HDB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, keep, pos, (int)n, s));
+  if (*scan_tmp_bytes < need) {
+    if (*scan_tmp) HDB_CUDA(cudaFree(*scan_tmp));
+    *scan_tmp = nullptr; *scan_tmp_bytes = 0;
+    HDB_CUDA(cudaMalloc(scan_tmp, need));
+    *scan_tmp_bytes = need;
+  }
+  HDB_CUDA(cub::DeviceScan::ExclusiveSum(*scan_tmp, need, keep, pos, (int)n, s));
+  HDB_LAUNCHED();
+  build_src_index_kernel<<<(unsigned)blocks, 256, 0, s>>>(keep, pos, n, src, d_n_new);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Compacts one per-row column in place: column[j] = column[src[j]] for j in [0, n_new), chunk by chunk through `bounce`.
+int launch_compact_column(void* column, int64_t row_bytes, int64_t n_new, const uint32_t* src, void* bounce, size_t bounce_bytes,
+                          cudaStream_t s) {
+  if (!column || n_new == 0 || row_bytes == 0) return 0;
+  int64_t chunk = (int64_t)(bounce_bytes / (size_t)row_bytes);
+  if (chunk < 1) return fail("compact: bounce buffer smaller than one row");
+  const bool vec = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(column) & 15) == 0) && ((reinterpret_cast<uintptr_t>(bounce) & 15) == 0);
+  for (int64_t j0 = 0; j0 < n_new; j0 += chunk) {
+    const int64_t cnt = n_new - j0 < chunk ? n_new - j0 : chunk;
+    int64_t blocks = (cnt * 32 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (vec) gather_rows_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const char*>(column), reinterpret_cast<char*>(bounce), row_bytes, src, j0, cnt);
+    else gather_rows_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const char*>(column), reinterpret_cast<char*>(bounce), row_bytes, src, j0, cnt);
+    HDB_LAUNCHED();
+    HDB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(column) + j0 * row_bytes, bounce, (size_t)(cnt * row_bytes), cudaMemcpyDeviceToDevice, s));
+  }
   HDB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -28,7 +28,9 @@ struct SweepParams {
   int64_t row_bytes;
   int nvec;                 // 16-byte vectors per row (vector path) or elements per row (scalar path)
   const void* qa;           // query in the accumulate type (global)
-  const void* inv_norms;    // accumulate type, or nullptr (not cosine)
+  const void* inv_norms;    // accumulate type, or nullptr (not cosine / pearson); pearson: 1/(std*d)
+  const void* row_means;    // pearson: np.mean per row (accumulate type), else nullptr
+  const double* qaux;       // pearson: {np.std(q), sum_j (q_j - mean)} of this query, else nullptr
   RowFilter f;
   uint64_t* cand;
   unsigned long long* tau;
@@ -213,6 +215,13 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
   const int my_row = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const bool rep = (lane & 3) == 0;
   const Acc* inv = reinterpret_cast<const Acc*>(p.inv_norms);
+  // pearson (MC == 0 only): sum_j (v_j - mean_v) b_j = v.b - mean_v * sum(b), then / (std_v * d) / std_q
+  const Acc* pmeans = reinterpret_cast<const Acc*>(p.row_means);
+  Acc q_sumb = Acc(0), q_scale = Acc(1);
+  if (MC == 0 && p.qaux) {
+    q_sumb = (Acc)p.qaux[1];
+    q_scale = (p.qaux[0] == 0.0) ? (Acc)__longlong_as_double(0x7ff8000000000000ll) : (Acc)(1.0 / p.qaux[0]);
+  }
   int since_refresh = 0;
   const int64_t g0 = (int64_t)blockIdx.x * kSweepWarps + warp;
   uint32_t next_bits = (g0 < nwin) ? window_keep_bits(p.f, g0, p.n) : 0u;
@@ -250,10 +259,11 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
       // per-row side inputs, issued before the streaming loop so their latency is hidden
       const bool mine_kept = (keep >> my_row) & 1u;
       const int64_t mrow = row0 + my_off;
-      Acc my_inv = Acc(1);
+      Acc my_inv = Acc(1), my_mean = Acc(0);
       double my_decay = 0.0;
       if (rep && mine_kept) {
         if (inv) my_inv = inv[mrow];
+        if (MC == 0 && pmeans) my_mean = pmeans[mrow];
         if (p.f.decay) my_decay = p.f.decay[mrow];
       }
 
@@ -290,6 +300,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
       // epilogue: similarity, decay, key
       float score;
       if (MC == 0) {
+        if (pmeans) total = (total - my_mean * q_sumb) * q_scale;
         total = total * my_inv;
         if (p.f.decay) score = (float)((double)total + p.f.bias * my_decay);
         else score = (float)total;
@@ -593,7 +604,7 @@ static int launch_mc(const SweepParams& p, bool vec, int mc, int kp, int grid, s
   return launch_kp<T, 2>(p, vec, kp, grid, smem, s);
 }
 
-int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const RowFilter& f, int kp,
+int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const double* qaux, const RowFilter& f, int kp,
                  const SweepOut& out, cudaStream_t s) {
   if (m.n >= (int64_t(1) << 32)) return fail("sweep: more than 2^32 rows per shard");
   if (kp != 32 && kp != 128) return fail("sweep: unsupported candidate class");
@@ -627,9 +638,12 @@ int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t
   const bool vec = (p.row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(m.rows) & 15) == 0);
   p.nvec = vec ? (int)(p.row_bytes / 16) : (int)m.d;
   p.qa = qa;
-  p.inv_norms = (metric == HDB_COSINE) ? m.inv_norms : nullptr;
+  p.inv_norms = (metric == HDB_COSINE) ? m.inv_norms : (metric == HDB_PEARSON ? m.pscale : nullptr);
+  p.row_means = (metric == HDB_PEARSON) ? m.pmean : nullptr;
+  p.qaux = (metric == HDB_PEARSON) ? qaux : nullptr;
+  if (metric == HDB_PEARSON && (!m.pscale || !m.pmean || !qaux)) return fail("sweep: pearson columns missing");
   p.f = f; p.cand = out.cand; p.tau = out.tau; p.metric = metric;
-  const int mc = (metric == HDB_DOT || metric == HDB_COSINE) ? 0 : (metric == HDB_EUCLIDEAN ? 1 : 2);
+  const int mc = (metric == HDB_DOT || metric == HDB_COSINE || metric == HDB_PEARSON) ? 0 : (metric == HDB_EUCLIDEAN ? 1 : 2);
   size_t smem = list_smem(kp) + (size_t)m.d * (m.dtype == 2 ? 8 : 4);
   if (smem > 200 * 1024) return fail("sweep: dimension too large for the fused pass");
   if (m.dtype == 0) return launch_mc<__half>(p, vec, mc, kp, out.grid, smem, s);

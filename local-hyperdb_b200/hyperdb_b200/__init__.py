@@ -18,10 +18,11 @@ from .ranking_algorithm import (  # noqa: F401
     hyperDB_ranking_algorithm_sort,
     jaccard_similarity,
     manhattan_distance,
+    pearson_correlation,
 )
 
 __all__ = [
     "DeviceMatrix", "ranking_algorithm", "cosine_similarity", "dot_product", "euclidean_metric",
-    "manhattan_distance", "hamming_distance", "jaccard_similarity", "get_norm_vector", "hyperDB_ranking_algorithm_sort",
+    "manhattan_distance", "hamming_distance", "jaccard_similarity", "pearson_correlation", "get_norm_vector", "hyperDB_ranking_algorithm_sort",
     "custom_ranking_algorithm_sort",
 ]

@@ -16,6 +16,7 @@ METRIC_IDS = {
     "manhattan_distance": 3,
     "hamming_distance": 4,
     "jaccard_similarity": 5,
+    "pearson_correlation": 6,
 }
 FLAG_FALLBACK, FLAG_QUERY_NAN, FLAG_TENSOR, FLAG_UNCERTIFIED = 1, 2, 4, 8
 
@@ -34,6 +35,10 @@ SIGNATURES = {
     "hdb_matrix_upload": (C.c_int, [vp, i64, i64, vp, C.c_int]),
     "hdb_matrix_adopt": (C.c_int, [vp, vp]),
     "hdb_matrix_finalize": (C.c_int, [vp]),
+    "hdb_matrix_reserve": (C.c_int, [vp, i64]),
+    "hdb_matrix_append": (C.c_int, [vp, i64, vp, C.c_int]),
+    "hdb_matrix_remove_rows": (C.c_int, [vp, vp, i64, C.c_int]),
+    "hdb_matrix_set_row_offset": (C.c_int, [vp, i64]),
     "hdb_matrix_set_stream": (C.c_int, [vp, vp]),
     "hdb_matrix_set_post_stream": (C.c_int, [vp, vp]),
     "hdb_matrix_info": (C.c_int, [vp, C.POINTER(C.c_int), i64p, i64p, i64p, i64p]),

@@ -95,6 +95,47 @@ class DeviceMatrix:
     def __len__(self):
         return self.shape[0]
 
+    # -- mutation (hyperdb/hyperdb.py:504-509 add, :718-728 remove_document) ---------------------------
+    def reserve(self, capacity_rows):
+        N.check(N.lib().hdb_matrix_reserve(self._h, int(capacity_rows)))
+
+    def append(self, rows):
+        """Append rows (NumPy array or CUDA tensor of the stored dtype; other float dtypes are cast as
+        `np.concatenate` would not: the stored dtype wins).  Resets mask / range / timestamps."""
+        if self._keep is not None:
+            raise ValueError("cannot append to a DeviceMatrix that adopted a CUDA tensor")
+        if _is_torch(rows):
+            import torch
+            t = rows.contiguous().to({np.dtype(np.float16): torch.float16, np.dtype(np.float32): torch.float32,
+                                      np.dtype(np.float64): torch.float64}[self.np_dtype])
+            if t.dim() != 2 or t.shape[1] != self.shape[1]:
+                raise ValueError("appended rows must be (m, d)")
+            p, space = _ptr(t)
+            cnt = int(t.shape[0])
+        else:
+            a = np.ascontiguousarray(np.asarray(rows), dtype=self.np_dtype)
+            if a.ndim != 2 or a.shape[1] != self.shape[1]:
+                raise ValueError("appended rows must be (m, d)")
+            p, space, cnt = C.c_void_p(a.ctypes.data), N.HDB_HOST, a.shape[0]
+        N.check(N.lib().hdb_matrix_append(self._h, cnt, p, space))
+        self.shape = (self.shape[0] + cnt, self.shape[1])
+        self._has_ts = False
+
+    def remove_rows(self, local_rows):
+        """Remove the listed local rows; survivors keep their order (stable device-side compaction)."""
+        if self._keep is not None:
+            raise ValueError("cannot remove rows of a DeviceMatrix that adopted a CUDA tensor")
+        idx = np.ascontiguousarray(np.atleast_1d(np.asarray(local_rows)), dtype=np.int64)
+        idx = np.where(idx < 0, idx + self.shape[0], idx)
+        N.check(N.lib().hdb_matrix_remove_rows(self._h, C.c_void_p(idx.ctypes.data), len(idx), N.HDB_HOST))
+        out = C.c_int64()
+        N.check(N.lib().hdb_matrix_info(self._h, None, C.byref(out), None, None, None))
+        self.shape = (int(out.value), self.shape[1])
+
+    def set_row_offset(self, row_offset):
+        N.check(N.lib().hdb_matrix_set_row_offset(self._h, int(row_offset)))
+        self.row_offset = int(row_offset)
+
     # -- row subset (the filters' output) ------------------------------------------------------
     def set_mask(self, keep):
         """keep: bool[n] (True = row takes part), packed uint32 bits, CUDA tensor of packed bits, or None."""
@@ -221,7 +262,7 @@ class DeviceMatrix:
         if q.shape[0] != self.shape[1]:
             raise ValueError(f"operands could not be broadcast together with shapes {self.shape} {q.shape}")
         rdt = np.promote_types(self.np_dtype, q.dtype)
-        out = np.empty(self.shape[0], np.uint64 if metric == "hamming_distance" else (np.float64 if metric == "jaccard_similarity" else rdt))
+        out = np.empty(self.shape[0], np.uint64 if metric == "hamming_distance" else (np.float64 if metric in ("jaccard_similarity", "pearson_correlation") else rdt))
         got = C.c_int()
         N.check(N.lib().hdb_scores(self._h, mid, C.c_void_p(q.ctypes.data), _NP2HDB[q.dtype], N.HDB_HOST,
                                    C.c_void_p(out.ctypes.data), N.HDB_HOST, C.byref(got)))

@@ -25,8 +25,6 @@ from .device_matrix import DeviceMatrix
 
 _METRICS = ['dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_distance', 'jaccard_similarity',
             'pearson_correlation', 'hamming_distance']
-_ON_DEVICE = ('dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_distance', 'hamming_distance',
-              'jaccard_similarity')
 
 
 def _nested(document, dotted):
@@ -74,7 +72,8 @@ class HyperDB:
         self._mask_cache.clear()
 
     def add(self, documents, vectors=None, add_timestamp=False):
-        """hyperdb/hyperdb.py:496-545, :626-689 reduced to: embed (if needed), cast to fp_precision, append, re-upload."""
+        """hyperdb/hyperdb.py:496-545, :626-689 reduced to: embed (if needed), cast to fp_precision, append on the device
+        (hdb_matrix_append: only the new rows are uploaded and ingested)."""
         documents = [documents] if isinstance(documents, (dict, str)) else list(documents)
         if add_timestamp or self.add_timestamp:
             now = time.time()
@@ -87,11 +86,21 @@ class HyperDB:
         vectors = np.asarray(vectors, dtype=self.fp_precision)
         if vectors.ndim != 2 or len(vectors) != len(documents):
             raise ValueError("one vector per document expected")
+        if self.vectors is None or self._matrix is None:
+            previous, self.vectors = self.vectors, vectors
+            try:
+                self._upload()                               # raises ValueError on NaN
+            except Exception:
+                self.vectors = previous
+                raise
+        else:
+            vectors = vectors.astype(self.vectors.dtype)
+            self._matrix.append(vectors)                     # device side: only the new rows are copied and ingested
+            self.vectors = np.concatenate([self.vectors, vectors])
+            self._mask_cache.clear()
         base = len(self.documents)
         self.documents.extend(documents)
         self.source_indices.extend(range(base, base + len(documents)))
-        self.vectors = vectors if self.vectors is None else np.concatenate([self.vectors, vectors.astype(self.vectors.dtype)])
-        self._upload()
 
     def remove_document(self, index):
         """hyperdb/hyperdb.py:691-766 for one-row-per-document stores."""
@@ -100,7 +109,11 @@ class HyperDB:
         self.documents = [d for d, k in zip(self.documents, keep) if k]
         self.vectors = self.vectors[keep]
         self.source_indices = list(range(len(self.documents)))
-        self._upload()
+        if self._matrix is not None and len(self.vectors):
+            self._matrix.remove_rows(np.flatnonzero(~keep))  # stable compaction on the device, no re-upload
+            self._mask_cache.clear()
+        else:
+            self._upload()
 
     def size(self):
         return len(self.documents)
@@ -179,8 +192,6 @@ class HyperDB:
             raise Exception("The database is empty. Cannot proceed with the query.")
         if metric not in _METRICS:
             raise ValueError(f"Invalid metric '{metric}'. Supported: 'dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_distance', 'jaccard_similarity', 'pearson_correlation', 'hamming_distance'")
-        if metric not in _ON_DEVICE:
-            raise NotImplementedError(f"metric {metric} is outside the B200 hot path (SURVEY.md section 8f)")
         try:
             q = self._query_vector(query_input)
             lo, hi, keep = self._apply_filters(filters)

@@ -111,9 +111,14 @@ def jaccard_similarity(vectors, query_vector):
     return _scores(vectors, query_vector, "jaccard_similarity")
 
 
+def pearson_correlation(vectors, query_vector):
+    """hyperdb/ranking_algorithm.py:78-113 -- sum((v - mean_v)(q - mean_q)) / (std_v * std_q * D) with np.mean / np.std in
+    each operand's own dtype; float64 output; NaN when either side is constant."""
+    return _scores(vectors, np.asarray(query_vector).flatten(), "pearson_correlation")
+
+
 _SUPPORTED = ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance",
-              "jaccard_similarity")
-_REFERENCE_ONLY = ("pearson_correlation",)      # not on the B200 path yet
+              "jaccard_similarity", "pearson_correlation")
 
 
 def hyperDB_ranking_algorithm_sort(vectors, query_vector, top_k=5, metric='cosine_similarity', timestamps=None,
@@ -130,8 +135,6 @@ def hyperDB_ranking_algorithm_sort(vectors, query_vector, top_k=5, metric='cosin
     if np.isnan(q).any():
         raise ValueError("Vectors and query_vector should not contain NaN values.")
     if metric not in _SUPPORTED:
-        if metric in _REFERENCE_ONLY:
-            raise NotImplementedError(f"metric {metric} is outside the B200 hot path (SURVEY.md section 8f)")
         if np.isnan(v).any():
             raise ValueError("Vectors and query_vector should not contain NaN values.")
         raise ValueError(f"Unknown metric: {metric}")

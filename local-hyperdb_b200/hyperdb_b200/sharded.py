@@ -60,6 +60,22 @@ class CudaEngine:
     def n_kept(self):
         return self.m.n_kept
 
+    # mutation of the local shard (ShardedMatrix.append / remove_rows)
+    def n_rows(self):
+        return self.m.shape[0]
+
+    def row_offset(self):
+        return self.m.row_offset
+
+    def append(self, rows):
+        self.m.append(rows)
+
+    def remove_local(self, local_rows):
+        self.m.remove_rows(local_rows)
+
+    def set_row_offset(self, off):
+        self.m.set_row_offset(off)
+
     def local_topk(self, queries, k, metric, bias, exact=False):
         """-> packed int64 CUDA tensor [packed_len(B, k)] (scores bit-cast)."""
         torch = self.torch
@@ -133,6 +149,39 @@ class ShardedMatrix:
         if self.world > 1:
             self.dist.all_reduce(t, group=self.group)
         return int(t.item())
+
+    # -- mutation: rows stay contiguous per rank, global ids stay 0..n_total-1 ---------------------------------------
+    def _renumber(self):
+        """All-gather the local row counts and give every shard its new global offset (exclusive prefix sum)."""
+        import torch
+        counts = torch.zeros(self.world, dtype=torch.int64, device=self._comm_device())
+        counts[self.rank] = self.engine.n_rows()
+        if self.world > 1:
+            self.dist.all_reduce(counts, group=self.group)
+        counts = counts.cpu()
+        self.engine.set_row_offset(int(counts[: self.rank].sum()))
+        self.n_total = int(counts.sum())
+        return self.n_total
+
+    def append(self, rows):
+        """Collective.  New documents get the next global ids (hyperdb/hyperdb.py:504-509 appends at the end), so they
+        go to the LAST rank's shard; the other ranks pass `rows` too (ignored) or None.  Returns the new total."""
+        if self.rank == self.world - 1 and rows is not None and len(rows):
+            self.engine.append(rows)
+        return self._renumber()
+
+    def remove_rows(self, global_rows):
+        """Collective: every rank passes the same GLOBAL row ids (hyperdb/hyperdb.py:718-728); each removes the ones
+        it owns, survivors keep their order, and the shards are renumbered.  Returns the new total."""
+        import numpy as np
+        ids = np.unique(np.asarray(global_rows, dtype=np.int64))
+        if len(ids) and (ids[0] < 0 or ids[-1] >= self.n_total):
+            raise IndexError("row id out of range")
+        off, n = self.engine.row_offset(), self.engine.n_rows()
+        mine = ids[(ids >= off) & (ids < off + n)] - off
+        if len(mine):
+            self.engine.remove_local(mine)
+        return self._renumber()
 
     def query_async(self, queries, top_k, metric, recency_bias=0.0, exact=False):
         """Enqueue sweep -> all-gather -> merge; returns device tensors (idx, score, count, per-shard flags)."""

@@ -115,6 +115,54 @@ def _dot(v, q):
     return acc.astype(v.dtype)
 
 
+# ---------------------------------------------------------------------------------------------
+# pearson_correlation (hyperdb/ranking_algorithm.py:78-113): np.mean / np.std spelled out
+# ---------------------------------------------------------------------------------------------
+def _div_count(x, n, out_dtype):
+    """um.true_divide(x, np.intp(n)) as numpy._core._methods._mean/_var call it: the count is a NumPy integer
+    scalar, so the quotient is formed in float64 and cast to the output dtype (float32 sums first, for float16)."""
+    return (x.astype(np.float64) / np.float64(n)).astype(out_dtype)
+
+
+def row_mean(x, scalar=False):
+    """np.mean(x, axis=1): float16 is summed in float32, divided, cast to float32 and only then to float16.
+    scalar=True: np.mean of a 1-D array returns a NumPy scalar, whose float64 quotient is cast to float16 directly."""
+    n = x.shape[1]
+    if x.dtype == np.float16:
+        s32 = _pairwise(x.astype(np.float32))
+        return _div_count(s32, n, np.float16) if scalar else _div_count(s32, n, np.float32).astype(np.float16)
+    return _div_count(_pairwise(x), n, x.dtype)
+
+
+def row_std(x):
+    """np.std(x, axis=1): mean of the squared deviations from np.add.reduce(x)/n, everything in x.dtype."""
+    n = x.shape[1]
+    with np.errstate(over="ignore", under="ignore", invalid="ignore"):
+        arrmean = _div_count(row_sum(x), n, x.dtype)
+        dev = x - arrmean[:, None]
+        dev = dev * dev
+        return _sqrt(_div_count(row_sum(dev), n, x.dtype))
+
+
+def pearson(v, q):
+    """pearson_correlation with each NumPy call replaced by its arithmetic.  v: (N, D), q: (D,) float arrays in their
+    OWN dtypes (the statistics are taken before NumPy promotes).  Returns float64 (np.zeros(N) receives the quotients)."""
+    q = q.reshape(-1)
+    d = v.shape[1]
+    R = _F[np.dtype(np.promote_types(v.dtype, q.dtype))]
+    with np.errstate(over="ignore", under="ignore", invalid="ignore", divide="ignore"):
+        q_mean, v_mean = row_mean(q[None, :], scalar=True)[0], row_mean(v)
+        q_std, v_std = row_std(q[None, :])[0], row_std(v)
+        prod = (v - v_mean[:, None]).astype(R) * (q - q_mean).astype(R)
+        numerator = row_sum(prod)
+        denominator = (v_std.astype(R) * R(q_std)) * R(d)
+        out = np.zeros(v.shape[0])
+        ok = denominator != 0
+        out[ok] = numerator[ok] / denominator[ok]
+        out[(v_std == 0) | (q_std == 0)] = np.nan
+    return out
+
+
 def scores(vectors, query, metric):
     """Canonical similarity vector in the reference's result dtype (uint64 for hamming)."""
     v, q = _as_float(vectors), _as_float(query)
@@ -127,6 +175,8 @@ def scores(vectors, query, metric):
         union = np.sum(vb | qb[None, :], axis=1).astype(np.float64)
         with np.errstate(invalid="ignore", divide="ignore"):
             return inter / union
+    if metric == "pearson_correlation":
+        return pearson(v, q)
     R = _F[np.dtype(result_dtype(v, q))]
     if metric == "cosine_similarity":
         # each operand is normalised in ITS OWN dtype (ranking_algorithm.py:37-38); np.dot promotes after

@@ -24,6 +24,7 @@ METRICS = (
     "manhattan_distance",
     "hamming_distance",
     "jaccard_similarity",
+    "pearson_correlation",
 )
 
 
@@ -90,6 +91,23 @@ def jaccard_scores(vectors, query):
         return np.sum(np.bitwise_and(vb, qb), axis=1) / np.sum(np.bitwise_or(vb, qb), axis=1)
 
 
+def pearson_scores(vectors, query):
+    """hyperdb/ranking_algorithm.py:78-113 (pearson_correlation): covariance sum / (std_v * std_q * D) with np.mean / np.std
+    taken in each operand's own dtype; float64 output (np.zeros(N)); NaN when either side is constant, 0 where the
+    denominator underflowed to zero."""
+    vectors = np.asarray(vectors)
+    query = np.asarray(query).flatten()
+    q_mean, v_mean = np.mean(query), np.mean(vectors, axis=1)
+    q_std, v_std = np.std(query), np.std(vectors, axis=1)
+    numerator = np.sum((vectors - v_mean[:, np.newaxis]) * (query - q_mean), axis=1)
+    denominator = v_std * q_std * vectors.shape[1]
+    ok = denominator != 0
+    out = np.zeros(vectors.shape[0])
+    out[ok] = numerator[ok] / denominator[ok]
+    out[(q_std == 0) | (v_std == 0)] = np.nan          # `:108-111`: both constant, or exactly one of them
+    return out
+
+
 _DISPATCH = {
     "dot_product": dot_scores,
     "cosine_similarity": cosine_scores,
@@ -97,6 +115,7 @@ _DISPATCH = {
     "manhattan_distance": manhattan_scores,
     "hamming_distance": hamming_scores,
     "jaccard_similarity": jaccard_scores,
+    "pearson_correlation": pearson_scores,
 }
 
 

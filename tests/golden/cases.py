@@ -12,7 +12,7 @@ import itertools
 import numpy as np
 
 METRICS = ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance",
-           "jaccard_similarity")
+           "jaccard_similarity", "pearson_correlation")
 DT = {"f16": np.float16, "f32": np.float32, "f64": np.float64}
 
 
@@ -39,6 +39,13 @@ def make_inputs(case):
     elif kind == "coarse":                  # few distinct values -> many ties in every metric
         base = np.round(base * 2) / 2
         q = np.round(q * 2) / 2
+    elif kind == "shifted":                 # non-zero means, a constant row, a zero row (pearson: NaN -> ranked last)
+        base = base * rng.uniform(0.2, 2.0, (n, 1)).astype(np.float32) + rng.uniform(-3.0, 3.0, (n, 1)).astype(np.float32)
+        base[n // 4] = 0.75
+        base[n // 2] = 0
+        q = q * 0.5 + 1.25
+    elif kind == "constq":                  # constant query: every pearson score is NaN
+        q[:] = 0.5
     V = base.astype(DT[case["vdt"]])
     qv = q.astype(DT[case["qdt"]])
     ts = None
@@ -81,6 +88,12 @@ def sort_cases():
     # an all-non-positive row and query: empty union -> 0/0 -> NaN -> ranked last
     seed += 1
     cases.append(dict(seed=seed, n=60, d=9, vdt="f32", qdt="f32", kind="coarse", metric="jaccard_similarity", k=60, ts=False, bias=0.0))
+    # pearson on data with non-zero means / constant rows / a constant query, own and mixed dtypes
+    for (vdt, qdt), (n, d), kind in itertools.product((("f16", "f16"), ("f32", "f32"), ("f64", "f64"), ("f16", "f64"), ("f32", "f64")),
+                                                      ((120, 24), (90, 200)), ("shifted", "constq")):
+        seed += 1
+        cases.append(dict(seed=seed, n=n, d=d, vdt=vdt, qdt=qdt, kind=kind, metric="pearson_correlation", k=12,
+                          ts=(seed % 2 == 0), bias=0.2))
     for k in (0, -1, 50, 1000):
         seed += 1
         cases.append(dict(seed=seed, n=40, d=16, vdt="f32", qdt="f32", kind="gauss", metric="cosine_similarity",

@@ -29,6 +29,26 @@ class OracleEngine:
     def n_kept(self):
         return len(self.V) if self.keep is None else int(self.keep.sum())
 
+    def n_rows(self):
+        return len(self.V)
+
+    def row_offset(self):
+        return self.off
+
+    def append(self, rows):
+        self.V = np.concatenate([self.V, np.asarray(rows, self.V.dtype)])
+        self.ts, self.keep = None, None
+
+    def remove_local(self, local_rows):
+        alive = np.ones(len(self.V), bool)
+        alive[np.asarray(local_rows)] = False
+        self.V = self.V[alive]
+        self.ts = None if self.ts is None else self.ts[alive]
+        self.keep = None
+
+    def set_row_offset(self, off):
+        self.off = off
+
     def local_topk(self, queries, k, metric, bias, exact=False):
         q = np.asarray(queries)
         q = q[None, :] if q.ndim == 1 else q

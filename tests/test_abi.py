@@ -23,9 +23,10 @@ def test_header_symbols_exported_and_bound():
     names = declared_functions()
     assert len(names) >= 20
     assert sorted(N.SIGNATURES) == names
-    if not os.path.exists(N.library_path()):
+    import shutil
+    if shutil.which("nvcc") or not os.path.exists(N.library_path()):
         import __graft_entry__ as ge
-        ge.build()
+        ge.build()                     # incremental make: a stale library never reaches the GPU box
     handle = ctypes.CDLL(N.library_path())
     for name in names:
         assert hasattr(handle, name), f"{name} declared in the header but not exported"

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = G.load_sort_golden()
 TOL = {"float16": 1e-3, "float32": 1e-5, "float64": 1e-12, "uint64": 0}
-NATIVE_DTYPE = {"hamming_distance": "uint64", "jaccard_similarity": "float64"}
+NATIVE_DTYPE = {"hamming_distance": "uint64", "jaccard_similarity": "float64", "pearson_correlation": "float64"}
 
 
 @pytest.fixture(scope="module")
@@ -23,7 +23,8 @@ def hb():
 
 
 def exact_expected(metric, dtype):
-    return dtype == "float16" or metric in ("euclidean_metric", "manhattan_distance", "hamming_distance", "jaccard_similarity")
+    return dtype == "float16" or metric in ("euclidean_metric", "manhattan_distance", "hamming_distance", "jaccard_similarity",
+                                            "pearson_correlation")
 
 
 def check_against_oracle(V, q, ts, bias, k, metric, idx, sc, keep=None):
@@ -73,7 +74,7 @@ def test_sort_golden(hb, entry, mode):
 
 METRIC_FN = {"dot_product": "dot_product", "cosine_similarity": "cosine_similarity", "euclidean_metric": "euclidean_metric",
              "manhattan_distance": "manhattan_distance", "hamming_distance": "hamming_distance",
-             "jaccard_similarity": "jaccard_similarity"}
+             "jaccard_similarity": "jaccard_similarity", "pearson_correlation": "pearson_correlation"}
 
 
 @pytest.mark.parametrize("entry", GOLDEN[::3], ids=[G.case_id(e[0]) for e in GOLDEN[::3]])
@@ -85,7 +86,7 @@ def test_metric_functions_golden(hb, entry):
     assert np.array_equal(V, V0) and np.array_equal(q, q0)        # no in-place binarisation (quirk 9)
     dt = str(ref_sims.dtype)
     assert str(out.dtype) == dt and out.shape == ref_sims.reshape(-1).shape
-    if case["metric"] == "jaccard_similarity":
+    if case["metric"] in ("jaccard_similarity", "pearson_correlation"):
         assert np.array_equal(out, ref_sims.reshape(-1), equal_nan=True)      # 0/0: NaN payloads may differ between x86 and CUDA
     elif exact_expected(case["metric"], dt):
         assert out.tobytes() == ref_sims.reshape(-1).tobytes()
@@ -116,10 +117,13 @@ def test_reference_kats_on_gpu(hb):
     assert np.array_equal(hb.hamming_distance(np.array([[1, 1], [0, 1], [1, 0]]), np.array([1, 1])), [2, 1, 1])
     assert np.array_equal(hb.jaccard_similarity(np.array([[1, 1], [1, 0], [0, 0]]), np.array([1, 1])), [1.0, 0.5, 0.0])   # :40-46
     assert np.array_equal(hb.jaccard_similarity(np.array([[2, 2], [2, 0], [0, 0]]), np.array([1, 1])), [1.0, 0.5, 0.0])   # :48-52
+    r = hb.pearson_correlation(np.array([[1, 1], [0, 1], [1, 0]]), np.array([1, 1]))                        # :55-62
+    assert np.isnan(r[0]) and r[1] != 0.0 and r[2] != 0.0
+    assert np.all(np.isnan(hb.pearson_correlation(np.array([[1, 1], [0, 0], [1, 1]]), np.array([1, 1]))))       # :64-71
     V = np.array([[1, 0], [0, 1], [0.5, 0.5]])
     q = np.array([1, 0])
     ts = [1627825200.0, 1627911600.0, 1627998000.0]
-    table = [("cosine_similarity", 0, [0, 2, 1]), ("cosine_similarity", 1, [2, 0, 1]), ("euclidean_metric", 0, [0, 2, 1]),
+    table = [("pearson_correlation", 0, [0, 1, 2]),("cosine_similarity", 0, [0, 2, 1]), ("cosine_similarity", 1, [2, 0, 1]), ("euclidean_metric", 0, [0, 2, 1]),
              ("manhattan_distance", 0, [0, 2, 1]), ("hamming_distance", 0, [0, 2, 1]), ("jaccard_similarity", 0, [0, 2, 1])]
     for metric, bias, want in table:
         idx, _ = hb.hyperDB_ranking_algorithm_sort(V, q, metric=metric, timestamps=ts, recency_bias=bias)
@@ -164,7 +168,7 @@ def test_pokemon_c1(hb):
 # ---- fused sweep == exact path on larger inputs; certification statistics ----------------------------------
 SWEEP_CASES = [(dt, m, n, d, kind) for dt in ("f16", "f32", "f64")
                for m in ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance",
-                         "jaccard_similarity")
+                         "jaccard_similarity", "pearson_correlation")
                for (n, d, kind) in ((20000, 96, "unit"), (50021, 200, "scaled"), (30000, 33, "coarse"))]
 
 

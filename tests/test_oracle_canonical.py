@@ -15,7 +15,8 @@ TOL = {"float16": 1e-3, "float32": 1e-5, "float64": 1e-12, "uint64": 0, "int64":
 
 
 def exact_expected(case, dtype):
-    return dtype == "float16" or case["metric"] in ("euclidean_metric", "manhattan_distance", "hamming_distance", "jaccard_similarity")
+    return dtype == "float16" or case["metric"] in ("euclidean_metric", "manhattan_distance", "hamming_distance", "jaccard_similarity",
+                                                 "pearson_correlation")
 
 
 @pytest.mark.parametrize("entry", GOLDEN, ids=[G.case_id(e[0]) for e in GOLDEN])
@@ -25,7 +26,9 @@ def test_canonical_matches_reference(entry):
     sims = K.scores(V, q, case["metric"])
     dt = str(ref_sims.dtype)
     assert str(sims.dtype) == dt
-    if exact_expected(case, dt):
+    if case["metric"] == "pearson_correlation":
+        assert np.array_equal(sims, ref_sims.reshape(-1), equal_nan=True)
+    elif exact_expected(case, dt):
         assert sims.tobytes() == ref_sims.reshape(-1).tobytes()
     else:
         a, b = sims.astype(np.float64), ref_sims.reshape(-1).astype(np.float64)

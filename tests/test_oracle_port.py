@@ -9,7 +9,8 @@ from oracle import reference_port as P
 
 GOLDEN = G.load_sort_golden()
 FN = {"dot_product": P.dot_scores, "cosine_similarity": P.cosine_scores, "euclidean_metric": P.euclidean_scores,
-      "manhattan_distance": P.manhattan_scores, "hamming_distance": P.hamming_scores, "jaccard_similarity": P.jaccard_scores}
+      "manhattan_distance": P.manhattan_scores, "hamming_distance": P.hamming_scores, "jaccard_similarity": P.jaccard_scores,
+      "pearson_correlation": P.pearson_scores}
 
 
 @pytest.mark.parametrize("entry", GOLDEN, ids=[G.case_id(e[0]) for e in GOLDEN])
@@ -27,7 +28,7 @@ def test_port_matches_reference(entry):
         cond = np.linalg.norm(V.astype(float), axis=1) * np.linalg.norm(q.astype(float)) if case["metric"] == "dot_product" else 1.0
         assert np.all(np.abs(sims.astype(float) - ref_sims.astype(float)) <= tol * np.maximum(cond, 1e-300))
         return
-    assert sims.tobytes() == ref_sims.tobytes()
+    assert np.array_equal(sims, ref_sims, equal_nan=True) if case["metric"] == "pearson_correlation" else sims.tobytes() == ref_sims.tobytes()
     with np.errstate(all="ignore"):
         idx, sc = P.rank(V, q, case["k"], case["metric"], ts, case["bias"] if ts is not None else 0, canonical=False)
     assert np.array_equal(np.asarray(sc, float).reshape(-1), ref_sc)

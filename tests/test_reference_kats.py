@@ -17,6 +17,8 @@ SORT_TABLE = [                                   # tests/test_ranking_algorithm.
     ("euclidean_metric", 0, [0, 2, 1], [1.0, 0.58578644, 0.41421356]),
     ("manhattan_distance", 0, [0, 2, 1], [1.0, 0.5, 0.33333333]),
     ("hamming_distance", 0, [0, 2, 1], [2.0, 1.0, 0.0]),
+    ("jaccard_similarity", 0, [0, 2, 1], [1.0, 0.5, 0.0]),
+    ("pearson_correlation", 0, [0, 1, 2], [1.0, -1.0, -np.inf]),
 ]
 
 

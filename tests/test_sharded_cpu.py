@@ -60,6 +60,20 @@ def _worker(rank, world, port, fail_first, result_dir):
             assert cnt[b] == 7
     assert sm.exchanges == (6 if fail_first else 3)
     assert eng.calls == ([False, True] * 3 if fail_first else [False] * 3)
+    # mutation: remove rows on both sides of the shard boundary, then append; global ids stay dense and ordered
+    drop = np.array([0, 10, 499, 500, 501, 1000, 10])
+    alive = np.ones(n, bool)
+    alive[drop] = False
+    assert sm.remove_rows(drop) == n - 6
+    extra = rng.standard_normal((5, d)).astype(np.float32)
+    assert sm.append(extra) == n - 1
+    V2 = np.concatenate([V[alive], extra])
+    idx, sc, cnt = sm.query(Q[1:], 9, "euclidean_metric")
+    for b in range(2):
+        oi, os_ = K.rank(V2, Q[1 + b], 9, "euclidean_metric")
+        assert list(idx[b]) == list(oi) and np.array_equal(sc[b], os_)
+    with pytest.raises(IndexError):
+        sm.remove_rows([n + 100])
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
