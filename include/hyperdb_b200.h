@@ -73,6 +73,10 @@ int hdb_matrix_set_stream(hdb_matrix* m, void* cuda_stream);
  * certify (and whatever the caller enqueues after it on the post stream: the candidate exchange, the merge) of query i
  * overlaps the sweep of query i+1.  Results are valid in POST-stream order.  NULL switches pipelining off. */
 int hdb_matrix_set_post_stream(hdb_matrix* m, void* post_stream);
+/* Pipelined mode only: let the sweeps of consecutive queries overlap (default on).  Odd-numbered queries sweep on an
+ * internal second stream, so the next query's CTAs fill the SMs the current one vacates during its tail.  Results are
+ * still ordered on the post stream. */
+int hdb_matrix_set_sweep_overlap(hdb_matrix* m, int on);
 int hdb_matrix_info(const hdb_matrix* m, int* dtype, int64_t* n_rows, int64_t* dim, int64_t* row_offset,
                     int64_t* n_kept);
 

@@ -71,6 +71,12 @@ struct hdb_matrix {
   cudaStream_t post_stream = nullptr;
   cudaStream_t pre_stream = nullptr;     // pipelined mode: query preparation runs here, ahead of the main stream
   cudaEvent_t ev_select = nullptr, ev_prep = nullptr;
+  // sweep overlap: the sweeps of odd workspace slots run on a second internal stream, so the CTAs of query i+1 fill the
+  // SMs that query i's persistent CTAs vacate during its tail (launch gap, ramp, straggler warps, per-CTA merge)
+  cudaStream_t alt_stream = nullptr;
+  cudaEvent_t ev_alt = nullptr;
+  bool alt_pending = false;
+  int overlap = 1;
   // tensor-core batched path workspace
   TcWorkspace tc{};
   int64_t tc_nq = 0;
@@ -120,7 +126,17 @@ static size_t cap_rows(const hdb_matrix* m) {
   return (size_t)(c > 0 ? c : 1);
 }
 
+// order the handle's stream after the last sweep that was launched on the alternate stream
+static int join_alt(hdb_matrix* m) {
+  if (m->alt_pending) {
+    HDB_CUDA(cudaStreamWaitEvent(m->stream, m->ev_alt, 0));
+    m->alt_pending = false;
+  }
+  return 0;
+}
+
 static int refresh_kept(hdb_matrix* m) {
+  HDB_TRY(join_alt(m));
   RowFilter f = filter_of(m, 0.0, false);
   HDB_TRY(launch_kept_ts_max(nullptr, f, m->n, m->misc, m->misc + 1, m->stream));
   unsigned long long host[2];
@@ -180,6 +196,8 @@ int hdb_matrix_destroy(hdb_matrix* m) {
     if (m->ev_select) cudaEventDestroy(m->ev_select);
     if (m->ev_prep) cudaEventDestroy(m->ev_prep);
     if (m->pre_stream) cudaStreamDestroy(m->pre_stream);
+    if (m->alt_stream) { cudaStreamSynchronize(m->alt_stream); cudaStreamDestroy(m->alt_stream); }
+    if (m->ev_alt) cudaEventDestroy(m->ev_alt);
   }
   void* ptrs[] = {m->norms, m->inv_norms, m->sqnorms, m->bits, m->pmean, m->pstd, m->pscale, m->mask, m->ts, m->decay, m->q_raw, m->qb.qa, m->qb.qc, m->qb.qbits,
                   m->qb.qnorm, m->qb.qflags, m->qb.qaux, m->cand, m->tau, m->uncertified, m->o_block,
@@ -202,8 +220,12 @@ int hdb_matrix_set_post_stream(hdb_matrix* m, void* cuda_stream) {
   HDB_CUDA(cudaSetDevice(m->device));
   HDB_CUDA(cudaStreamSynchronize(m->stream));
   if (m->post_stream) HDB_CUDA(cudaStreamSynchronize(m->post_stream));
+  if (m->alt_stream) HDB_CUDA(cudaStreamSynchronize(m->alt_stream));
+  m->alt_pending = false;
   m->post_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   if (m->post_stream) {
+    if (!m->alt_stream) HDB_CUDA(cudaStreamCreateWithFlags(&m->alt_stream, cudaStreamNonBlocking));
+    if (!m->ev_alt) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_alt, cudaEventDisableTiming));
     if (!m->ev_select) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_select, cudaEventDisableTiming));
     if (!m->ev_prep) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_prep, cudaEventDisableTiming));
     if (!m->pre_stream) HDB_CUDA(cudaStreamCreateWithFlags(&m->pre_stream, cudaStreamNonBlocking));
@@ -217,6 +239,14 @@ int hdb_matrix_set_post_stream(hdb_matrix* m, void* cuda_stream) {
   slot_store(m);
   for (auto& q : m->slots) { if (q.cand) { cudaFree(q.cand); q.cand = nullptr; } q.pending = false; }
   slot_load(m, m->cur_slot);
+  return 0;
+}
+
+int hdb_matrix_set_sweep_overlap(hdb_matrix* m, int on) {
+  if (!m) return fail("null handle");
+  HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
+  m->overlap = on ? 1 : 0;
   return 0;
 }
 
@@ -343,6 +373,7 @@ static int ensure_pearson(hdb_matrix* m) {
 int hdb_matrix_set_mask(hdb_matrix* m, const uint32_t* bits, int src_space) {
   if (!m) return fail("null handle");
   HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
   if (!bits) {
     if (m->mask) { cudaStreamSynchronize(m->stream); cudaFree(m->mask); m->mask = nullptr; }
   } else {
@@ -369,6 +400,7 @@ int hdb_matrix_set_range(hdb_matrix* m, int64_t lo, int64_t hi) {
 int hdb_matrix_set_timestamps(hdb_matrix* m, const double* ts, int src_space) {
   if (!m) return fail("null handle");
   HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
   m->decay_valid = false;
   if (!ts) {
     if (m->ts) { cudaStreamSynchronize(m->stream); cudaFree(m->ts); m->ts = nullptr; }
@@ -387,6 +419,7 @@ int hdb_matrix_kept_ts_max(hdb_matrix* m, double* ts_max, int64_t* n_kept) {
   if (!m) return fail("null handle");
   if (!m->ts) return fail("hdb_matrix_kept_ts_max: no timestamps set");
   HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
   RowFilter f = filter_of(m, 0.0, false);
   HDB_TRY(launch_kept_ts_max(m->ts, f, m->n, m->misc, m->misc + 1, m->stream));
   unsigned long long host[2];
@@ -402,6 +435,7 @@ int hdb_matrix_set_decay_reference(hdb_matrix* m, double ts_max) {
   if (!m) return fail("null handle");
   if (!m->ts) return fail("hdb_matrix_set_decay_reference: no timestamps set");
   HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
   if (!m->decay) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->decay), cap_rows(m) * 8));     // dropped by a mutation
   HDB_TRY(launch_decay(m->ts, m->decay, m->n, ts_max, m->stream));
   m->decay_valid = true;
@@ -412,6 +446,7 @@ int hdb_matrix_stage1_recency(hdb_matrix* m, double bias1, double ts_max) {
   if (!m) return fail("null handle");
   if (!m->ts) return fail("hdb_matrix_stage1_recency: no timestamps set");
   HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
   m->decay_valid = false;
   return launch_stage1(m->ts, m->n, bias1, ts_max, m->stream);
 }
@@ -427,6 +462,8 @@ static int quiesce(hdb_matrix* m) {
   HDB_CUDA(cudaStreamSynchronize(m->stream));
   if (m->post_stream) HDB_CUDA(cudaStreamSynchronize(m->post_stream));
   if (m->pre_stream) HDB_CUDA(cudaStreamSynchronize(m->pre_stream));
+  if (m->alt_stream) HDB_CUDA(cudaStreamSynchronize(m->alt_stream));
+  m->alt_pending = false;
   for (auto& q : m->slots) q.pending = false;
   return 0;
 }
@@ -638,9 +675,11 @@ static int pick_kp(const hdb_matrix* m, int64_t k) {
 
 // Enqueue the fused path for queries [b0, b0+cnt) of the prepared batch; results go to (idx, score, count, flags).
 static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int64_t cnt, int64_t k, const RowFilter& f,
-                     int64_t* idx, double* score, int64_t* count, uint32_t* flags, cudaStream_t fin_stream = nullptr) {
+                     int64_t* idx, double* score, int64_t* count, uint32_t* flags, cudaStream_t fin_stream = nullptr,
+                     cudaStream_t sweep_stream = nullptr) {
   MatrixView v = view_of(m);
-  if (!(fin_stream && fin_stream != m->stream)) HDB_CUDA(cudaMemsetAsync(m->tau + b0, 0, (size_t)cnt * 8, m->stream));   // pipelined: prep zeroed it
+  cudaStream_t sw = sweep_stream ? sweep_stream : m->stream;
+  if (!(fin_stream && fin_stream != m->stream)) HDB_CUDA(cudaMemsetAsync(m->tau + b0, 0, (size_t)cnt * 8, sw));   // pipelined: prep zeroed it
   const int elt = (m->dtype == 2) ? 8 : 4;
   for (int64_t i = 0; i < cnt; ++i) {
     SweepOut so;
@@ -650,9 +689,9 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
     const void* qa = reinterpret_cast<const char*>(m->qb.qa) + (size_t)(b0 + i) * m->d * elt;
     const uint32_t* qbits = m->qb.qbits + (size_t)(b0 + i) * m->words;
     const bool prof = m->prof_used + 2 <= m->prof_ev.size();
-    if (prof) HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used], m->stream));
-    HDB_TRY(launch_sweep(v, metric, qa, qbits, m->qb.qaux + 2 * (b0 + i), f, kp, so, m->stream));
-    if (prof) { HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used + 1], m->stream)); m->prof_used += 2; }
+    if (prof) HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used], sw));
+    HDB_TRY(launch_sweep(v, metric, qa, qbits, m->qb.qaux + 2 * (b0 + i), f, kp, so, sw));
+    if (prof) { HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used + 1], sw)); m->prof_used += 2; }
   }
   FinalizeArgs a;
   a.m = v; a.f = f; a.metric = metric; a.rdt = rdt; a.kp = kp; a.k = (int)k; a.n_kept = m->n_kept; a.grid = m->grid;
@@ -664,11 +703,11 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
   a.cand_count = nullptr; a.cand_stride = 0; a.tau0 = nullptr; a.extra_flags = 0; a.tau0_negd2 = 0;
   if (fin_stream && fin_stream != m->stream) {
     // pipelined: the certify step runs on the post stream, ordered after the sweeps by an event
-    HDB_CUDA(cudaEventRecord(m->ev_select, m->stream));
+    HDB_CUDA(cudaEventRecord(m->ev_select, sw));
     HDB_CUDA(cudaStreamWaitEvent(fin_stream, m->ev_select, 0));
     return launch_finalize(a, cnt, fin_stream);
   }
-  return launch_finalize(a, cnt, m->stream);
+  return launch_finalize(a, cnt, sw);
 }
 
 constexpr int64_t kTcChunk = 4096;       // queries per tensor-core batch (bounds the sample / candidate workspaces)
@@ -761,6 +800,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
     hdb_matrix::QuerySlot& qs = m->slots[m->cur_slot];
     if (qs.pending) HDB_CUDA(cudaStreamWaitEvent(m->pre_stream, qs.done, 0));
   }
+  if (!pipelined) HDB_TRY(join_alt(m));
   if (!pipelined && m->post_stream) {
     // a host-output call while pipelining is on: order it after every certify step still in flight on the post stream
     for (auto& qs : m->slots)
@@ -818,7 +858,13 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
       const int64_t cnt = nq - b0 < kChunk ? nq - b0 : kChunk;
       // only a single chunk can hand its certify step to the post stream (the candidate buffer is reused per chunk)
       const bool hand_over = pipelined && nq <= kChunk;
-      HDB_TRY(run_fused(m, metric, rdt, kp, b0, cnt, k, f, idx, score, count, flags, hand_over ? m->post_stream : nullptr));
+      cudaStream_t sw = nullptr;
+      if (hand_over && m->overlap && m->alt_stream && (m->cur_slot & 1)) {
+        sw = m->alt_stream;                                  // odd slots sweep on the alternate stream (see hdb_matrix::alt_stream)
+        HDB_CUDA(cudaStreamWaitEvent(sw, m->ev_prep, 0));
+      }
+      HDB_TRY(run_fused(m, metric, rdt, kp, b0, cnt, k, f, idx, score, count, flags, hand_over ? m->post_stream : nullptr, sw));
+      if (sw) { HDB_CUDA(cudaEventRecord(m->ev_alt, sw)); m->alt_pending = true; }
       on_post = hand_over;
     }
     if (pipelined && on_post) {
@@ -908,6 +954,7 @@ int hdb_profile_enable(hdb_matrix* m, int max_pairs) {
 int hdb_profile_read(hdb_matrix* m, int* n_launches, float* total_ms) {
   if (!m || !n_launches || !total_ms) return fail("null argument");
   HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
   HDB_CUDA(cudaStreamSynchronize(m->stream));
   float sum = 0.f;
   for (size_t i = 0; i + 1 < m->prof_used; i += 2) {
@@ -926,6 +973,7 @@ int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter) 
   if (!m->last.valid || m->last.kp == 0 || m->last.k == 0) return fail("hdb_time_last_query: no fused query to replay");
   if (iters < 1) iters = 1;
   HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
   const bool use_decay = m->ts != nullptr && m->decay_valid;
   const RowFilter f = filter_of(m, m->last.bias, use_decay);
   cudaEvent_t e0, e1;
@@ -964,6 +1012,7 @@ int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_
   if (q_dtype < 0 || q_dtype > 2) return fail("hdb_scores: q_dtype must be HDB_F16/F32/F64");
   if (!query || !out) return fail("hdb_scores: NULL argument");
   HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(join_alt(m));
   HDB_TRY(ensure_workspace(m, 1, 1));
   const int rdt = m->dtype > q_dtype ? m->dtype : q_dtype;
   if (metric == HDB_HAMMING || metric == HDB_JACCARD) HDB_TRY(ensure_bits(m));

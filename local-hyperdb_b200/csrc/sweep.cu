@@ -9,6 +9,8 @@
 // threshold.  The N-length score vector is never written.  Output: per-CTA top-KP selection keys;
 // csrc/finalize.cu merges them, re-scores the KP candidates in the reference's exact arithmetic and
 // certifies the top-k (DESIGN.md "select then certify").
+#include <cstdlib>
+
 #include "hdb_common.cuh"
 #include "hdb_internal.h"
 #include "../../include/hyperdb_b200.h"
@@ -497,51 +499,217 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_lpr_kernel(Ham
   const int64_t g0 = (int64_t)blockIdx.x * kSweepWarps + warp;
   uint32_t next_bits = (g0 < nwin) ? window_keep_bits(p.f, g0, p.n) : 0u;
 
+  // the PPR loads of round `round` of window `win` (dropped rows / idle lanes: the query itself, i.e. xor = 0)
+  auto load_round = [&](uint4 (&v)[PPR], int64_t win, uint32_t wbits, int round) {
+#pragma unroll
+    for (int r = 0; r < PPR; ++r) {
+      const int loc = (round * PPR + r) * RPP + slot;
+      const bool k = ((wbits >> loc) & 1u) && lane_has;
+      v[r] = k ? ld_stream16(vbits + (win * 32 + loc) * p.nvec + sub) : my_q;
+    }
+  };
+  // Software pipeline: round 0 of the NEXT window is in flight (registers) while the current window is counted,
+  // reduced and pushed, so every warp keeps 32 rows of loads outstanding at all times.
+  uint4 cur[PPR];
+  if (g0 < nwin) load_round(cur, g0, next_bits, 0);
+
   for (int64_t g = g0; g < nwin; g += wstride) {
     const uint32_t bits = next_bits;
     next_bits = (g + wstride < nwin) ? window_keep_bits(p.f, g + wstride, p.n) : 0u;
-    if (bits == 0) continue;
-    {
-      unsigned long long t = *reinterpret_cast<volatile unsigned long long*>(s_tau);
-      if (++since_refresh >= 8) {
-        since_refresh = 0;
-        unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(p.tau);
-        if (gt > t) { t = gt; if (lane == 0) atomicMax(s_tau, gt); }
+    uint4 nxt[PPR];
+    if (g + wstride < nwin) load_round(nxt, g + wstride, next_bits, 0);
+    if (bits != 0) {
+      {
+        unsigned long long t = *reinterpret_cast<volatile unsigned long long*>(s_tau);
+        if (++since_refresh >= 8) {
+          since_refresh = 0;
+          unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(p.tau);
+          if (gt > t) { t = gt; if (lane == 0) atomicMax(s_tau, gt); }
+        }
+        if (t > wl.tau) wl.tau = t;
       }
-      if (t > wl.tau) wl.tau = t;
+      const int64_t row0 = g * 32;
+#pragma unroll
+      for (int round = 0; round < ROUNDS; ++round) {
+        const int my_loc = (round * PPR + my_pass) * RPP + slot;        // the row this lane will own after the reduce
+        const bool my_kept = (bits >> my_loc) & 1u;
+        double my_decay = 0.0;
+        if (p.f.decay && rep && my_kept) my_decay = p.f.decay[row0 + my_loc];
+        uint4 v[PPR];
+        if (round == 0) {
+#pragma unroll
+          for (int r = 0; r < PPR; ++r) v[r] = cur[r];
+        } else {
+          load_round(v, g, bits, round);
+        }
+        int cnt[PPR];
+#pragma unroll
+        for (int r = 0; r < PPR; ++r) {
+          if (JAC)          // both popcounts packed in one int (16 bits each: d <= 4096 here), reduced together
+            cnt[r] = (__popc(v[r].x & my_q.x) + __popc(v[r].y & my_q.y) + __popc(v[r].z & my_q.z) + __popc(v[r].w & my_q.w)) +
+                     ((__popc(v[r].x | my_q.x) + __popc(v[r].y | my_q.y) + __popc(v[r].z | my_q.z) + __popc(v[r].w | my_q.w)) << 16);
+          else
+            cnt[r] = __popc(v[r].x ^ my_q.x) + __popc(v[r].y ^ my_q.y) + __popc(v[r].z ^ my_q.z) + __popc(v[r].w ^ my_q.w);
+        }
+        const int diff = transpose_reduce<PPR, LPR>(cnt, sub);
+        double exact = JAC ? (double)(diff & 0xffff) / (double)(diff >> 16) : (double)((int)p.d - diff);
+        if (p.f.decay) exact += p.f.bias * my_decay;
+        const float score = (float)exact;
+        const uint64_t key = make_key(score, (uint32_t)(row0 + my_loc));
+        wl.push(rep && my_kept && key > wl.tau, key, lane, s_tau, p.tau);
+      }
     }
-    const int64_t row0 = g * 32;
 #pragma unroll
-    for (int round = 0; round < ROUNDS; ++round) {
-      const int my_loc = (round * PPR + my_pass) * RPP + slot;        // the row this lane will own after the reduce
-      const bool my_kept = (bits >> my_loc) & 1u;
-      double my_decay = 0.0;
-      if (p.f.decay && rep && my_kept) my_decay = p.f.decay[row0 + my_loc];
-      uint4 v[PPR];
-#pragma unroll
-      for (int r = 0; r < PPR; ++r) {
-        const int loc = (round * PPR + r) * RPP + slot;
-        const bool k = ((bits >> loc) & 1u) && lane_has;
-        v[r] = k ? ld_stream16(vbits + (row0 + loc) * p.nvec + sub) : my_q;      // dropped rows: xor = 0
-      }
-      int cnt[PPR];
-#pragma unroll
-      for (int r = 0; r < PPR; ++r) {
-        if (JAC)          // both popcounts packed in one int (16 bits each: d <= 4096 here), reduced together
-          cnt[r] = (__popc(v[r].x & my_q.x) + __popc(v[r].y & my_q.y) + __popc(v[r].z & my_q.z) + __popc(v[r].w & my_q.w)) +
-                   ((__popc(v[r].x | my_q.x) + __popc(v[r].y | my_q.y) + __popc(v[r].z | my_q.z) + __popc(v[r].w | my_q.w)) << 16);
-        else
-          cnt[r] = __popc(v[r].x ^ my_q.x) + __popc(v[r].y ^ my_q.y) + __popc(v[r].z ^ my_q.z) + __popc(v[r].w ^ my_q.w);
-      }
-      const int diff = transpose_reduce<PPR, LPR>(cnt, sub);
-      double exact = JAC ? (double)(diff & 0xffff) / (double)(diff >> 16) : (double)((int)p.d - diff);
-      if (p.f.decay) exact += p.f.bias * my_decay;
-      const float score = (float)exact;
-      const uint64_t key = make_key(score, (uint32_t)(row0 + my_loc));
-      wl.push(rep && my_kept && key > wl.tau, key, lane, s_tau, p.tau);
-    }
+    for (int r = 0; r < PPR; ++r) cur[r] = nxt[r];
   }
   cta_merge_and_store<KP>(s_lists, wl, lane, warp, s_tau, p.tau, p.cand + (int64_t)blockIdx.x * KP);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged form for unmasked shards with rows of at most 8 vectors (d <= 1024): the window of 32 consecutive rows is ONE
+// contiguous block of HBM (32 * NVEC * 16 bytes); every lane copies NVEC coalesced 16-byte pieces of it straight into
+// shared memory with cp.async (no registers, no L1), double-buffered per warp, and then OWNS one row: it reads its row
+// back with NVEC conflict-free 128-bit shared loads (row pitch = an odd number of 16-byte units) and popcounts it
+// against the query held in registers.  No shuffles, no transposing reduce: ~3x fewer instructions per row than the
+// cooperative form above, which was issue-latency bound (0.49 IPC per scheduler, 4 warps) rather than HBM bound.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int NVEC> struct StagedCfg {
+  static constexpr int kPitch = NVEC | 1;                 // 16-byte units per staged row
+  static constexpr int kStageU4 = 32 * kPitch;            // one window
+  static constexpr size_t kBytes = (size_t)kSweepWarps * 2 * kStageU4 * 16;
+};
+
+template <int KP, int NVEC, bool JAC>
+__global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_staged_kernel(HammingParams p) {
+  constexpr int kCap = ListCfg<KP>::kCap;
+  constexpr int PITCH = StagedCfg<NVEC>::kPitch;
+  constexpr int STAGE = StagedCfg<NVEC>::kStageU4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* s_lists = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(s_lists + kSweepWarps * kCap);
+  uint4* s_stage = reinterpret_cast<uint4*>(s_tau + 2);                             // [warps][2][STAGE]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) *s_tau = 0;
+  uint4 q[NVEC];
+#pragma unroll
+  for (int c = 0; c < NVEC; ++c) q[c] = reinterpret_cast<const uint4*>(p.qbits)[c];
+  __syncthreads();
+
+  WarpList<KP> wl;
+  wl.buf = s_lists + warp * kCap;
+  wl.cnt = 0;
+  wl.tau = 0;
+
+  uint4* my_stage = s_stage + (size_t)warp * 2 * STAGE;
+  // piece i = j*32 + lane of a window is piece (i % NVEC) of row (i / NVEC): coalesced in HBM, scattered into the padded rows
+  int dst_off[NVEC];
+#pragma unroll
+  for (int j = 0; j < NVEC; ++j) {
+    const int i = j * 32 + lane;
+    dst_off[j] = (i / NVEC) * PITCH + (i % NVEC);
+  }
+  const int64_t nwin = (p.n + 31) / 32;
+  const int64_t wstride = (int64_t)gridDim.x * kSweepWarps;
+  const uint4* vbits = reinterpret_cast<const uint4*>(p.bits);
+  const int64_t total_u4 = p.n * NVEC;
+
+  auto issue = [&](int buf, int64_t win) {
+    const int64_t base = win * (32 * NVEC);
+    uint4* dst = my_stage + buf * STAGE;
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int64_t src = base + j * 32 + lane;
+      if (src < total_u4) cp_async16(dst + dst_off[j], vbits + src);
+    }
+  };
+
+  int since_refresh = 0;
+  const int64_t g0 = (int64_t)blockIdx.x * kSweepWarps + warp;
+  uint32_t bits = (g0 < nwin) ? window_keep_bits(p.f, g0, p.n) : 0u;
+  if (bits) issue(0, g0);
+  cp_async_commit();
+  int buf = 0;
+
+  for (int64_t g = g0; g < nwin; g += wstride) {
+    const int64_t gn = g + wstride;
+    const uint32_t next_bits = (gn < nwin) ? window_keep_bits(p.f, gn, p.n) : 0u;
+    if (next_bits) issue(buf ^ 1, gn);                    // overlaps everything below
+    cp_async_commit();
+    cp_async_wait<1>();                                   // this lane's pieces of window g have landed ...
+    __syncwarp();                                         // ... and so have everybody else's
+    if (bits) {
+      {
+        unsigned long long t = *reinterpret_cast<volatile unsigned long long*>(s_tau);
+        if (++since_refresh >= 8) {
+          since_refresh = 0;
+          unsigned long long gt = *reinterpret_cast<volatile unsigned long long*>(p.tau);
+          if (gt > t) { t = gt; if (lane == 0) atomicMax(s_tau, gt); }
+        }
+        if (t > wl.tau) wl.tau = t;
+      }
+      const int64_t row = g * 32 + lane;
+      const bool kept = (bits >> lane) & 1u;
+      double my_decay = 0.0;
+      if (p.f.decay && kept) my_decay = p.f.decay[row];
+      const uint4* rowp = my_stage + buf * STAGE + lane * PITCH;
+      int a = 0, b = 0;
+#pragma unroll
+      for (int c = 0; c < NVEC; ++c) {
+        const uint4 v = rowp[c];
+        if (JAC) {
+          a += __popc(v.x & q[c].x) + __popc(v.y & q[c].y) + __popc(v.z & q[c].z) + __popc(v.w & q[c].w);
+          b += __popc(v.x | q[c].x) + __popc(v.y | q[c].y) + __popc(v.z | q[c].z) + __popc(v.w | q[c].w);
+        } else {
+          a += __popc(v.x ^ q[c].x) + __popc(v.y ^ q[c].y) + __popc(v.z ^ q[c].z) + __popc(v.w ^ q[c].w);
+        }
+      }
+      double exact = JAC ? (double)a / (double)b : (double)((int)p.d - a);
+      if (p.f.decay) exact += p.f.bias * my_decay;
+      const uint64_t key = make_key((float)exact, (uint32_t)row);
+      wl.push(kept && key > wl.tau, key, lane, s_tau, p.tau);
+    }
+    __syncwarp();                                         // every lane is done with `buf` before the next issue refills it
+    buf ^= 1;
+    bits = next_bits;
+  }
+  cp_async_wait<0>();
+  cta_merge_and_store<KP>(s_lists, wl, lane, warp, s_tau, p.tau, p.cand + (int64_t)blockIdx.x * KP);
+}
+
+template <int KP, int NVEC, bool JAC>
+static int launch_hamming_staged3(const HammingParams& hp, int grid, cudaStream_t s) {
+  auto kern = sweep_hamming_staged_kernel<KP, NVEC, JAC>;
+  const size_t smem = (size_t)kSweepWarps * ListCfg<KP>::kCap * 8 + 16 + StagedCfg<NVEC>::kBytes;
+  if (smem > 48 * 1024) HDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kSweepThreads, smem, s>>>(hp);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int KP, int NVEC>
+static int launch_hamming_staged2(const HammingParams& hp, int grid, cudaStream_t s) {
+  return hp.jaccard ? launch_hamming_staged3<KP, NVEC, true>(hp, grid, s) : launch_hamming_staged3<KP, NVEC, false>(hp, grid, s);
+}
+template <int KP>
+static int launch_hamming_staged(const HammingParams& hp, int grid, cudaStream_t s) {
+  switch (hp.nvec) {
+    case 1: return launch_hamming_staged2<KP, 1>(hp, grid, s);
+    case 2: return launch_hamming_staged2<KP, 2>(hp, grid, s);
+    case 3: return launch_hamming_staged2<KP, 3>(hp, grid, s);
+    case 4: return launch_hamming_staged2<KP, 4>(hp, grid, s);
+    case 5: return launch_hamming_staged2<KP, 5>(hp, grid, s);
+    case 6: return launch_hamming_staged2<KP, 6>(hp, grid, s);
+    case 7: return launch_hamming_staged2<KP, 7>(hp, grid, s);
+    default: return launch_hamming_staged2<KP, 8>(hp, grid, s);
+  }
 }
 
 template <int KP, int LPR, bool JAC>
@@ -572,6 +740,12 @@ static int launch_hamming_kp(const HammingParams& hp, int grid, size_t smem, cud
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// A/B testing: HDB_HAMMING_COOPERATIVE=1 keeps the register-cooperative hamming kernels for every shape
+static bool force_cooperative_hamming() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HDB_HAMMING_COOPERATIVE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 static size_t list_smem(int kp) { return (size_t)kSweepWarps * (kp <= 32 ? 128 : 2 * kp) * 8 + 16; }
 
 int sweep_grid_size(int device) {
@@ -619,6 +793,8 @@ int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t
     hp.f = f; hp.cand = out.cand; hp.tau = out.tau;
     size_t smem = list_smem(kp) + (size_t)hp.nvec * 16;
     if (smem > 200 * 1024) return fail("sweep: dimension too large for the fused hamming pass");
+    if (hp.nvec <= 8 && !f.mask && !force_cooperative_hamming())       // contiguous windows: cp.async-staged, lane-per-row form
+      return kp <= 32 ? launch_hamming_staged<32>(hp, out.grid, s) : launch_hamming_staged<128>(hp, out.grid, s);
     if (hp.nvec <= 32) return kp <= 32 ? launch_hamming_kp<32>(hp, out.grid, smem, s) : launch_hamming_kp<128>(hp, out.grid, smem, s);
     if (kp <= 32) {
       if (smem > 48 * 1024) HDB_CUDA(cudaFuncSetAttribute(sweep_hamming_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -41,6 +41,7 @@ SIGNATURES = {
     "hdb_matrix_set_row_offset": (C.c_int, [vp, i64]),
     "hdb_matrix_set_stream": (C.c_int, [vp, vp]),
     "hdb_matrix_set_post_stream": (C.c_int, [vp, vp]),
+    "hdb_matrix_set_sweep_overlap": (C.c_int, [vp, C.c_int]),
     "hdb_matrix_info": (C.c_int, [vp, C.POINTER(C.c_int), i64p, i64p, i64p, i64p]),
     "hdb_matrix_set_mask": (C.c_int, [vp, vp, C.c_int]),
     "hdb_matrix_set_range": (C.c_int, [vp, i64, i64]),

@@ -208,6 +208,10 @@ class DeviceMatrix:
         """Pipelining of device-output queries: certify on this stream, overlapping the next query's sweep (0 = off)."""
         N.check(N.lib().hdb_matrix_set_post_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_sweep_overlap(self, on):
+        """Pipelined mode: sweeps of consecutive queries may overlap (default) or run strictly one after the other."""
+        N.check(N.lib().hdb_matrix_set_sweep_overlap(self._h, 1 if on else 0))
+
     def set_stream(self, cuda_stream_ptr):
         N.check(N.lib().hdb_matrix_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

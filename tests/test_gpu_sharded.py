@@ -76,6 +76,30 @@ def test_pipelined_queries_match():
                 assert np.array_equal(sc.cpu().numpy()[0], ref[i][1][0])
             got = sm.query(Q[3], 10, metric, 0.3)                                            # host path while pipelined
             assert np.array_equal(got[0], ref[3][0]) and np.array_equal(got[1], ref[3][1])
+            # sweeps on alternating streams: a row-mask change between two in-flight queries must be ordered after the
+            # sweep that still reads the old mask (join of the alternate stream), with and without overlap
+            for overlap in (True, False):
+                m.set_sweep_overlap(overlap)
+                keep = rng.random(n) < 0.5
+                a1 = sm.query_async(qd[0:1], 10, metric, 0.3)
+                a2 = sm.query_async(qd[1:2], 10, metric, 0.3)
+                m.set_mask(keep)
+                m.refresh_decay()                   # the decay reference is the maximum over KEPT rows
+                b1 = sm.query_async(qd[0:1], 10, metric, 0.3)
+                b2 = sm.query_async(qd[1:2], 10, metric, 0.3)
+                sm.wait_results()
+                torch.cuda.synchronize()
+                unmasked = [a1, a2]
+                masked = [b1, b2]
+                m.set_mask(None)
+                for j in range(2):
+                    if not int(unmasked[j][3].flatten()[0]) & 8:
+                        assert np.array_equal(unmasked[j][0].cpu().numpy()[0], ref[j][0][0]), (metric, overlap, j)
+                    if not int(masked[j][3].flatten()[0]) & 8:
+                        oi, _ = K.rank(V, Q[j], 10, metric, ts, 0.3, keep)
+                        assert list(masked[j][0].cpu().numpy()[0]) == list(oi), (metric, overlap, j)
+                m.refresh_decay()                   # the mask changed the decay reference; restore it for the next metric
+            m.set_sweep_overlap(True)
             sm.engine.enable_pipeline(False)
     finally:
         m.close()
