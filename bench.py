@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debugging only; invalidates the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="keep every kernel of a query on one stream")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU candidate exchange: NVLink peer-memory kernels (default) or the NCCL all-gather")
     ap.add_argument("--no-overlap", action="store_true", help="pipelined mode: do not let consecutive sweeps overlap")
     ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph (single GPU only)")
     args = ap.parse_args()
@@ -266,6 +268,8 @@ def main():
         m.set_mask(keep_bits)
     eng = CudaEngine(m)
     sm = ShardedMatrix(eng, w["n"])
+    if world > 1 and args.exchange == "peer":
+        sm.enable_peer_exchange(max_batch=w["b"], max_k=w["k"])
     if not args.no_pipeline and w["b"] < 2:
         eng.enable_pipeline()            # certify/exchange/merge of query i overlap the sweep of query i+1
         m.set_sweep_overlap(not args.no_overlap)     # ... and the head of sweep i+1 fills the tail of sweep i
@@ -388,6 +392,7 @@ def main():
             "config": {"workload": args.workload, "rows": w["n"], "dim": w["d"], "metric": w["metric"], "top_k": k, "batch": b,
                        "sharding": f"rows/{world}", "l2": "inputs larger than L2 (shard %.2f GB per GPU, a new query every step)"
                        % (shard_bytes / 1e9), "uncertified_steps": uncertified, "cuda_graph": bool(graphed),
+                       "exchange": ("peer-memory" if sm.xchg is not None else "nccl all-gather") if world > 1 else None,
                        "pipelined": eng.post is not None, "sweep_overlap": bool(eng.post is not None and not args.no_overlap and b < 2)},
             "clocks": clocks,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(b * w["d"] * ITEM[w["dtype"]]),

@@ -27,6 +27,7 @@ extern "C" {
 #endif
 
 typedef struct hdb_matrix hdb_matrix; /* opaque: one row shard of the stored matrix on one GPU */
+typedef struct hdb_exchange hdb_exchange; /* opaque: this rank's end of the peer-memory candidate exchange */
 
 enum { HDB_F16 = 0, HDB_F32 = 1, HDB_F64 = 2 };   /* HyperDB fp_precision, hyperdb/hyperdb.py:65-66,80 */
 enum { HDB_HOST = 0, HDB_DEVICE = 1 };
@@ -141,6 +142,34 @@ int hdb_normalize_rows(int device, int dtype, int64_t n_rows, int64_t dim, const
 int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t n_queries, int64_t k, int64_t list_stride,
                    const double* scores, const int64_t* ids, const int64_t* counts, int in_space,
                    int64_t* out_idx, double* out_score, int64_t* out_count, int out_space);
+
+/* ---- multi-GPU: the same exchange + merge over NVLink peer memory, without a collective library call -------------
+ * One process per GPU.  Every rank creates an exchange (a small device buffer of 4 slots x world x max_words 8-byte
+ * words plus sequence flags), publishes its CUDA IPC handle (hdb_exchange_handle_bytes() bytes) to the other ranks by
+ * any means (the host uses torch.distributed once, at set-up) and connects to all of them.  hdb_exchange_step then
+ * enqueues on `cuda_stream`: peer stores of this rank's packed result block
+ *     [scores nq*k (f64) | ids nq*k (i64) | counts nq (i64) | flags nq (u32, padded to 8 bytes)]      (`words` words)
+ * into every rank's buffer, a bounded wait until all `world` blocks of this step have arrived, and the merge of the
+ * world x k candidates per query by (score desc, global id asc).  out_flags receives [world][nq] per-shard flags.
+ * Every rank must call hdb_exchange_step the same number of times with the same (nq, k). */
+int hdb_exchange_create(int device, int world, int rank, int64_t max_words, hdb_exchange** out);
+int hdb_exchange_destroy(hdb_exchange* x);
+int hdb_exchange_handle_bytes(void);
+int hdb_exchange_local_handle(hdb_exchange* x, void* handle_out);
+/* all_handles: world consecutive IPC handles, indexed by rank (this rank's own entry is ignored). */
+int hdb_exchange_connect(hdb_exchange* x, const void* all_handles);
+/* Same-process form (several shards of one process, tests): peers given as device pointers from hdb_exchange_local_buffer. */
+int hdb_exchange_connect_pointers(hdb_exchange* x, void* const* peer_buffers);
+int hdb_exchange_local_buffer(hdb_exchange* x, void** buffer);
+int hdb_exchange_step(hdb_exchange* x, void* cuda_stream, const void* mine, int64_t words, int64_t n_queries, int64_t k,
+                      int64_t* out_idx, double* out_score, int64_t* out_count, uint32_t* out_flags);
+/* The two halves of a step (a process that drives several ranks must enqueue every rank's push before any wait:
+ * a waiting kernel may sit in front of another stream's push in the same hardware queue). */
+int hdb_exchange_push(hdb_exchange* x, void* cuda_stream, const void* mine, int64_t words);
+int hdb_exchange_wait_merge(hdb_exchange* x, void* cuda_stream, int64_t n_queries, int64_t k, int64_t* out_idx, double* out_score,
+                            int64_t* out_count, uint32_t* out_flags);
+/* 1 if a wait gave up after 10 s because a peer never delivered (synchronises the device). */
+int hdb_exchange_error(hdb_exchange* x, int* error);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */

@@ -53,6 +53,17 @@ SIGNATURES = {
     "hdb_scores": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]),
     "hdb_normalize_rows": (C.c_int, [C.c_int, C.c_int, i64, i64, vp, C.c_int, vp, C.c_int]),
     "hdb_merge_topk": (C.c_int, [C.c_int, vp, i64, i64, i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]),
+    "hdb_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.POINTER(vp)]),
+    "hdb_exchange_destroy": (C.c_int, [vp]),
+    "hdb_exchange_handle_bytes": (C.c_int, []),
+    "hdb_exchange_local_handle": (C.c_int, [vp, vp]),
+    "hdb_exchange_connect": (C.c_int, [vp, vp]),
+    "hdb_exchange_connect_pointers": (C.c_int, [vp, C.POINTER(vp)]),
+    "hdb_exchange_local_buffer": (C.c_int, [vp, C.POINTER(vp)]),
+    "hdb_exchange_step": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]),
+    "hdb_exchange_push": (C.c_int, [vp, vp, vp, i64]),
+    "hdb_exchange_wait_merge": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp]),
+    "hdb_exchange_error": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "hdb_launch_count": (C.c_int64, [C.c_int]),
     "hdb_time_last_query": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "hdb_matrix_set_path": (C.c_int, [vp, C.c_int]),

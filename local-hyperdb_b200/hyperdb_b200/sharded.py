@@ -116,6 +116,66 @@ class CudaEngine:
         return idx, sc, cnt, flags
 
 
+class PeerExchange:
+    """This rank's end of the NVLink peer-memory candidate exchange (include/hyperdb_b200.h, hdb_exchange_*): every
+    rank's result block is stored straight into every rank's buffer and merged there -- two tiny kernels per step and
+    no collective-library call on the query path (the NCCL all-gather cost more host time than a sharded sweep takes)."""
+
+    def __init__(self, device_index, world, rank, max_words):
+        self._h = C.c_void_p()
+        self.world, self.rank, self.max_words = int(world), int(rank), int(max_words) + (int(max_words) & 1)
+        N.check(N.lib().hdb_exchange_create(int(device_index), self.world, self.rank, self.max_words, C.byref(self._h)))
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(N.lib().hdb_exchange_handle_bytes())
+        N.check(N.lib().hdb_exchange_local_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: the `handle()` bytes of every rank, indexed by rank (CUDA IPC: one process per GPU)."""
+        blob = b"".join(handles)
+        N.check(N.lib().hdb_exchange_connect(self._h, C.c_char_p(blob)))
+
+    def local_buffer(self) -> int:
+        p = C.c_void_p()
+        N.check(N.lib().hdb_exchange_local_buffer(self._h, C.byref(p)))
+        return p.value
+
+    def connect_pointers(self, buffers):
+        """Same-process form: `local_buffer()` of every rank (several shards driven by one process)."""
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(b) for b in buffers])
+        N.check(N.lib().hdb_exchange_connect_pointers(self._h, arr))
+
+    def step(self, stream_ptr, mine, b, k, out_idx, out_score, out_count, out_flags):
+        N.check(N.lib().hdb_exchange_step(self._h, C.c_void_p(stream_ptr), C.c_void_p(mine.data_ptr()), mine.numel(), b, k,
+                                          C.c_void_p(out_idx.data_ptr()), C.c_void_p(out_score.data_ptr()),
+                                          C.c_void_p(out_count.data_ptr()), C.c_void_p(out_flags.data_ptr())))
+
+    def push(self, stream_ptr, mine):
+        N.check(N.lib().hdb_exchange_push(self._h, C.c_void_p(stream_ptr), C.c_void_p(mine.data_ptr()), mine.numel()))
+
+    def wait_merge(self, stream_ptr, b, k, out_idx, out_score, out_count, out_flags):
+        N.check(N.lib().hdb_exchange_wait_merge(self._h, C.c_void_p(stream_ptr), b, k, C.c_void_p(out_idx.data_ptr()),
+                                                C.c_void_p(out_score.data_ptr()), C.c_void_p(out_count.data_ptr()),
+                                                C.c_void_p(out_flags.data_ptr())))
+
+    def error(self) -> bool:
+        e = C.c_int()
+        N.check(N.lib().hdb_exchange_error(self._h, C.byref(e)))
+        return bool(e.value)
+
+    def close(self):
+        if self._h.value:
+            N.lib().hdb_exchange_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedMatrix:
     """engine: the local shard (CudaEngine in production); group: torch.distributed process group."""
 
@@ -128,6 +188,20 @@ class ShardedMatrix:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_total = int(n_total)
         self.exchanges = 0
+        self.xchg = None                      # PeerExchange (enable_peer_exchange), else torch.distributed all-gather
+
+    def enable_peer_exchange(self, max_batch=64, max_k=128):
+        """Exchange candidates through NVLink peer memory instead of an NCCL all-gather (CUDA engines, world > 1).
+        Collective: the IPC handles travel once through torch.distributed; batches that do not fit the exchange buffer
+        (more than max_batch queries or top_k > max_k) keep using the all-gather."""
+        if self.world == 1 or self.xchg is not None:
+            return
+        dev = self.engine.device
+        self.xchg = PeerExchange(dev.index, self.world, self.rank, packed_len(max_batch, max_k))
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, self.xchg.handle(), group=self.group)
+        self.xchg.connect(handles)
+        self.dist.barrier(group=self.group)
 
     def _comm_device(self):
         return getattr(self.engine, "device", "cpu")
@@ -199,6 +273,16 @@ class ShardedMatrix:
 
     def _exchange_and_merge(self, mine, b, k, post):
         import torch
+        if self.xchg is not None and mine.numel() <= self.xchg.max_words and k > 0:
+            w = self.world
+            out = torch.empty(2 * b * k + b + (w * b + 1) // 2, dtype=torch.int64, device=mine.device)   # [idx | score | count | flags]
+            idx = out[: b * k].view(b, k)
+            sc = out[b * k: 2 * b * k].view(torch.float64).view(b, k)
+            cnt = out[2 * b * k: 2 * b * k + b]
+            flags = out[2 * b * k + b:].view(torch.int32)[: w * b].view(w, b)
+            self.xchg.step(torch.cuda.current_stream(mine.device).cuda_stream, mine, b, k, idx, sc, cnt, flags)
+            self.exchanges += 1
+            return idx, sc, cnt, flags
         if self.world > 1:
             gathered = torch.empty(self.world * mine.numel(), dtype=mine.dtype, device=mine.device)
             self.dist.all_gather_into_tensor(gathered, mine, group=self.group)

@@ -47,6 +47,60 @@ def test_two_shards_one_gpu_merge():
             e.m.close()
 
 
+def test_peer_exchange_two_ranks_one_process():
+    """hdb_exchange_* with both ranks in this process (buffers connected by pointer instead of CUDA IPC): push with peer
+    stores, flag wait, merge; several steps so that the slot ring wraps, and each rank's step on its own stream."""
+    import torch
+    import hyperdb_b200 as hb
+    from hyperdb_b200.sharded import CudaEngine, PeerExchange, packed_len, shard_bounds
+    rng = np.random.default_rng(17)
+    n, d, k = 40_001, 48, 10
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    V[30_000] = V[7]                                        # tie across the shard boundary
+    Q = rng.standard_normal((11, d)).astype(np.float32)
+    Q[2] = V[7]
+    engines = []
+    for r in range(2):
+        lo, hi = shard_bounds(n, 2, r)
+        engines.append(CudaEngine(hb.DeviceMatrix(V[lo:hi], row_offset=lo)))
+    xs = [PeerExchange(0, 2, r, packed_len(4, 16)) for r in range(2)]
+    bufs = [x.local_buffer() for x in xs]
+    for x in xs:
+        x.connect_pointers(bufs)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    try:
+        for step, (b0, b1) in enumerate([(0, 1), (1, 4), (4, 5), (5, 8), (8, 9), (9, 11), (0, 3)]):     # 7 steps > 4 slots
+            b = b1 - b0
+            q = torch.as_tensor(Q[b0:b1]).cuda()
+            outs = []
+            mines = [engines[r].local_topk(q, k, "cosine_similarity", 0.0) for r in range(2)]
+            torch.cuda.synchronize()
+            for r in range(2):              # one process drives both ranks: every push before any wait (see the header)
+                xs[r].push(streams[r].cuda_stream, mines[r])
+            for r in range(2):
+                mine = mines[r]
+                out = torch.empty(2 * b * k + b + b, dtype=torch.int64, device="cuda")
+                idx, sc = out[: b * k].view(b, k), out[b * k: 2 * b * k].view(torch.float64).view(b, k)
+                cnt, flags = out[2 * b * k: 2 * b * k + b], out[2 * b * k + b:].view(torch.int32)[: 2 * b].view(2, b)
+                xs[r].wait_merge(streams[r].cuda_stream, b, k, idx, sc, cnt, flags)
+                outs.append((idx, sc, cnt, flags, mine))
+            torch.cuda.synchronize()
+            for r in range(2):
+                idx, sc, cnt, flags, _ = outs[r]
+                assert not xs[r].error()
+                assert not (flags.cpu().numpy() & 8).any()
+                for j in range(b):
+                    oi, os_ = K.rank(V, Q[b0 + j], k, "cosine_similarity")
+                    assert list(idx[j].cpu().numpy()) == list(oi), (step, r, j)
+                    np.testing.assert_allclose(sc[j].cpu().numpy(), os_, rtol=1e-5)
+                    assert int(cnt[j]) == k
+    finally:
+        for x in xs:
+            x.close()
+        for e in engines:
+            e.m.close()
+
+
 def test_pipelined_queries_match():
     """certify of query i on the post stream while the sweep of query i+1 runs: same answers, slot rotation exercised"""
     import torch
@@ -132,12 +186,30 @@ def _nccl_worker(rank, world, port, out_dir):
     sm = ShardedMatrix(CudaEngine(m), n)
     sm.refresh_decay()
     assert sm.total_kept() == int(keep.sum())
-    for metric in ("cosine_similarity", "euclidean_metric", "hamming_distance"):
-        idx, sc, cnt = sm.query(Q, 10, metric, 0.3)
-        for b in range(len(Q)):
-            oi, os_ = K.rank(V, Q[b], 10, metric, ts, 0.3, keep)
-            assert list(idx[b]) == list(oi), (metric, b)
-            np.testing.assert_allclose(sc[b], os_, rtol=1e-5)
+    for use_peer in (False, True):
+        if use_peer:
+            sm.enable_peer_exchange(max_batch=8, max_k=16)       # CUDA IPC between the ranks' processes
+        for metric in ("cosine_similarity", "euclidean_metric", "hamming_distance"):
+            for rep in range(3):                                 # 9 steps through a 4-slot ring
+                idx, sc, cnt = sm.query(Q, 10, metric, 0.3)
+                for b in range(len(Q)):
+                    oi, os_ = K.rank(V, Q[b], 10, metric, ts, 0.3, keep)
+                    assert list(idx[b]) == list(oi), (metric, b, use_peer)
+                    np.testing.assert_allclose(sc[b], os_, rtol=1e-5)
+    assert sm.xchg is not None and not sm.xchg.error()
+    # pipelined, back to back, no host synchronisation between the steps
+    sm.engine.enable_pipeline(True)
+    qd = torch.as_tensor(Q).cuda()
+    outs = [sm.query_async(qd[i % 2:i % 2 + 1], 10, "cosine_similarity", 0.3) for i in range(20)]
+    sm.wait_results()
+    torch.cuda.synchronize()
+    assert not sm.xchg.error()
+    for i, (idx, sc, cnt, flags) in enumerate(outs):
+        if (flags.cpu().numpy() & 8).any():
+            continue
+        oi, _ = K.rank(V, Q[i % 2], 10, "cosine_similarity", ts, 0.3, keep)
+        assert list(idx[0].cpu().numpy()) == list(oi), i
+    sm.engine.enable_pipeline(False)
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
