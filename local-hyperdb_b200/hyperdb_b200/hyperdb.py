@@ -17,7 +17,10 @@ arithmetic on the stored values.  Out of scope: embedding 
 """
 from __future__ import annotations
 
+import hashlib
+import sys
 import time
+from collections import OrderedDict
 
 import numpy as np
 
@@ -54,6 +57,12 @@ class HyperDB:
         self.source_indices = []
         self._matrix = None
         self._mask_cache = {}
+        # query cache (hyperdb/hyperdb.py:60-62, :1368-1388): same semantics, but the key is a 128-bit digest of the
+        # query's bytes instead of tuple(query.tolist()) -- O(D) C speed instead of D Python floats per lookup
+        self.cache_size = int(cache_size)
+        self.lru_cache = OrderedDict()
+        self.cache_hits = 0
+        self.cache_misses = 0
         if vectors is not None:
             if documents is None or len(documents) != len(vectors):
                 raise ValueError("documents and vectors must have the same length")
@@ -66,6 +75,7 @@ class HyperDB:
 
     # -- storage ---------------------------------------------------------------------------------
     def _upload(self):
+        self.clear_cache()
         if self._matrix is not None:
             self._matrix.close()
         self._matrix = DeviceMatrix(self.vectors, device=self.device) if self.vectors is not None and len(self.vectors) else None
@@ -98,6 +108,7 @@ class HyperDB:
             self._matrix.append(vectors)                     # device side: only the new rows are copied and ingested
             self.vectors = np.concatenate([self.vectors, vectors])
             self._mask_cache.clear()
+            self.clear_cache()                               # hyperdb/hyperdb.py:566
         base = len(self.documents)
         self.documents.extend(documents)
         self.source_indices.extend(range(base, base + len(documents)))
@@ -112,11 +123,46 @@ class HyperDB:
         if self._matrix is not None and len(self.vectors):
             self._matrix.remove_rows(np.flatnonzero(~keep))  # stable compaction on the device, no re-upload
             self._mask_cache.clear()
+            self.clear_cache()                               # hyperdb/hyperdb.py:766
         else:
             self._upload()
 
     def size(self):
         return len(self.documents)
+
+    # -- query cache ---------------------------------------------------------------------------------
+    def clear_cache(self):
+        """hyperdb/hyperdb.py:1390-1396."""
+        self.lru_cache.clear()
+        self.cache_hits = 0
+        self.cache_misses = 0
+
+    def get_cache_size_and_info(self):
+        """hyperdb/hyperdb.py:1398-1427 (sizes from sys.getsizeof instead of pympler)."""
+        nbytes = sys.getsizeof(self.lru_cache) + sum(sys.getsizeof(k) + sys.getsizeof(v) for k, v in self.lru_cache.items())
+        if nbytes >= 1024 * 1024:
+            size = f"{nbytes / (1024 * 1024):.2f} MB"
+        elif nbytes >= 1024:
+            size = f"{nbytes / 1024:.2f} KB"
+        else:
+            size = f"{int(nbytes)} bytes"
+        return {"cache_info": {"hits": self.cache_hits, "misses": self.cache_misses, "maxsize": self.cache_size,
+                               "currsize": len(self.lru_cache)}, "cache_memory_size": size}
+
+    @staticmethod
+    def _hashable_key(query_input, top_k, return_similarities, filters, recency_bias, timestamp_key, metric, ann_percent):
+        """hyperdb/hyperdb.py:1368-1379 with the array turned into a digest (value-equal float64 queries share a key, as
+        tuple(tolist()) keys do)."""
+        if isinstance(query_input, (np.ndarray, list, tuple)):
+            q = np.ascontiguousarray(np.asarray(query_input, dtype=np.float64))
+            query_input = (q.shape, hashlib.blake2b(q.tobytes(), digest_size=16).digest())
+        if filters is None:
+            hashable_filters = None
+        else:
+            hashable_filters = tuple(
+                (name, tuple(sorted(params.items())) if isinstance(params, dict) else tuple(params) if isinstance(params, list) else params)
+                for name, params in filters)
+        return (query_input, top_k, return_similarities, hashable_filters, recency_bias, timestamp_key, metric, ann_percent)
 
     def close(self):
         if self._matrix is not None:
@@ -192,6 +238,23 @@ class HyperDB:
             raise Exception("The database is empty. Cannot proceed with the query.")
         if metric not in _METRICS:
             raise ValueError(f"Invalid metric '{metric}'. Supported: 'dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_distance', 'jaccard_similarity', 'pearson_correlation', 'hamming_distance'")
+        key = None
+        if self.cache_size > 0:
+            key = self._hashable_key(query_input, top_k, return_similarities, filters, recency_bias, timestamp_key, metric, ann_percent)
+            if key in self.lru_cache:                        # hyperdb/hyperdb.py:1381-1384
+                self.cache_hits += 1
+                self.lru_cache.move_to_end(key)
+                return self.lru_cache[key]
+            self.cache_misses += 1
+        results = self._execute_query(query_input, top_k, return_similarities, filters, recency_bias, timestamp_key, metric)
+        if key is not None:
+            self.lru_cache[key] = results
+            if len(self.lru_cache) > self.cache_size:
+                self.lru_cache.popitem(last=False)
+        return results
+
+    def _execute_query(self, query_input, top_k, return_similarities, filters, recency_bias, timestamp_key, metric):
+        """hyperdb/hyperdb.py:1429-1582, brute-force branch."""
         try:
             q = self._query_vector(query_input)
             lo, hi, keep = self._apply_filters(filters)

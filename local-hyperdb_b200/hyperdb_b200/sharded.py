@@ -40,6 +40,8 @@ class CudaEngine:
         self.torch = torch
         self.device = torch.device("cuda", matrix.device)
         self.post = None                      # torch stream of the pipelined certify / exchange / merge
+        self._path = 0
+        self._qdt = {torch.float16: N.HDB_F16, torch.float32: N.HDB_F32, torch.float64: N.HDB_F64}
 
     def enable_pipeline(self, on=True):
         """Run certify / exchange / merge of query i on a second stream while the sweep of query i+1 streams the matrix."""
@@ -80,18 +82,18 @@ class CudaEngine:
         """-> packed int64 CUDA tensor [packed_len(B, k)] (scores bit-cast)."""
         torch = self.torch
         q = queries if torch.is_tensor(queries) else torch.as_tensor(queries)
-        q = q.to(self.device).contiguous()
+        if q.device != self.device or not q.is_contiguous():
+            q = q.to(self.device).contiguous()
         b = 1 if q.dim() == 1 else q.shape[0]
         buf = torch.empty(packed_len(b, k), dtype=torch.int64, device=self.device)
-        sc = buf[: b * k].view(torch.float64)
-        ids = buf[b * k: 2 * b * k]
-        cnt = buf[2 * b * k: 2 * b * k + b]
-        flags = buf[2 * b * k + b:].view(torch.int32)
-        self.m.set_path(1 if exact else 0)
-        try:
-            self.m.query_device(q, k, metric, bias, ids, sc, cnt, flags)
-        finally:
-            self.m.set_path(0)
+        # [scores b*k | ids b*k | counts b | flags]: addresses by arithmetic (this runs once per query: no tensor views)
+        base = buf.data_ptr()
+        want = 1 if exact else 0
+        if want != self._path:
+            self.m.set_path(want)
+            self._path = want
+        N.check(N.lib().hdb_query(self.m._h, N.METRIC_IDS[metric], q.data_ptr(), self._qdt[q.dtype], N.HDB_DEVICE, b, int(k), float(bias),
+                                  base + 8 * b * k, base, base + 16 * b * k, base + 16 * b * k + 8 * b, N.HDB_DEVICE))
         return buf
 
     def merge(self, gathered, b, k):
@@ -174,6 +176,33 @@ class PeerExchange:
             self.close()
         except Exception:
             pass
+
+
+class StepResult:
+    """(idx [b,k], score [b,k], count [b], per-shard flags [world,b]) of one sharded query step as views of ONE device
+    block [idx | score | count | flags]; the views are only built when somebody looks (a pipelined loop that keeps the
+    results on the device pays one allocation per step).  Unpacks like the 4-tuple it replaces."""
+    __slots__ = ("block", "b", "k", "w", "_views")
+
+    def __init__(self, block, b, k, w):
+        self.block, self.b, self.k, self.w, self._views = block, b, k, w, None
+
+    def views(self):
+        if self._views is None:
+            import torch
+            o, b, k, w = self.block, self.b, self.k, self.w
+            self._views = (o[: b * k].view(b, k), o[b * k: 2 * b * k].view(torch.float64).view(b, k), o[2 * b * k: 2 * b * k + b],
+                           o[2 * b * k + b:].view(torch.int32)[: w * b].view(w, b))
+        return self._views
+
+    def __iter__(self):
+        return iter(self.views())
+
+    def __getitem__(self, i):
+        return self.views()[i]
+
+    def __len__(self):
+        return 4
 
 
 class ShardedMatrix:
@@ -267,7 +296,7 @@ class ShardedMatrix:
         if post is not None:
             # pipelined: `mine` is completed on the post stream; exchange and merge follow it there
             mine.record_stream(post)
-            with torch.cuda.stream(post):
+            with torch.cuda.stream(post):       # allocations made here belong to the post stream
                 return self._exchange_and_merge(mine, b, k, post)
         return self._exchange_and_merge(mine, b, k, None)
 
@@ -276,13 +305,12 @@ class ShardedMatrix:
         if self.xchg is not None and mine.numel() <= self.xchg.max_words and k > 0:
             w = self.world
             out = torch.empty(2 * b * k + b + (w * b + 1) // 2, dtype=torch.int64, device=mine.device)   # [idx | score | count | flags]
-            idx = out[: b * k].view(b, k)
-            sc = out[b * k: 2 * b * k].view(torch.float64).view(b, k)
-            cnt = out[2 * b * k: 2 * b * k + b]
-            flags = out[2 * b * k + b:].view(torch.int32)[: w * b].view(w, b)
-            self.xchg.step(torch.cuda.current_stream(mine.device).cuda_stream, mine, b, k, idx, sc, cnt, flags)
+            base = out.data_ptr()
+            stream = post.cuda_stream if post is not None else torch.cuda.current_stream(mine.device).cuda_stream
+            N.check(N.lib().hdb_exchange_step(self.xchg._h, stream, mine.data_ptr(), mine.numel(), b, k, base, base + 8 * b * k,
+                                              base + 16 * b * k, base + 16 * b * k + 8 * b))
             self.exchanges += 1
-            return idx, sc, cnt, flags
+            return StepResult(out, b, k, w)
         if self.world > 1:
             gathered = torch.empty(self.world * mine.numel(), dtype=mine.dtype, device=mine.device)
             self.dist.all_gather_into_tensor(gathered, mine, group=self.group)

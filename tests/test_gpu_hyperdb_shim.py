@@ -51,3 +51,36 @@ def test_add_remove_roundtrip():
     db.remove_document(41)
     assert db.size() == 49 and db.query(V[41], top_k=1)[0][0]["id"] != 41
     db.close()
+
+
+def test_query_cache_semantics(capsys):
+    """hyperdb/hyperdb.py:1368-1396: repeated queries are served from the LRU (keyed on a digest of the query bytes here),
+    value-equal queries of another dtype share the entry (the reference's tuple(tolist()) key is float64 too), mutations
+    clear it, cache_size bounds it."""
+    from hyperdb_b200.hyperdb import HyperDB
+    rng = np.random.default_rng(5)
+    V = rng.standard_normal((300, 16)).astype(np.float32)
+    docs = [{"id": i} for i in range(len(V))]
+    db = HyperDB(documents=docs, vectors=V, cache_size=2)
+    try:
+        q = rng.standard_normal(16).astype(np.float32)
+        r1 = db.query(q, top_k=4)
+        capsys.readouterr()
+        r2 = db.query(q.astype(np.float64), top_k=4)              # same values: same key
+        assert "Bruteforce" not in capsys.readouterr().out        # served from the cache: _execute_query did not run
+        assert r2 is r1 and (db.cache_hits, db.cache_misses) == (1, 1)
+        db.query(q, top_k=5)
+        db.query(q, top_k=6)                                      # evicts the top_k=4 entry (maxsize 2)
+        info = db.get_cache_size_and_info()["cache_info"]
+        assert info == {"hits": 1, "misses": 3, "maxsize": 2, "currsize": 2}
+        db.query(q, top_k=4)
+        assert db.cache_misses == 4
+        db.add([{"id": 300}], vectors=rng.standard_normal((1, 16)).astype(np.float32))
+        assert len(db.lru_cache) == 0 and db.cache_misses == 0    # clear_cache() on mutation, as the reference
+        nocache = HyperDB(documents=docs, vectors=V, cache_size=0)
+        nocache.query(q, top_k=3)
+        nocache.query(q, top_k=3)
+        assert nocache.cache_hits == 0 and len(nocache.lru_cache) == 0
+        nocache.close()
+    finally:
+        db.close()

@@ -1,0 +1,34 @@
+"""Host-side logic that needs no GPU: the query-cache key of the HyperDB shim (hyperdb/hyperdb.py:1368-1379), the lazy
+result views of a sharded step, message sizes."""
+import numpy as np
+
+from hyperdb_b200.hyperdb import HyperDB
+from hyperdb_b200.sharded import StepResult, packed_len
+
+
+def test_cache_key_is_value_based_and_hashable():
+    key = HyperDB._hashable_key
+    q32 = np.array([0.25, -1.5, 3.0], np.float32)
+    base = key(q32, 5, True, None, 0, None, "cosine_similarity", 5)
+    assert base == key(q32.astype(np.float64), 5, True, None, 0, None, "cosine_similarity", 5)      # tuple(tolist()) would match too
+    assert base == key(q32.tolist(), 5, True, None, 0, None, "cosine_similarity", 5)
+    assert base != key(q32 + 1e-6, 5, True, None, 0, None, "cosine_similarity", 5)
+    assert base != key(q32, 6, True, None, 0, None, "cosine_similarity", 5)
+    assert base != key(q32.reshape(1, 3), 5, True, None, 0, None, "cosine_similarity", 5)           # shape is part of the key
+    f1 = [("metadata", {"group": "a", "lang": "en"}), ("skip_doc", 3)]
+    f2 = [("metadata", {"lang": "en", "group": "a"}), ("skip_doc", 3)]
+    assert key(q32, 5, True, f1, 0.3, "timestamp", "dot_product", 5) == key(q32, 5, True, f2, 0.3, "timestamp", "dot_product", 5)
+    hash(key(q32, 5, True, f1, 0.3, "timestamp", "dot_product", 5))
+    assert key("some text", 5, True, None, 0, None, "cosine_similarity", 5)[0] == "some text"
+
+
+def test_step_result_views():
+    import torch
+    b, k, w = 3, 4, 2
+    block = torch.arange(2 * b * k + b + (w * b + 1) // 2, dtype=torch.int64)
+    r = StepResult(block, b, k, w)
+    idx, sc, cnt, flags = r
+    assert idx.shape == (b, k) and sc.shape == (b, k) and sc.dtype == torch.float64 and cnt.shape == (b,) and flags.shape == (w, b)
+    assert idx.data_ptr() + 8 * b * k == sc.data_ptr()          # ShardedMatrix.query copies [idx | score | count] in one piece
+    assert r[3] is flags and len(r) == 4
+    assert packed_len(b, k) == 2 * b * k + b + 2
