@@ -186,6 +186,10 @@ int hdb_matrix_destroy(hdb_matrix* m) {
   if (!m) return 0;
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
+  // pipelined queries may still be running on the internal / post streams: nothing is freed under them
+  if (m->pre_stream) cudaStreamSynchronize(m->pre_stream);
+  if (m->alt_stream) cudaStreamSynchronize(m->alt_stream);
+  if (m->post_stream) cudaStreamSynchronize(m->post_stream);
   if (m->owns_rows) cudaFree(m->rows);
   slot_store(m);
   {

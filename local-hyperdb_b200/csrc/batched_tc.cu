@@ -226,6 +226,7 @@ struct TcParams : TcParamsBase {
   unsigned* rec_count;          // [gridDim.x]
   unsigned rec_cap;
   int debug;                    // HDB_TC_DEBUG: 1 = epilogue drains TMEM but skips the compare/append (timing experiments)
+  int prefetch_dist;            // row tiles between the L2 bulk prefetch and its use (single-CTA form)
 };
 
 template <int BN, bool TF32, bool DENSE>
@@ -284,14 +285,19 @@ batched_tc_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_consta
         if (mv >= p.n_tiles_m) break;
         const int64_t mt = mv * p.sample_stride;
         const int64_t qt = sq % p.n_tiles_q;
-        if (qt == 0 && mv + gridDim.x < p.n_tiles_m) {
-          // The TMA boxes below gather 128-byte pieces of 128 rows (poor DRAM locality when they miss L2).  The
-          // row tile itself is ONE contiguous region: stream the NEXT one into L2 now with a bulk prefetch.
-          const int64_t mtn = (mv + gridDim.x) * p.sample_stride;
-          const int64_t rows_n = (p.n - mtn * kTileM) < kTileM ? (p.n - mtn * kTileM) : kTileM;
-          const int64_t region = (rows_n * row_bytes) & ~int64_t(15);
-          if (region > 0)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rows + mtn * kTileM * row_bytes), "r"((uint32_t)region) : "memory");
+        if (qt == 0) {
+          // The TMA boxes below gather 128-byte pieces of 128 rows (poor DRAM locality when they miss L2).  A row
+          // tile itself is ONE contiguous region: stream the tile `prefetch_dist` visits ahead into L2 now with a
+          // bulk prefetch (on the first visit also the ones in between).
+          for (int ahead = (sq == 0 ? 1 : p.prefetch_dist); ahead <= p.prefetch_dist; ++ahead) {
+            const int64_t mvn = mv + (int64_t)ahead * gridDim.x;
+            if (mvn >= p.n_tiles_m) break;
+            const int64_t mtn = mvn * p.sample_stride;
+            const int64_t rows_n = (p.n - mtn * kTileM) < kTileM ? (p.n - mtn * kTileM) : kTileM;
+            const int64_t region = (rows_n * row_bytes) & ~int64_t(15);
+            if (region > 0)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rows + mtn * kTileM * row_bytes), "r"((uint32_t)region) : "memory");
+          }
         }
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -740,6 +746,8 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
   p.n_tiles_q = (nq + BN - 1) / BN;
   p.rows = reinterpret_cast<const char*>(m.rows);
   p.debug = getenv("HDB_TC_DEBUG") ? atoi(getenv("HDB_TC_DEBUG")) : 0;
+  p.prefetch_dist = getenv("HDB_TC_PREFETCH_DIST") ? atoi(getenv("HDB_TC_PREFETCH_DIST")) : 1;
+  if (p.prefetch_dist < 1) p.prefetch_dist = 1;
   p.inv_norms = metric == HDB_COSINE ? reinterpret_cast<const float*>(m.inv_norms) : nullptr;
   p.sqnorms = nullptr; p.qsq = nullptr;
   if (metric == HDB_EUCLIDEAN) {

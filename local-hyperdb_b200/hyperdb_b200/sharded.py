@@ -332,6 +332,8 @@ class ShardedMatrix:
         idx, sc, cnt, flags = self.query_async(queries, top_k, metric, recency_bias)
         self.wait_results()
         flags = flags.cpu().numpy()
+        if self.xchg is not None and self.xchg.error():
+            raise RuntimeError("peer-memory exchange: a rank did not deliver its candidates within 10 s")
         if (flags & N.FLAG_QUERY_NAN).any():
             raise ValueError("Vectors and query_vector should not contain NaN values.")
         if (flags & N.FLAG_UNCERTIFIED).any():      # every rank sees every flag after the all-gather: same branch everywhere
