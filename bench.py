@@ -269,7 +269,13 @@ def main():
     eng = CudaEngine(m)
     sm = ShardedMatrix(eng, w["n"])
     if world > 1 and args.exchange == "peer":
-        sm.enable_peer_exchange(max_batch=w["b"], max_k=w["k"])
+        # CUDA IPC between the ranks' processes; if the box forbids it, every rank fails here alike and the run
+        # continues on the NCCL all-gather (reported in config.exchange)
+        try:
+            sm.enable_peer_exchange(max_batch=w["b"], max_k=w["k"])
+        except Exception as e:                                   # noqa: BLE001
+            print(f"bench.py: peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+            sm.xchg = None
     if not args.no_pipeline and w["b"] < 2:
         eng.enable_pipeline()            # certify/exchange/merge of query i overlap the sweep of query i+1
         m.set_sweep_overlap(not args.no_overlap)     # ... and the head of sweep i+1 fills the tail of sweep i

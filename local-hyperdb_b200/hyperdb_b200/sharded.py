@@ -224,13 +224,33 @@ class ShardedMatrix:
         Collective: the IPC handles travel once through torch.distributed; batches that do not fit the exchange buffer
         (more than max_batch queries or top_k > max_k) keep using the all-gather."""
         if self.world == 1 or self.xchg is not None:
-            return
+            return self.xchg is not None
+        import torch
         dev = self.engine.device
-        self.xchg = PeerExchange(dev.index, self.world, self.rank, packed_len(max_batch, max_k))
+        xchg, err = None, None
+        try:
+            xchg = PeerExchange(dev.index, self.world, self.rank, packed_len(max_batch, max_k))
+            mine = xchg.handle()
+        except Exception as e:                                   # noqa: BLE001
+            mine, err = None, e
         handles = [None] * self.world
-        self.dist.all_gather_object(handles, self.xchg.handle(), group=self.group)
-        self.xchg.connect(handles)
-        self.dist.barrier(group=self.group)
+        self.dist.all_gather_object(handles, mine, group=self.group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                xchg.connect(handles)
+            except Exception as e:                               # noqa: BLE001
+                err = e
+        # every rank must take the same decision: one failed mapping switches the whole group back to the all-gather
+        ok = torch.tensor([0 if (err is not None or any(h is None for h in handles)) else 1], dtype=torch.int32, device=dev)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            if xchg is not None:
+                xchg.close()
+            if err is not None:
+                raise RuntimeError(f"peer-memory exchange unavailable on rank {self.rank}: {err}")
+            raise RuntimeError("peer-memory exchange unavailable on another rank")
+        self.xchg = xchg
+        return True
 
     def _comm_device(self):
         return getattr(self.engine, "device", "cpu")
