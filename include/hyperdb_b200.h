@@ -72,7 +72,9 @@ int hdb_matrix_set_stream(hdb_matrix* m, void* cuda_stream);
 /* Query pipelining for device-output calls.  With a post stream set, hdb_query(..., HDB_DEVICE) enqueues the query
  * preparation and the streaming sweep on the handle's stream and the certify step on `post_stream`, so that the
  * certify (and whatever the caller enqueues after it on the post stream: the candidate exchange, the merge) of query i
- * overlaps the sweep of query i+1.  Results are valid in POST-stream order.  NULL switches pipelining off. */
+ * overlaps the sweep of query i+1.  Results are valid in POST-stream order.  NULL switches pipelining off.
+ * Give the post stream a HIGH priority (cudaStreamCreateWithPriority): its small kernels then take the SMs a finishing
+ * sweep vacates before the next query's pending sweep CTAs do. */
 int hdb_matrix_set_post_stream(hdb_matrix* m, void* post_stream);
 /* Pipelined mode only: let the sweeps of consecutive queries overlap (default on).  Odd-numbered queries sweep on an
  * internal second stream, so the next query's CTAs fill the SMs the current one vacates during its tail.  Results are

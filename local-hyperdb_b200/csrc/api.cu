@@ -232,7 +232,16 @@ int hdb_matrix_set_post_stream(hdb_matrix* m, void* cuda_stream) {
     if (!m->ev_alt) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_alt, cudaEventDisableTiming));
     if (!m->ev_select) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_select, cudaEventDisableTiming));
     if (!m->ev_prep) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_prep, cudaEventDisableTiming));
-    if (!m->pre_stream) HDB_CUDA(cudaStreamCreateWithFlags(&m->pre_stream, cudaStreamNonBlocking));
+    if (!m->pre_stream) {
+      // The small kernels must not queue behind the NEXT query's sweep CTAs when the current sweep's CTAs leave the SMs:
+      // query preparation runs on a high-priority stream (the caller should give the post stream a high priority too)
+      int least = 0, greatest = 0;
+      if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess ||
+          cudaStreamCreateWithPriority(&m->pre_stream, cudaStreamNonBlocking, greatest) != cudaSuccess) {
+        cudaGetLastError();
+        HDB_CUDA(cudaStreamCreateWithFlags(&m->pre_stream, cudaStreamNonBlocking));
+      }
+    }
     for (auto& q : m->slots)
       if (!q.done) HDB_CUDA(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
     m->grid = sweep_grid_size(m->device) - 2;     // leave room on one SM for the certify / exchange / merge kernels

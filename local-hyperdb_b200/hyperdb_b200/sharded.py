@@ -46,7 +46,9 @@ class CudaEngine:
     def enable_pipeline(self, on=True):
         """Run certify / exchange / merge of query i on a second stream while the sweep of query i+1 streams the matrix."""
         if on and self.post is None:
-            self.post = self.torch.cuda.Stream(device=self.device)
+            # high priority: when a sweep's CTAs leave the SMs, certify / exchange / merge are scheduled before the next
+            # query's pending sweep CTAs
+            self.post = self.torch.cuda.Stream(device=self.device, priority=-1)
             self.m.set_post_stream(self.post.cuda_stream)
         elif not on and self.post is not None:
             self.torch.cuda.current_stream(self.device).wait_stream(self.post)
