@@ -584,6 +584,7 @@ extern "C" int hdb_matrix_remove_rows(hdb_matrix* m, const int64_t* local_rows, 
   if (m->rows && !m->owns_rows) return fail("hdb_matrix_remove_rows: the shard uses adopted memory");
   if (count < 0) return fail("hdb_matrix_remove_rows: negative count");
   if (count == 0 || m->n == 0) return count == 0 ? 0 : fail("hdb_matrix_remove_rows: row index out of range");
+  if (m->n > 0x7fffffff) return fail("hdb_matrix_remove_rows: more than 2^31 rows per shard");
   if (!local_rows) return fail("hdb_matrix_remove_rows: NULL rows");
   HDB_TRY(quiesce(m));
   const int64_t n = m->n;

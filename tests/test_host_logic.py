@@ -32,3 +32,22 @@ def test_step_result_views():
     assert idx.data_ptr() + 8 * b * k == sc.data_ptr()          # ShardedMatrix.query copies [idx | score | count] in one piece
     assert r[3] is flags and len(r) == 4
     assert packed_len(b, k) == 2 * b * k + b + 2
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c2_cosine_b1",
+                          "--rows", "20000", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "queries/s" and j["higher_is_better"] is True
+    assert j["value"] > 0 and j["steps"] == 1 and j["config"]["workload"] == "c2_cosine_b1"
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

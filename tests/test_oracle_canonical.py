@@ -66,3 +66,33 @@ def test_pairwise_sum_matches_numpy_reduce():
             x = (rng.standard_normal((50, d)) * 3).astype(dt)
             assert K.row_sum(x).tobytes() == np.add.reduce(x, axis=1).tobytes()
             assert K.row_norm(x).tobytes() == np.linalg.norm(x, axis=1).tobytes()
+
+
+def test_mean_std_match_numpy():
+    """np.mean / np.std spelled out (numpy/_core/_methods.py::_mean, _var, _std) -- the per-row statistics of
+    pearson_correlation (hyperdb/ranking_algorithm.py:90-94), array form (axis=1) and scalar form (1-D query)."""
+    rng = np.random.default_rng(2)
+    for d in (1, 2, 7, 8, 9, 100, 128, 129, 384, 1000):
+        for dt in (np.float16, np.float32, np.float64):
+            for scale, shift in ((1.0, 0.0), (0.03, 0.5), (4.0, -20.0)):
+                x = (rng.standard_normal((40, d)) * scale + shift).astype(dt)
+                with np.errstate(all="ignore"):
+                    assert K.row_mean(x).tobytes() == np.mean(x, axis=1).tobytes(), (d, dt, scale)
+                    assert K.row_std(x).tobytes() == np.std(x, axis=1).tobytes(), (d, dt, scale)
+                    for r in (0, 17):
+                        assert K.row_mean(x[r][None, :], scalar=True)[0].tobytes() == np.mean(x[r]).tobytes()
+                        assert K.row_std(x[r][None, :])[0].tobytes() == np.std(x[r]).tobytes()
+
+
+def test_pearson_edge_cases_match_port():
+    from oracle import reference_port as P
+    rng = np.random.default_rng(3)
+    for vdt, qdt in ((np.float16, np.float16), (np.float16, np.float64), (np.float32, np.float32), (np.float32, np.float64), (np.float64, np.float32)):
+        V = (rng.standard_normal((50, 24)) * 2 + 1).astype(vdt)
+        V[3] = 0.75                                   # constant row -> NaN
+        V[4] = 0
+        V[5] = V[5] * 1e-4                            # tiny std: float16 denominators can underflow to zero -> 0.0, not NaN
+        for q in ((rng.standard_normal(24) + 0.5).astype(qdt), np.full(24, 0.5, qdt)):
+            with np.errstate(all="ignore"):
+                ref = P.pearson_scores(V, q)
+            assert np.array_equal(K.pearson(V, q), ref, equal_nan=True), (vdt, qdt)
