@@ -439,10 +439,12 @@ int launch_finalize(const FinalizeArgs& a_in, int64_t nq, cudaStream_t s) {
   if (want > 160 * 1024) want = 160 * 1024;
   if (want < qbytes + row_pitch || a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) want = 0;
   a.smem_bytes = (int)want;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};           // the attribute belongs to a device's context: one process may hold shards on several
+  int dev = 0;
+  HDB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     HDB_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   finalize_kernel<<<(unsigned)nq, kFinThreads, (size_t)a.smem_bytes, s>>>(a);
   HDB_LAUNCHED();
