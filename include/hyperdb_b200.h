@@ -119,16 +119,19 @@ int hdb_matrix_stage1_recency(hdb_matrix* m, double bias1, double ts_max);
 /* n_queries independent queries (row-major n_queries x dim, dtype q_dtype) against the shard.
  * For query b: out_count[b] = min(top_k, kept rows); out_idx[b*top_k + j] = GLOBAL row id and
  * out_score[b*top_k + j] = float64 score of rank j, ordered by (score desc, row id asc).
- * Scores are the reference's arithmetic (see DESIGN.md "canonical scores").
- * out_flags may be NULL.  All outputs live in `out_space`. */
+ * Scores are the reference's arithmetic (see DESIGN.md "canonical scores"); NaN similarities (jaccard 0/0, pearson of a
+ * constant row or query) rank last as -inf (ranking_algorithm.py:174).  metric is one of HDB_DOT .. HDB_PEARSON.
+ * out_flags may be NULL.  All outputs live in `out_space`.  With device outputs nothing is synchronised and a query
+ * whose certificate failed only carries HDB_FLAG_UNCERTIFIED; with host outputs it is repaired before the call returns. */
 int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q_space,
               int64_t n_queries, int64_t top_k, double recency_bias,
               int64_t* out_idx, double* out_score, int64_t* out_count, uint32_t* out_flags,
               int out_space);
 
-/* ---- full similarity vector: the metric functions themselves, ranking_algorithm.py:24-61,:128-147 */
+/* ---- full similarity vector: the metric functions themselves, ranking_algorithm.py:24-113,:128-147 */
 /* out holds n_rows values of the NumPy result dtype promote(matrix dtype, q_dtype)
- * (uint64 for HDB_HAMMING, float64 for HDB_JACCARD), reported through *out_dtype (HDB_F16/F32/F64; 3 = uint64). */
+ * (uint64 for HDB_HAMMING, float64 for HDB_JACCARD and HDB_PEARSON, NaN where the reference returns NaN),
+ * reported through *out_dtype (HDB_F16/F32/F64; 3 = uint64). */
 int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_space,
                void* out, int out_space, int* out_dtype);
 /* L2-normalised copy of `n_rows` x `dim` values (get_norm_vector, ranking_algorithm.py:8-21). */
