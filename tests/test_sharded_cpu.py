@@ -74,6 +74,42 @@ def _worker(rank, world, port, fail_first, result_dir):
         assert list(idx[b]) == list(oi) and np.array_equal(sc[b], os_)
     with pytest.raises(IndexError):
         sm.remove_rows([n + 100])
+    # enable_peer_exchange is collective-safe: if ONE rank cannot map its peers, EVERY rank raises (nobody is left waiting
+    # in a collective) and the all-gather path stays in force; if all succeed, all switch.  (PeerExchange itself needs CUDA
+    # IPC: a stand-in with the same interface is patched in.)
+    import hyperdb_b200.sharded as S
+
+    class FakeExchange:
+        fail_on = None
+
+        def __init__(self, device_index, world_, rank_, max_words):
+            self.rank, self.max_words, self.closed = rank_, max_words, False
+
+        def handle(self):
+            return bytes([self.rank]) * 8
+
+        def connect(self, handles):
+            assert [h[0] for h in handles] == list(range(world))
+            if FakeExchange.fail_on == self.rank:
+                raise RuntimeError("cudaIpcOpenMemHandle failed")
+
+        def close(self):
+            self.closed = True
+
+    real, S.PeerExchange = S.PeerExchange, FakeExchange
+    eng.device = torch.device("cpu")
+    try:
+        FakeExchange.fail_on = 1
+        with pytest.raises(RuntimeError):
+            sm.enable_peer_exchange(max_batch=4, max_k=8)
+        assert sm.xchg is None
+        idx, sc, cnt = sm.query(Q[1:], 9, "euclidean_metric")         # still answers through the all-gather
+        assert list(idx[0]) == list(K.rank(V2, Q[1], 9, "euclidean_metric")[0])
+        FakeExchange.fail_on = None
+        assert sm.enable_peer_exchange(max_batch=4, max_k=8) is True and isinstance(sm.xchg, FakeExchange)
+        sm.xchg = None
+    finally:
+        S.PeerExchange = real
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
