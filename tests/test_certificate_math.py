@@ -1,0 +1,71 @@
+"""The pearson certificate of csrc/finalize.cu (outsider_bound, HDB_PEARSON branch) restated in NumPy and checked
+against the oracle: for every row, the reference's value must not exceed the bound computed from the sweep's own (fp32 /
+fp64) score and the ingest statistics.  A violated bound would mean a row outside the candidate list could belong to the
+top-k without the certificate noticing -- this runs on the CPU, the GPU tests check the resulting indices."""
+import numpy as np
+import pytest
+
+from oracle import canonical as K
+
+U = {np.float16: 2.0 ** -11, np.float32: 2.0 ** -24, np.float64: 2.0 ** -53}
+
+
+def bound_and_canon(rng, sdt, qdt, n, d, scale, shift):
+    V = (rng.standard_normal((n, d)) * scale * rng.uniform(0.2, 3, (n, 1)) + shift * rng.uniform(-1, 1, (n, 1))).astype(sdt)
+    q = (rng.standard_normal(d) * scale + shift).astype(qdt)
+    R = np.promote_types(sdt, qdt).type
+    with np.errstate(all="ignore"):
+        canon = K.pearson(V, q)
+        vmean = K.row_mean(V).astype(np.float64)
+        vstd = K.row_std(V).astype(np.float64)
+        qmean = K.row_mean(q[None, :], scalar=True)[0]
+        qstd = float(K.row_std(q[None, :])[0])
+    ok = (vstd > 0) & np.isfinite(vstd) & np.isfinite(canon)
+    if not ok.any() or not (qstd > 0):
+        return None
+    b = q - qmean                                            # in the query's dtype, as prep_query stores it
+    acc = np.float64 if sdt == np.float64 else np.float32   # the sweep's accumulate type
+    b_acc = b.astype(acc)
+    sumb = float(np.sum(b_acc.astype(np.float64)))
+    with np.errstate(all="ignore"):
+        t = (V.astype(acc) @ b_acc).astype(acc)
+        pscale = (1.0 / (vstd * d)).astype(acc)
+        sweep = ((t - vmean.astype(acc) * acc(sumb)) * acc(1.0 / qstd) * pscale).astype(np.float32).astype(np.float64)
+    Vd = V.astype(np.float64)
+    max_pratio = np.max(np.linalg.norm(Vd[ok], axis=1) / (vstd[ok] * np.sqrt(d))) * (1 + 1e-6)
+    max_cratio = np.max(np.linalg.norm(Vd[ok] - vmean[ok, None], axis=1) / (vstd[ok] * np.sqrt(d))) * (1 + 1e-6)
+    min_std = np.min(vstd[ok]) * (1 - 1e-6)
+    qn = np.linalg.norm(b.astype(np.float64)) / (qstd * np.sqrt(d))
+    D = d + 8.0
+    ua = 4.440892098500626e-16 if sdt == np.float64 else 2.0 ** -23
+    uk, uT, uR = 2.0 ** -23, U[sdt], U[R]
+    uaccR = 2.0 ** -53 if R == np.float64 else 2.0 ** -24
+    A, Ac = max_pratio * qn, max_cratio * qn
+    s = sweep[ok]
+    bound = s + np.abs(s) * uk + A * ((D + 16) * ua + 2.0 ** -23) + Ac * 1.05 * (uT + uR + D * uaccR)
+    bound = bound + 6 * uR * np.abs(bound)
+    if R == np.float16 or sdt == np.float16:
+        max_norm = np.max(np.linalg.norm(Vd, axis=1))
+        if not (min_std * qstd > 2.44140625e-4) or not (max_norm * np.sqrt(D) * qstd * max(1.0, 2 * A) < 3.0e4):
+            return None                                      # the kernel refuses to certify (exact path)
+        bound = bound + 2.0 ** -25 * (qn / min_std + 1.0 / (min_std * qstd)) * 1.5
+    return canon[ok], s, bound
+
+
+@pytest.mark.parametrize("sdt", [np.float16, np.float32, np.float64])
+@pytest.mark.parametrize("qdt", [np.float16, np.float32, np.float64])
+def test_pearson_bound_covers_the_reference(sdt, qdt):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32((sdt.__name__ + qdt.__name__).encode()))
+    checked = 0
+    for d in (8, 33, 96, 384, 1536):
+        for scale, shift in ((1.0, 0.0), (0.04, 0.0), (1.0, 5.0), (0.04, 0.3), (3.0, 20.0)):
+            r = bound_and_canon(rng, sdt, qdt, 200, d, scale, shift)
+            if r is None:
+                continue
+            canon, s, bound = r
+            assert np.all(canon <= bound), (d, scale, shift, float(np.max(canon - bound)))
+            used = np.max((canon - s) / np.maximum(bound - s, 1e-300))
+            assert used < 0.9, (d, scale, shift, used)        # the slack is not razor-thin either
+            checked += 1
+    assert checked >= 10
