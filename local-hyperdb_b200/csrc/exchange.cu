@@ -3,7 +3,7 @@
 //
 // The NCCL form (torch.distributed.all_gather_into_tensor + hdb_merge_topk) costs ~17 us of host time per collective
 // plus the Python around it, and a sharded step at 8 GPUs is a ~0.3 ms sweep: the step was HOST-bound (measured,
-// gpurun_out/r02/mg_diag.log: 137 us of host work per step at 2 GPUs).  Here every rank owns a small exchange buffer
+// profiles/r01b_bench/mg_diag_2gpu.log: 137 us of host work per step at 2 GPUs).  Here every rank owns a small exchange buffer
 // that its peers map through CUDA IPC; one step is two tiny kernels on the post stream and no library call:
 //   push : copies this rank's packed result block straight into EVERY rank's buffer with peer stores, then publishes
 //          a per-(slot, source) sequence flag with a system-scope release;
