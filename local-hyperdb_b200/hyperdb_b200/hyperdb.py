@@ -30,6 +30,27 @@ _METRICS = ['dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_d
             'pearson_correlation', 'hamming_distance']
 
 
+class _LRUCache(OrderedDict):
+    """The slice of cachetools.LRUCache the reference uses (hyperdb/hyperdb.py:60, :1381-1388, :1398-1404): `maxsize`,
+    `in`, `[]`, `[]=` with least-recently-used eviction, `clear()`, `len()`.  A cachetools.LRUCache assigned to
+    `HyperDB.lru_cache` (as the reference's tests do, tests/test_hyperdb.py:724-736) works as well."""
+
+    def __init__(self, maxsize):
+        super().__init__()
+        self.maxsize = int(maxsize)
+
+    def __getitem__(self, key):
+        value = super().__getitem__(key)
+        self.move_to_end(key)
+        return value
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        self.move_to_end(key)
+        while len(self) > self.maxsize:
+            self.popitem(last=False)
+
+
 def _nested(document, dotted):
     cur = document
     for part in dotted.split('.'):
@@ -59,8 +80,7 @@ class HyperDB:
         self._mask_cache = {}
         # query cache (hyperdb/hyperdb.py:60-62, :1368-1388): same semantics, but the key is a 128-bit digest of the
         # query's bytes instead of tuple(query.tolist()) -- O(D) C speed instead of D Python floats per lookup
-        self.cache_size = int(cache_size)
-        self.lru_cache = OrderedDict()
+        self.lru_cache = _LRUCache(cache_size)
         self.cache_hits = 0
         self.cache_misses = 0
         if vectors is not None:
@@ -146,7 +166,7 @@ class HyperDB:
             size = f"{nbytes / 1024:.2f} KB"
         else:
             size = f"{int(nbytes)} bytes"
-        return {"cache_info": {"hits": self.cache_hits, "misses": self.cache_misses, "maxsize": self.cache_size,
+        return {"cache_info": {"hits": self.cache_hits, "misses": self.cache_misses, "maxsize": self.lru_cache.maxsize,
                                "currsize": len(self.lru_cache)}, "cache_memory_size": size}
 
     @staticmethod
@@ -239,18 +259,15 @@ class HyperDB:
         if metric not in _METRICS:
             raise ValueError(f"Invalid metric '{metric}'. Supported: 'dot_product', 'cosine_similarity', 'euclidean_metric', 'manhattan_distance', 'jaccard_similarity', 'pearson_correlation', 'hamming_distance'")
         key = None
-        if self.cache_size > 0:
+        if self.lru_cache.maxsize > 0:
             key = self._hashable_key(query_input, top_k, return_similarities, filters, recency_bias, timestamp_key, metric, ann_percent)
             if key in self.lru_cache:                        # hyperdb/hyperdb.py:1381-1384
                 self.cache_hits += 1
-                self.lru_cache.move_to_end(key)
                 return self.lru_cache[key]
             self.cache_misses += 1
         results = self._execute_query(query_input, top_k, return_similarities, filters, recency_bias, timestamp_key, metric)
         if key is not None:
-            self.lru_cache[key] = results
-            if len(self.lru_cache) > self.cache_size:
-                self.lru_cache.popitem(last=False)
+            self.lru_cache[key] = results                    # evicts the least recently used entry beyond maxsize
         return results
 
     def _execute_query(self, query_input, top_k, return_similarities, filters, recency_bias, timestamp_key, metric):

@@ -51,3 +51,54 @@ def test_bench_reference_arm_line():
     assert j["value"] > 0 and j["steps"] == 1 and j["config"]["workload"] == "c2_cosine_b1"
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def _shim_without_gpu(cache_size=256):
+    """A HyperDB shim whose ranking is stubbed out: only the cache / bookkeeping logic runs (no CUDA needed)."""
+    db = HyperDB(cache_size=cache_size)
+    db.documents = [{"id": i} for i in range(3)]
+    db.vectors = np.zeros((3, 4), np.float32)
+    calls = []
+
+    def fake_execute(query_input, top_k, *rest):
+        calls.append(query_input if isinstance(query_input, str) else tuple(np.asarray(query_input).ravel().tolist()))
+        return [("doc", 1.0, 0)][:top_k]
+    db._execute_query = fake_execute
+    return db, calls
+
+
+def test_cache_counters_like_the_reference_tests():
+    """tests/test_hyperdb.py:708-736 of the reference, against the shim's cache (ranking stubbed)."""
+    db, calls = _shim_without_gpu()
+    db.query("Abra")
+    assert db.get_cache_size_and_info()["cache_info"]["hits"] == 0 and db.get_cache_size_and_info()["cache_info"]["misses"] == 1
+    db.query("Abra")
+    info = db.get_cache_size_and_info()["cache_info"]
+    assert info["hits"] == 1 and info["misses"] == 1 and calls == ["Abra"]
+    # :724-728 -- the tests swap the cache object for a cachetools.LRUCache and read maxsize back
+    cachetools = __import__("pytest").importorskip("cachetools")
+    db.lru_cache = cachetools.LRUCache(maxsize=128)
+    assert db.get_cache_size_and_info()["cache_info"]["maxsize"] == 128
+    # :730-737 -- eviction
+    db.lru_cache = cachetools.LRUCache(maxsize=2)
+    for i in range(3):
+        db.query(f"Query {i}")
+    assert db.get_cache_size_and_info()["cache_info"]["currsize"] == 2
+
+
+def test_builtin_lru_evicts_least_recently_used():
+    db, calls = _shim_without_gpu(cache_size=2)
+    q = [np.full(4, float(i), np.float32) for i in range(3)]
+    db.query(q[0]); db.query(q[1]); db.query(q[0])            # q0 is now the most recently used
+    db.query(q[2])                                             # evicts q1
+    assert len(db.lru_cache) == 2 and db.get_cache_size_and_info()["cache_info"]["maxsize"] == 2
+    n = len(calls)
+    db.query(q[0])
+    assert len(calls) == n                                     # still cached
+    db.query(q[1])
+    assert len(calls) == n + 1                                 # was evicted: ranked again
+    db.clear_cache()
+    assert len(db.lru_cache) == 0 and db.cache_hits == 0 and db.cache_misses == 0
+    off, _ = _shim_without_gpu(cache_size=0)
+    off.query(q[0]); off.query(q[0])
+    assert len(off.lru_cache) == 0 and off.cache_hits == 0
