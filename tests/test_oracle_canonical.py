@@ -96,3 +96,34 @@ def test_pearson_edge_cases_match_port():
             with np.errstate(all="ignore"):
                 ref = P.pearson_scores(V, q)
             assert np.array_equal(K.pearson(V, q), ref, equal_nan=True), (vdt, qdt)
+
+
+def test_spec_equals_numpy_on_random_shapes():
+    """Beyond the golden cases: the operation-by-operation spec against the NumPy calls of the reference (the port) on
+    seeded random shapes / scales / dtype pairs, bit for bit wherever NumPy is deterministic."""
+    from oracle import reference_port as P
+    rng = np.random.default_rng(20241018)
+    fns = {"euclidean_metric": P.euclidean_scores, "manhattan_distance": P.manhattan_scores, "hamming_distance": P.hamming_scores,
+           "jaccard_similarity": P.jaccard_scores, "pearson_correlation": P.pearson_scores, "dot_product": P.dot_scores,
+           "cosine_similarity": P.cosine_scores}
+    dts = (np.float16, np.float32, np.float64)
+    checked = 0
+    for trial in range(120):
+        n, d = int(rng.integers(1, 40)), int(rng.integers(1, 300))
+        vdt, qdt = dts[int(rng.integers(0, 3))], dts[int(rng.integers(0, 3))]
+        scale, shift = float(rng.choice([0.01, 1.0, 30.0])), float(rng.choice([0.0, 0.0, 2.5]))
+        V = (rng.standard_normal((n, d)) * scale + shift).astype(vdt)
+        q = (rng.standard_normal(d) * scale + shift).astype(qdt)
+        if trial % 7 == 0:
+            V[0] = 0
+        for metric, fn in fns.items():
+            rdt = np.promote_types(vdt, qdt)
+            if metric in ("dot_product", "cosine_similarity") and rdt != np.float16:
+                continue                                   # OpenBLAS order: covered by tolerance tests
+            with np.errstate(all="ignore"):
+                want = np.asarray(fn(V.copy(), q.copy())).reshape(-1)
+                got = K.scores(V, q, metric)
+            assert got.dtype == want.dtype, (metric, vdt, qdt)
+            assert np.array_equal(got, want, equal_nan=True), (trial, metric, vdt.__name__, qdt.__name__, n, d, scale, shift)
+            checked += 1
+    assert checked > 500
