@@ -1,0 +1,130 @@
+"""The PRODUCT's canonical arithmetic (local-hyperdb_b200/csrc/canonical.cuh -- the code the certify step and the exact
+path run on the GPU) compiled for the HOST (tests/emul/canonical_host.cpp maps the CUDA rounding intrinsics to IEEE
+operations) and compared with NumPy / the reference port on seeded random inputs.  The GPU tests check the same code on
+the device against the golden vectors; this widens the input space without needing a GPU."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import reference_port as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DT = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
+DTS = (np.float16, np.float32, np.float64)
+METRIC = {"dot_product": 0, "cosine_similarity": 1, "euclidean_metric": 2, "manhattan_distance": 3, "hamming_distance": 4,
+          "jaccard_similarity": 5, "pearson_correlation": 6}
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    inc = "/usr/local/cuda/include"
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(inc, "cuda_fp16.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    so = str(tmp_path_factory.mktemp("emul") / "libcanon_host.so")
+    cmd = ["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-I" + inc, "-Wno-attributes", "-o", so,
+           os.path.join(HERE, "emul", "canonical_host.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(so)
+    lib.emul_pairwise_sum.restype = C.c_double
+    lib.emul_pairwise_sum.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    lib.emul_norm.restype = C.c_double
+    lib.emul_norm.argtypes = [C.c_int, C.c_void_p, C.c_int64]
+    lib.emul_mean_std.restype = None
+    lib.emul_mean_std.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.emul_similarity.restype = C.c_double
+    lib.emul_similarity.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                    C.c_void_p, C.c_void_p, C.c_int]
+    return lib
+
+
+def _same(a, b):
+    return (a == b) or (np.isnan(a) and np.isnan(b))
+
+
+def test_pairwise_sum_norm_mean_std(emul):
+    rng = np.random.default_rng(7)
+    for trial in range(900):
+        d = int(rng.integers(1, 2100))
+        dt = DTS[trial % 3]
+        x = np.ascontiguousarray((rng.standard_normal(d) * float(rng.choice([0.01, 1.0, 40.0])) + float(rng.choice([0.0, 3.0]))).astype(dt))
+        p = C.c_void_p(x.ctypes.data)
+        with np.errstate(all="ignore"):
+            assert _same(emul.emul_pairwise_sum(DT[x.dtype], p, d), float(np.add.reduce(x))), (trial, d, dt)
+            # get_norm_vector calls np.linalg.norm(axis=-1, keepdims=True): sqrt(add.reduce(x*x)), NOT the BLAS dot of axis=None
+            assert _same(emul.emul_norm(DT[x.dtype], p, d), float(np.linalg.norm(x, axis=-1, keepdims=True)[0])), (trial, d, dt)
+            m, s = C.c_double(), C.c_double()
+            emul.emul_mean_std(DT[x.dtype], p, d, 1, C.byref(m), C.byref(s))            # 1-D input: np.mean's scalar branch
+            assert _same(m.value, float(np.mean(x))) and _same(s.value, float(np.std(x))), (trial, d, dt)
+            emul.emul_mean_std(DT[x.dtype], p, d, 0, C.byref(m), C.byref(s))            # a row of a 2-D array (axis=1)
+            x2 = np.stack([x, x])
+            assert _same(m.value, float(np.mean(x2, axis=1)[0])) and _same(s.value, float(np.std(x2, axis=1)[0])), (trial, d, dt)
+
+
+def _prepared_query(q, metric):
+    """What prep_query stores in qc (float64 carrier) for this metric."""
+    with np.errstate(all="ignore"):
+        if metric == "cosine_similarity":
+            return P.unit_rows(q).astype(np.float64)
+        if metric == "pearson_correlation":
+            return (q - np.mean(q)).astype(np.float64)
+    return q.astype(np.float64)
+
+
+def _bits(x, words):
+    b = np.zeros(words * 32, bool)
+    b[: len(x)] = np.asarray(x) > 0
+    return np.packbits(b, bitorder="little").view(np.uint32).copy()
+
+
+@pytest.mark.parametrize("metric", sorted(METRIC))
+def test_similarity_of_the_product_source(emul, metric):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(metric.encode()))
+    fn = {"dot_product": P.dot_scores, "cosine_similarity": P.cosine_scores, "euclidean_metric": P.euclidean_scores,
+          "manhattan_distance": P.manhattan_scores, "hamming_distance": P.hamming_scores, "jaccard_similarity": P.jaccard_scores,
+          "pearson_correlation": P.pearson_scores}[metric]
+    exact_cases = 0
+    for trial in range(150):
+        n, d = 6, int(rng.integers(1, 400))
+        vdt, qdt = DTS[int(rng.integers(0, 3))], DTS[int(rng.integers(0, 3))]
+        scale, shift = float(rng.choice([0.02, 1.0, 25.0])), float(rng.choice([0.0, 0.0, 2.0]))
+        V = np.ascontiguousarray((rng.standard_normal((n, d)) * scale + shift).astype(vdt))
+        q = np.ascontiguousarray((rng.standard_normal(d) * scale + shift).astype(qdt))
+        V[0] = 0
+        if d > 1:
+            V[1] = V[1, 0]                                     # a constant row
+        rdt = np.promote_types(vdt, qdt)
+        with np.errstate(all="ignore"):
+            want = np.asarray(fn(V.copy(), q.copy())).reshape(-1)
+            qc = np.ascontiguousarray(_prepared_query(q, metric))
+            qstd = float(np.std(q))
+            words = ((d + 31) // 32 + 3) // 4 * 4
+            qb = _bits(q, words)
+            for i in range(n):
+                row = np.ascontiguousarray(V[i])
+                nrm, aux2 = 1.0, 0.0
+                if metric == "cosine_similarity":
+                    nrm = float(np.linalg.norm(row, axis=-1, keepdims=True)[0]) or 1.0
+                elif metric == "pearson_correlation":
+                    V2 = np.stack([row, row])
+                    nrm, aux2 = float(np.mean(V2, axis=1)[0]), float(np.std(V2, axis=1)[0])
+                rb = _bits(row, words)
+                got = emul.emul_similarity(DT[np.dtype(rdt)], DT[row.dtype], METRIC[metric], C.c_void_p(row.ctypes.data),
+                                           C.c_void_p(qc.ctypes.data), d, nrm, aux2, qstd, C.c_void_p(rb.ctypes.data),
+                                           C.c_void_p(qb.ctypes.data), words)
+                ref = float(want[i])
+                if metric in ("dot_product", "cosine_similarity") and rdt != np.float16:
+                    # OpenBLAS summation order is not NumPy's to define: the canonical value is the exact dot rounded once
+                    tol = (1e-5 if rdt == np.float32 else 1e-12)
+                    cond = 1.0 if metric == "cosine_similarity" else float(np.linalg.norm(row.astype(float)) * np.linalg.norm(q.astype(float)))
+                    assert abs(got - ref) <= tol * max(abs(ref), cond, 1e-300), (trial, i, vdt, qdt, d)
+                else:
+                    assert _same(got, ref), (trial, i, metric, vdt.__name__, qdt.__name__, d, scale, shift, got, ref)
+                    exact_cases += 1
+    if metric not in ("dot_product", "cosine_similarity"):
+        assert exact_cases == 150 * 6
