@@ -9,6 +9,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "canonical.cuh"
+#include "certificate.cuh"
 #include "hdb_internal.h"
 #include "../../include/hyperdb_b200.h"
 
@@ -43,81 +44,6 @@ __device__ __forceinline__ void load_batch<double>(const void* src, int64_t j0, 
     const int64_t j = j0 + 32 * u;
     v[u] = p[j < d ? j : j0];
   }
-}
-
-// Upper bound of the CANONICAL total score of any row whose selection key is <= the KP-th key
-// (score part s).  See DESIGN.md "certificate"; every term is a worst-case rounding bound.
-__device__ double outsider_bound(double s, const FinalizeArgs& a, double qnorm, double qstd) {
-  const double D = (double)a.m.d + 8.0;
-  const double uk = 1.1920928955078125e-7;                    // 2^-23: float32 key rounding (2x slack)
-  // accumulate type of the select pass; the tensor cores' fp32 accumulation is not IEEE round-to-nearest
-  const double ua = a.cand_count ? 1.9073486328125e-6 /*2^-19*/ : (a.m.dtype == 2) ? 4.440892098500626e-16 : 1.1920928955078125e-7;
-  const double uR = unit_roundoff(a.rdt);
-  const double uT = unit_roundoff(a.m.dtype);
-  const bool decay = a.f.decay != nullptr;
-  const double chain16 = (a.rdt == 0) ? D * 1.1920928955078125e-7 : 0.0;   // HALF_dot / f16 pairwise run in float32
-  if (a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) return s + fabs(s) * uk;     // exact on both sides: only the key rounding
-  if (a.metric == HDB_PEARSON) {
-    // Both sides evaluate rho~ = sum_j (v_j - mean_v) b_j / (std_v std_q d) from the SAME rounded statistics (b = q - mean_q).
-    // Magnitudes: sum_j |v_j b_j| / (std_v std_q d) <= A := max_i ||v_i|| / (std_i sqrt d) * ||b|| / (std_q sqrt d)   (qnorm slot),
-    // and ||v - mean_v|| <= 2 ||v||, so |rho~| <= 2A.
-    //             sum_j |(v_j - mean_v) b_j| / (std_v std_q d) <= Ac := max_i ||v_i - mean_i|| / (std_i sqrt d) * (same query factor), ~1.
-    const double A = (double)a.m.max_pratio * qnorm, Ac = (double)a.m.max_cratio * qnorm;
-    const double uaccR = (a.rdt == 2) ? 1.1102230246251565e-16 : 5.9604644775390625e-8;
-    double b = s + fabs(s) * uk
-             + A * ((D + 16.0) * ua + 1.1920928955078125e-7)   // sweep: FMA chains, mean correction, scalings; query rounded to the accumulate type
-             + Ac * 1.05 * (uT + uR + D * uaccR);              // reference: (v - mean) rounded to S, products to R, pairwise sum
-    // reference: rounding of the sum, the denominator (3 roundings) and the quotient, relative to the similarity itself
-    b += 6.0 * uR * (decay ? Ac : fabs(b));
-    if (a.rdt == 0 || a.m.dtype == 0) {
-      // float16: differences / products are multiples of 2^-24 (absolute errors), and the denominator must stay normal and finite
-      const double smin = (double)a.m.min_pstd;
-      if (!(smin * qstd > 2.44140625e-4) || !((double)a.m.max_norm * sqrt(D) * qstd * fmax(1.0, 2.0 * A) < 3.0e4)) return INFINITY;
-      b += 2.98023223876953125e-8 * (qnorm / smin + 1.0 / (smin * qstd)) * 1.5;
-    }
-    return decay ? b + fabs(b) * 1e-15 : b;
-  }
-  if (a.metric == HDB_DOT || a.metric == HDB_COSINE) {
-    const double A = (double)(a.metric == HDB_DOT ? a.m.max_norm : a.m.max_ratio) * qnorm;   // >= sum |v_i q_i|
-    double e = D * ua + chain16;
-    if (a.cand_count && a.m.dtype == 1) e += 3.90625e-3;       // kind::tf32 keeps 10 mantissa bits of each fp32 operand (2 * 2^-9)
-    if (a.metric == HDB_COSINE) e += 3.0 * uT + (a.m.dtype == 0 ? sqrt(D) * 5.9604644775390625e-8 : 0.0);
-    const double b = s + fabs(s) * uk + A * e;
-    return decay ? b + 2.0 * uR * A + fabs(b) * 1e-15 : b + 2.0 * uR * fabs(b);
-  }
-  // euclidean / manhattan: similarity in (0, 1]
-  if (decay) {
-    // total = sim + bias*decay.  With bias >= 0 the outsider's similarity is at most min(1, s'), and the
-    // similarity's error is relative to it (d(sim) <= d(dist)/(1+dist)^2 <= rel(dist) * sim).
-    const double smax = (a.f.bias >= 0.0) ? fmin(1.0, fmax(s, 0.0) * (1.0 + uk) + 1e-300) : 1.0;
-    double rel = (a.metric == HDB_EUCLIDEAN) ? 0.5 * (D * ua + 6.0 * uR + chain16) + 6.0 * uR
-                                             : (D * ua + 4.0 * uR + chain16) + 3.0 * uR;
-    double e = rel * smax + ua * qnorm;
-    if (a.rdt == 0 && a.metric == HDB_EUCLIDEAN) {
-      const double under = D * 5.9604644775390625e-8, dmin = 1.0 / smax - 1.0;
-      e += (dmin > 1e-2) ? under / (2.0 * dmin) : sqrt(under);
-    }
-    return s + fabs(s) * uk + e;
-  }
-  if (!(s > 0.0)) return INFINITY;
-  const double s_hi = s * (1.0 + uk);
-  double d_lo = 1.0 / s_hi - 1.0 - 4.76837158203125e-7 - ua * qnorm;          // distance of the fast pass, lower bound
-  if (d_lo < 0.0) d_lo = 0.0;
-  double dc;
-  if (a.metric == HDB_EUCLIDEAN) {
-    double d2 = d_lo * d_lo * (1.0 - D * ua - 6.0 * uR - chain16);
-    if (a.cand_count) {
-      // batched pass: d^2 = |v|^2 + |q|^2 - 2 v.q on the tensor cores -> ABSOLUTE error from the cancellation
-      const double A = (double)a.m.max_norm * qnorm;
-      d2 -= 2.0 * A * (D * ua + (a.m.dtype == 1 ? 3.90625e-3 : 0.0)) + 8.0 * 1.1920928955078125e-7 * ((double)a.m.max_norm * a.m.max_norm + qnorm * qnorm);
-    }
-    if (a.rdt == 0) d2 -= D * 5.9604644775390625e-8;                          // float16 squares flushed below 2^-24
-    dc = sqrt(d2 > 0.0 ? d2 : 0.0) * (1.0 - 3.0 * uR);
-  } else {
-    dc = d_lo * (1.0 - D * ua - 4.0 * uR - chain16);
-    if (dc < 0.0) dc = 0.0;
-  }
-  return (1.0 / (1.0 + dc)) * (1.0 + 3.0 * uR);
 }
 
 // Typed fast path of the canonical re-scoring: T = storage type, SDT/RDT = storage / result dtype ids

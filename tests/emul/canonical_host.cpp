@@ -33,6 +33,7 @@ static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f
 static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 #include "../../local-hyperdb_b200/csrc/canonical.cuh"
+#include "../../local-hyperdb_b200/csrc/certificate.cuh"
 
 using namespace hdb;
 
@@ -65,6 +66,23 @@ double emul_similarity(int rdt, int sdt, int metric, const void* row, const doub
   CanonArgs a;
   a.sdt = sdt; a.d = d; a.qc = qc; a.qbits = qbits; a.words = words; a.metric = metric; a.qstd = qstd;
   return canonical_similarity_rt(a, rdt, row, bitrow, nrm, aux2);
+}
+
+// csrc/certificate.cuh::outsider_bound with the statistics a shard would carry
+double emul_outsider_bound(double s, int metric, int rdt, int sdt, int64_t d, double max_norm, double max_ratio, double max_pratio,
+                           double max_cratio, double min_pstd, int has_decay, double bias, int tensor_path, double qnorm, double qstd) {
+  FinalizeArgs a;
+  std::memset(&a, 0, sizeof(a));
+  static double dummy_decay = 0.0;
+  static unsigned dummy_count = 0;
+  a.m.d = d; a.m.dtype = sdt;
+  a.m.max_norm = (float)max_norm; a.m.max_ratio = (float)max_ratio;
+  a.m.max_pratio = (float)max_pratio; a.m.max_cratio = (float)max_cratio; a.m.min_pstd = (float)min_pstd;
+  a.rdt = rdt; a.metric = metric;
+  a.f.decay = has_decay ? &dummy_decay : nullptr;
+  a.f.bias = bias;
+  a.cand_count = tensor_path ? &dummy_count : nullptr;
+  return outsider_bound(s, a, qnorm, qstd);
 }
 
 double emul_unit_elem(double v, double norm, int dt) { return unit_elem(v, norm, dt); }

@@ -69,3 +69,47 @@ def test_pearson_bound_covers_the_reference(sdt, qdt):
             assert used < 0.9, (d, scale, shift, used)        # the slack is not razor-thin either
             checked += 1
     assert checked >= 10
+
+
+@pytest.mark.parametrize("sdt", [np.float16, np.float32, np.float64])
+def test_pearson_bound_of_the_product_code(emul, sdt):
+    """The same property through the PRODUCT's own outsider_bound (csrc/certificate.cuh compiled for the host): the
+    NumPy restatement above and the shipped code must agree, and the shipped code must cover the reference."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(("product" + sdt.__name__).encode()))
+    rows = 0
+    for qdt in (np.float16, np.float32, np.float64):
+        for d in (8, 96, 768):
+            for scale, shift in ((1.0, 0.0), (0.04, 0.3), (3.0, 20.0)):
+                n = 150
+                V = (rng.standard_normal((n, d)) * scale * rng.uniform(0.2, 3, (n, 1)) + shift * rng.uniform(-1, 1, (n, 1))).astype(sdt)
+                q = (rng.standard_normal(d) * scale + shift).astype(qdt)
+                R = np.promote_types(sdt, qdt)
+                with np.errstate(all="ignore"):
+                    canon = K.pearson(V, q)
+                    vmean, vstd = K.row_mean(V).astype(np.float64), K.row_std(V).astype(np.float64)
+                    qmean = K.row_mean(q[None, :], scalar=True)[0]
+                    qstd = float(K.row_std(q[None, :])[0])
+                    b = q - qmean
+                    acc = np.float64 if sdt == np.float64 else np.float32
+                    b_acc = b.astype(acc)
+                    sumb = float(np.sum(b_acc.astype(np.float64)))
+                    t = (V.astype(acc) @ b_acc).astype(acc)
+                    sweep = ((t - vmean.astype(acc) * acc(sumb)) * acc(1.0 / qstd) * (1.0 / (vstd * d)).astype(acc)).astype(np.float32).astype(np.float64)
+                ok = (vstd > 0) & np.isfinite(vstd) & np.isfinite(canon) & np.isfinite(sweep)
+                if not ok.any() or not (qstd > 0):
+                    continue
+                Vd = V.astype(np.float64)
+                f32 = lambda x: float(np.float32(x))
+                max_norm = f32(np.max(np.linalg.norm(Vd, axis=1)) * (1 + 1e-6))
+                max_pratio = f32(np.max(np.linalg.norm(Vd[ok], axis=1) / (vstd[ok] * np.sqrt(d))) * (1 + 1e-6))
+                max_cratio = f32(np.max(np.linalg.norm(Vd[ok] - vmean[ok, None], axis=1) / (vstd[ok] * np.sqrt(d))) * (1 + 1e-6))
+                min_pstd = f32(np.min(vstd[ok]) * (1 - 1e-6))
+                qn = float(np.linalg.norm(b.astype(np.float64)) / (qstd * np.sqrt(d)))
+                dts = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
+                for i in np.flatnonzero(ok):
+                    bound = emul.emul_outsider_bound(float(sweep[i]), 6, dts[np.dtype(R)], dts[np.dtype(sdt)], d, max_norm, 1.0, max_pratio,
+                                                     max_cratio, min_pstd, 0, 0.0, 0, qn, qstd)
+                    assert canon[i] <= bound, (qdt.__name__, d, scale, shift, i, canon[i], sweep[i], bound)
+                    rows += 1
+    assert rows > 2000

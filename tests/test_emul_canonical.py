@@ -4,8 +4,6 @@ operations) and compared with NumPy / the reference port on seeded random inputs
 the device against the golden vectors; this widens the input space without needing a GPU."""
 import ctypes as C
 import os
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
@@ -17,29 +15,6 @@ DT = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
 DTS = (np.float16, np.float32, np.float64)
 METRIC = {"dot_product": 0, "cosine_similarity": 1, "euclidean_metric": 2, "manhattan_distance": 3, "hamming_distance": 4,
           "jaccard_similarity": 5, "pearson_correlation": 6}
-
-
-@pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    inc = "/usr/local/cuda/include"
-    if shutil.which("g++") is None or not os.path.exists(os.path.join(inc, "cuda_fp16.h")):
-        pytest.skip("needs g++ and the CUDA headers")
-    so = str(tmp_path_factory.mktemp("emul") / "libcanon_host.so")
-    cmd = ["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-I" + inc, "-Wno-attributes", "-o", so,
-           os.path.join(HERE, "emul", "canonical_host.cpp")]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    lib = C.CDLL(so)
-    lib.emul_pairwise_sum.restype = C.c_double
-    lib.emul_pairwise_sum.argtypes = [C.c_int, C.c_void_p, C.c_int]
-    lib.emul_norm.restype = C.c_double
-    lib.emul_norm.argtypes = [C.c_int, C.c_void_p, C.c_int64]
-    lib.emul_mean_std.restype = None
-    lib.emul_mean_std.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    lib.emul_similarity.restype = C.c_double
-    lib.emul_similarity.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
-                                    C.c_void_p, C.c_void_p, C.c_int]
-    return lib
 
 
 def _same(a, b):
@@ -128,3 +103,86 @@ def test_similarity_of_the_product_source(emul, metric):
                     exact_cases += 1
     if metric not in ("dot_product", "cosine_similarity"):
         assert exact_cases == 150 * 6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The certificate (csrc/certificate.cuh::outsider_bound, compiled for the host) against the oracle: for every row, the
+# reference's total score must not exceed the bound derived from the sweep's own float32 score and the ingest
+# statistics.  The sweep is emulated in NumPy with the kernel's accumulate type (fp32, or fp64 for fp64 storage).
+# ---------------------------------------------------------------------------------------------------------------------
+def _sweep_scores(V, q, metric, acc):
+    """float32 score part of the selection key, as sweep_kernel's epilogue forms it, and what prep_query derives from q."""
+    from oracle import canonical as K
+    with np.errstate(all="ignore"):
+        if metric == "cosine_similarity":
+            c = K.unit_rows(q).astype(np.float64)
+        else:
+            c = q.astype(np.float64)
+        qa = c.astype(acc)
+        qnorm = float(np.sqrt(np.sum(c * c)))
+        Va = V.astype(acc)
+        if metric in ("dot_product", "cosine_similarity"):
+            total = (Va @ qa).astype(acc)
+            if metric == "cosine_similarity":
+                norms = K.row_norm(V).astype(np.float64)
+                norms[norms == 0] = 1
+                total = total * (acc(1) / norms.astype(acc))
+            sim = total
+        else:
+            df = Va - qa[None, :]
+            dist = np.sqrt(np.sum(df * df, axis=1, dtype=acc)) if metric == "euclidean_metric" else np.sum(np.abs(df), axis=1, dtype=acc)
+            sim = acc(1) / (acc(1) + dist)
+    return sim.astype(np.float64), qnorm
+
+
+@pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance"])
+@pytest.mark.parametrize("decay", [False, True], ids=["plain", "decay"])
+def test_certificate_bound_covers_the_reference(emul, metric, decay):
+    import zlib
+    from oracle import canonical as K
+    rng = np.random.default_rng(zlib.crc32((metric + str(decay)).encode()))
+    worst_use, rows_checked = 0.0, 0
+    for trial in range(90):
+        n, d = 64, int(rng.choice([3, 16, 96, 384, 768, 1536]))
+        vdt, qdt = DTS[int(rng.integers(0, 3))], DTS[int(rng.integers(0, 3))]
+        kind = trial % 3
+        V = rng.standard_normal((n, d))
+        q = rng.standard_normal(d)
+        if kind == 0:                                    # the bench distribution: unit rows, unit query
+            V /= np.linalg.norm(V, axis=1, keepdims=True)
+            q /= np.linalg.norm(q)
+        elif kind == 1:                                  # rows of very different lengths, near-duplicates of the query
+            V *= rng.uniform(0.05, 4.0, (n, 1))
+            V[:8] = q[None, :] * rng.uniform(0.5, 1.5, (8, 1)) + rng.standard_normal((8, d)) * 1e-3
+        else:                                            # shifted data (large common component: cancellation in dot products)
+            V += 1.5
+            q += 1.5
+        V, q = np.ascontiguousarray(V.astype(vdt)), np.ascontiguousarray(q.astype(qdt))
+        rdt = np.promote_types(vdt, qdt)
+        acc = np.float64 if vdt == np.float64 else np.float32
+        with np.errstate(all="ignore"):
+            canon = K.scores(V, q, metric).astype(np.float64)
+            sim, qnorm = _sweep_scores(V, q, metric, acc)
+            bias, dec = 0.0, np.zeros(n)
+            if decay:
+                bias = float(rng.choice([0.3, 1.0, -0.5]))
+                dec = np.exp(-rng.uniform(0, 5, n))
+            sweep = (sim + bias * dec).astype(np.float32).astype(np.float64)
+            total = canon + bias * dec
+            Vd = V.astype(np.float64)
+            true_norm = np.linalg.norm(Vd, axis=1)
+            cn = K.row_norm(V).astype(np.float64)
+            cn[cn == 0] = 1
+            max_norm = float(np.float32(min(true_norm.max() * (1 + 1e-6), 3e38)))
+            max_ratio = float(np.float32(min((true_norm / cn).max() * (1 + 1e-6), 3e38)))
+        for i in range(n):
+            if not (np.isfinite(total[i]) and np.isfinite(sweep[i])):
+                continue
+            b = emul.emul_outsider_bound(float(sweep[i]), METRIC[metric], DT[np.dtype(rdt)], DT[V.dtype], d, max_norm, max_ratio,
+                                         0.0, 0.0, 0.0, int(decay), bias, 0, qnorm, 1.0)
+            assert total[i] <= b, (trial, i, metric, vdt.__name__, qdt.__name__, d, kind, total[i], sweep[i], b)
+            if b > sweep[i] and np.isfinite(b):
+                worst_use = max(worst_use, (total[i] - sweep[i]) / (b - sweep[i]))
+            rows_checked += 1
+    assert rows_checked > 3000
+    assert worst_use < 0.95, worst_use
