@@ -11,7 +11,7 @@
 
 namespace hdb {
 thread_local std::string g_error;
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 int fail(const std::string& msg) { g_error = msg; return 1; }
 int cuda_fail(cudaError_t e, const char* what) {
   g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
@@ -155,9 +155,7 @@ int hdb_device_count(int* count) {
   return 0;
 }
 int64_t hdb_launch_count(int reset) {
-  int64_t v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int hdb_matrix_create(int device, int dtype, int64_t n_rows, int64_t dim, int64_t row_offset, hdb_matrix** out) {

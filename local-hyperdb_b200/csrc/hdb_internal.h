@@ -3,12 +3,13 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 namespace hdb {
 
 extern thread_local std::string g_error;
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;     // instrumentation only; handles may live on different host threads
 int fail(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 
@@ -22,7 +23,7 @@ int cuda_fail(cudaError_t e, const char* what);
     int rc__ = (x);           \
     if (rc__ != 0) return rc__; \
   } while (0)
-#define HDB_LAUNCHED() (++::hdb::g_launches)
+#define HDB_LAUNCHED() (::hdb::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 constexpr int kMaxKP = 128;            // largest candidate-list class of the fused pass
 constexpr int kSweepThreads = 256;     // 8 warps per CTA
