@@ -245,7 +245,6 @@ def main():
     from hyperdb_b200 import _native as N
     from hyperdb_b200.sharded import CudaEngine, ShardedMatrix, shard_bounds
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("HDB_NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout: one JSON line only
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -70,9 +70,13 @@ int hdb_matrix_finalize(hdb_matrix* m);
 /* Run the handle's work on this cudaStream_t (NULL = legacy default stream). */
 int hdb_matrix_set_stream(hdb_matrix* m, void* cuda_stream);
 /* Query pipelining for device-output calls.  With a post stream set, hdb_query(..., HDB_DEVICE) enqueues the query
- * preparation and the streaming sweep on the handle's stream and the certify step on `post_stream`, so that the
- * certify (and whatever the caller enqueues after it on the post stream: the candidate exchange, the merge) of query i
- * overlaps the sweep of query i+1.  Results are valid in POST-stream order.  NULL switches pipelining off.
+ * preparation on an internal high-priority stream, the streaming sweep on the handle's stream (or its internal twin,
+ * see hdb_matrix_set_sweep_overlap) and the certify step on `post_stream`, so that the certify (and whatever the
+ * caller enqueues after it on the post stream: the candidate exchange, the merge) of query i overlaps the sweep of
+ * query i+1.  Ordering contract: a device-resident query is read only after all work enqueued on the HANDLE'S stream
+ * before the call (the internal stream waits for an event recorded there); a query produced on any other stream must
+ * be complete, or that stream must be joined into the handle's stream, before hdb_query is called.  Results are valid
+ * in POST-stream order.  NULL switches pipelining off.
  * Give the post stream a HIGH priority (cudaStreamCreateWithPriority): its small kernels then take the SMs a finishing
  * sweep vacates before the next query's pending sweep CTAs do. */
 int hdb_matrix_set_post_stream(hdb_matrix* m, void* post_stream);
@@ -134,6 +138,12 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
  * reported through *out_dtype (HDB_F16/F32/F64; 3 = uint64). */
 int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_space,
                void* out, int out_space, int* out_dtype);
+/* The same with option bits.  HDB_SCORES_DISTANCE: for HDB_EUCLIDEAN write the distance np.linalg.norm(v - q) itself
+ * instead of 1/(1+d) -- euclidean_metric(..., get_similarity_score=False), ranking_algorithm.py:49-52 (ignored for
+ * the other metrics). */
+enum { HDB_SCORES_DISTANCE = 1 };
+int hdb_scores_ex(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_space,
+                  void* out, int out_space, int* out_dtype, int flags);
 /* L2-normalised copy of `n_rows` x `dim` values (get_norm_vector, ranking_algorithm.py:8-21). */
 int hdb_normalize_rows(int device, int dtype, int64_t n_rows, int64_t dim, const void* src, int src_space,
                        void* dst, int dst_space);

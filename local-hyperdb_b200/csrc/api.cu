@@ -70,7 +70,7 @@ struct hdb_matrix {
   int cur_slot = 0;
   cudaStream_t post_stream = nullptr;
   cudaStream_t pre_stream = nullptr;     // pipelined mode: query preparation runs here, ahead of the main stream
-  cudaEvent_t ev_select = nullptr, ev_prep = nullptr;
+  cudaEvent_t ev_select = nullptr, ev_prep = nullptr, ev_qready = nullptr;
   // sweep overlap: the sweeps of odd workspace slots run on a second internal stream, so the CTAs of query i+1 fill the
   // SMs that query i's persistent CTAs vacate during its tail (launch gap, ramp, straggler warps, per-CTA merge)
   cudaStream_t alt_stream = nullptr;
@@ -197,6 +197,7 @@ int hdb_matrix_destroy(hdb_matrix* m) {
     for (auto& q : m->slots) if (q.done) cudaEventDestroy(q.done);
     if (m->ev_select) cudaEventDestroy(m->ev_select);
     if (m->ev_prep) cudaEventDestroy(m->ev_prep);
+    if (m->ev_qready) cudaEventDestroy(m->ev_qready);
     if (m->pre_stream) cudaStreamDestroy(m->pre_stream);
     if (m->alt_stream) { cudaStreamSynchronize(m->alt_stream); cudaStreamDestroy(m->alt_stream); }
     if (m->ev_alt) cudaEventDestroy(m->ev_alt);
@@ -230,6 +231,7 @@ int hdb_matrix_set_post_stream(hdb_matrix* m, void* cuda_stream) {
     if (!m->ev_alt) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_alt, cudaEventDisableTiming));
     if (!m->ev_select) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_select, cudaEventDisableTiming));
     if (!m->ev_prep) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_prep, cudaEventDisableTiming));
+    if (!m->ev_qready) HDB_CUDA(cudaEventCreateWithFlags(&m->ev_qready, cudaEventDisableTiming));
     if (!m->pre_stream) {
       // The small kernels must not queue behind the NEXT query's sweep CTAs when the current sweep's CTAs leave the SMs:
       // query preparation runs on a high-priority stream (the caller should give the post stream a high priority too)
@@ -830,8 +832,14 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
     q_dev = m->q_raw;
   }
   if (pipelined) {
-    // the preparation of THIS query runs on the internal pre stream, i.e. while the previous query's sweep still
-    // occupies the main stream (device queries must therefore be complete when hdb_query is called)
+    // The preparation of THIS query runs on the internal pre stream, ahead of the sweeps still queued on the main
+    // stream.  A device-resident query may have been produced by work enqueued on the handle's stream just before this
+    // call (an embedding kernel, a copy): the pre stream is ordered after that work by an event.  With overlapping
+    // sweeps the main stream's last sweep is two queries old, so the wait costs nothing.
+    if (q_space == HDB_DEVICE) {
+      HDB_CUDA(cudaEventRecord(m->ev_qready, m->stream));
+      HDB_CUDA(cudaStreamWaitEvent(m->pre_stream, m->ev_qready, 0));
+    }
     HDB_TRY(launch_prep_query(q_dev, q_dtype, nq, m->d, metric, m->dtype, m->words, m->qb, m->tau, m->pre_stream));
     HDB_CUDA(cudaEventRecord(m->ev_prep, m->pre_stream));
     HDB_CUDA(cudaStreamWaitEvent(m->stream, m->ev_prep, 0));
@@ -1018,6 +1026,11 @@ int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter) 
 
 int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_space, void* out, int out_space,
                int* out_dtype) {
+  return hdb_scores_ex(m, metric, query, q_dtype, q_space, out, out_space, out_dtype, 0);
+}
+
+int hdb_scores_ex(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_space, void* out, int out_space,
+                  int* out_dtype, int flags) {
   if (!m) return fail("null handle");
   if (!m->finalized) return fail("hdb_scores: call hdb_matrix_finalize first");
   if (metric < 0 || metric > 6) return fail("Unknown metric");
@@ -1044,7 +1057,7 @@ int hdb_scores(hdb_matrix* m, int metric, const void* query, int q_dtype, int q_
     HDB_CUDA(cudaMalloc(&tmp, (size_t)(m->n ? m->n : 1) * esz));
     dst = tmp;
   }
-  int rc = launch_scores_out(view_of(m), metric, rdt, m->qb.qc, m->qb.qbits, m->qb.qaux, dst, m->stream);
+  int rc = launch_scores_out(view_of(m), metric, rdt, m->qb.qc, m->qb.qbits, m->qb.qaux, dst, (flags & HDB_SCORES_DISTANCE) ? 1 : 0, m->stream);
   if (!rc && out_space == HDB_HOST) {
     cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)m->n * esz, cudaMemcpyDeviceToHost, m->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);

@@ -591,13 +591,15 @@ batched_tc_pair_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_c
 
 // ---------------------------------------------------------------------------------------------
 // CTA-private records -> per-query candidate lists.  One CTA per source CTA; a source buffer that overflowed
-// poisons every query (count = UINT_MAX -> finalize reports them uncertified and the host retries).
+// poisons every query by setting the TOP BIT of its counter with an atomic OR: the other CTAs' concurrent atomicAdds
+// cannot clear it (a plain store of UINT_MAX could be wrapped back to a small count by a later add), so finalize
+// sees count > capacity, reports the query uncertified and the host retries.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bucket_records_kernel(const uint4* rec, const unsigned* rec_count, unsigned rec_cap,
                                                              uint64_t* cand, unsigned* cand_count, int cap, int64_t nq) {
   const unsigned n = rec_count[blockIdx.x];
   if (n > rec_cap) {
-    for (int64_t b = threadIdx.x; b < nq; b += 256) cand_count[b] = 0xffffffffu;
+    for (int64_t b = threadIdx.x; b < nq; b += 256) atomicOr(&cand_count[b], 0x80000000u);
     return;
   }
   const uint4* src = rec + (size_t)blockIdx.x * rec_cap;

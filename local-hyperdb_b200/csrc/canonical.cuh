@@ -177,6 +177,129 @@ __device__ typename Arith<RDT>::C pairwise_sum_warp(Term term, int n, int lane, 
   return A::acc_done(ret);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pairwise PLAN: the shape of NumPy's pairwise recursion depends only on n, so the row-wise kernels (csrc/rowwise.cu:
+// one warp per row, every row has the same length) get it precomputed once on the host instead of walking the
+// recursion per row: the leaves (offset, length <= 128) in order, and the post-order additions as a flat program
+// over result slots (leaf i -> slot i, addition t -> slot kPlanLeaves + t).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPlanLeaves = 64;
+struct PwPlan {
+  int n, nleaves, nadds, root;
+  int leaf_off[kPlanLeaves];
+  short leaf_len[kPlanLeaves];
+  unsigned char add_dst[kPlanLeaves], add_a[kPlanLeaves], add_b[kPlanLeaves];
+};
+
+// false: more than kPlanLeaves leaves (rows longer than ~4-8 k elements): the caller keeps the per-row recursion
+__host__ __device__ inline bool pw_plan_build(PwPlan& p, int n) {
+  p.n = n; p.nleaves = 0; p.nadds = 0; p.root = 0;
+  struct Frame { int off, n, state, left; };
+  Frame st[32];
+  int sp = 0, ret = 0;
+  st[0] = Frame{0, n, 0, 0};
+  while (sp >= 0) {
+    Frame& f = st[sp];
+    if (f.n <= 128) {
+      if (p.nleaves >= kPlanLeaves) return false;
+      p.leaf_off[p.nleaves] = f.off;
+      p.leaf_len[p.nleaves] = (short)f.n;
+      ret = p.nleaves++;
+      --sp;
+      continue;
+    }
+    int half = f.n / 2;
+    half -= half % 8;
+    if (f.state == 0) { f.state = 1; st[sp + 1] = Frame{f.off, half, 0, 0}; ++sp; continue; }
+    if (f.state == 1) { f.left = ret; f.state = 2; st[sp + 1] = Frame{f.off + half, f.n - half, 0, 0}; ++sp; continue; }
+    const int dst = kPlanLeaves + p.nadds;
+    p.add_dst[p.nadds] = (unsigned char)dst;
+    p.add_a[p.nadds] = (unsigned char)f.left;
+    p.add_b[p.nadds] = (unsigned char)ret;
+    ++p.nadds;
+    ret = dst;
+    --sp;
+  }
+  p.root = ret;
+  return true;
+}
+
+// One leaf exactly as pairwise_sum's: 8 interleaved accumulators, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail.
+template <int RDT, typename Term>
+__device__ inline typename Arith<RDT>::C pw_leaf_seq(Term term, int off, int m) {
+  using A = Arith<RDT>;
+  using C = typename A::C;
+  if (m < 8) {
+    C acc = 0;
+    for (int i = 0; i < m; ++i) acc = A::acc_add(acc, term(off + i));
+    return acc;
+  }
+  C r[8];
+  for (int j = 0; j < 8; ++j) r[j] = term(off + j);
+  const int full = m - (m % 8);
+  int i = 8;
+  for (; i < full; i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = A::acc_add(r[j], term(off + i + j));
+  C acc = A::acc_add(A::acc_add(A::acc_add(r[0], r[1]), A::acc_add(r[2], r[3])),
+                     A::acc_add(A::acc_add(r[4], r[5]), A::acc_add(r[6], r[7])));
+  for (; i < m; ++i) acc = A::acc_add(acc, term(off + i));
+  return acc;
+}
+
+// Sequential evaluation of a plan (the host-side tests check it against np.add.reduce; the warp form below does the
+// same additions in the same order).
+template <int RDT, typename Term>
+__device__ inline typename Arith<RDT>::C pairwise_sum_plan_seq(Term term, const PwPlan& plan) {
+  using A = Arith<RDT>;
+  using C = typename A::C;
+  C res[2 * kPlanLeaves];
+  for (int l = 0; l < plan.nleaves; ++l) res[l] = pw_leaf_seq<RDT>(term, plan.leaf_off[l], plan.leaf_len[l]);
+  for (int t = 0; t < plan.nadds; ++t) res[plan.add_dst[t]] = A::acc_add(res[plan.add_a[t]], res[plan.add_b[t]]);
+  return A::acc_done(res[plan.root]);
+}
+
+#ifdef __CUDACC__
+// Warp form: 8 lanes own one leaf (the 8 interleaved accumulators), 4 leaves per round, 3-step butterfly; lane 0 then
+// runs the addition program over the per-warp result slots `res` (2*kPlanLeaves values of C in shared memory).
+// term(i) must be readable by every lane; all 32 lanes call and all return the sum.
+template <int RDT, typename Term>
+__device__ __forceinline__ typename Arith<RDT>::C pairwise_sum_plan(Term term, const PwPlan& plan, int lane, typename Arith<RDT>::C* res) {
+  using A = Arith<RDT>;
+  using C = typename A::C;
+  const int sub = lane & 7, grp = lane >> 3;
+  for (int base = 0; base < plan.nleaves; base += 4) {
+    const int li = base + grp;
+    const bool have = li < plan.nleaves;
+    const int off = have ? plan.leaf_off[li] : 0;
+    const int m = have ? plan.leaf_len[li] : 0, full = m - (m % 8);
+    C acc = 0;
+    if (m >= 8) {
+      acc = term(off + sub);
+      for (int i = 8; i < full; i += 8) acc = A::acc_add(acc, term(off + i + sub));
+    }
+    acc = A::acc_add(acc, __shfl_xor_sync(kFull, acc, 1));
+    acc = A::acc_add(acc, __shfl_xor_sync(kFull, acc, 2));
+    acc = A::acc_add(acc, __shfl_xor_sync(kFull, acc, 4));
+    if (have && sub == 0) {
+      if (m < 8) {
+        acc = 0;
+        for (int i = 0; i < m; ++i) acc = A::acc_add(acc, term(off + i));
+      } else {
+        for (int i = full; i < m; ++i) acc = A::acc_add(acc, term(off + i));
+      }
+      res[li] = acc;
+    }
+  }
+  __syncwarp();
+  if (lane == 0)
+    for (int t = 0; t < plan.nadds; ++t) res[plan.add_dst[t]] = A::acc_add(res[plan.add_a[t]], res[plan.add_b[t]]);
+  __syncwarp();
+  const C out = A::acc_done(res[plan.root]);
+  __syncwarp();                                  // `res` may be rewritten by the caller's next sum
+  return out;
+}
+#endif
+
 // np.linalg.norm of one row/vector in dtype DT: sqrt(add.reduce(x*x)); zero -> caller's business.
 template <int DT>
 __device__ typename Arith<DT>::C canonical_norm(const void* x, int64_t d) {
@@ -291,6 +414,7 @@ struct CanonArgs {
   int words;             // 32-bit words per packed row
   int metric;
   double qstd;           // pearson: np.std(query) (query dtype, widened)
+  int distance;          // euclidean: return the distance itself (get_similarity_score=False, ranking_algorithm.py:49-52)
 };
 
 // Element-wise half of a canonical score (parallelisable): the per-column term the reference feeds into
@@ -307,12 +431,13 @@ __device__ __forceinline__ typename Arith<RDT>::C canonical_term(int metric, dou
 
 // Order-dependent half: the reference's reduction over the terms (sequential by nature).
 template <int RDT, typename GetTerm, typename GetQ>
-__device__ double canonical_reduce(int metric, GetTerm term, GetQ gq, int d) {
+__device__ double canonical_reduce(int metric, GetTerm term, GetQ gq, int d, bool distance = false) {
   using A = Arith<RDT>;
   using C = typename A::C;
   if (metric <= 1) return (double)canonical_dot<RDT>(term, gq, d);
   C dist = pairwise_sum<RDT>(term, d);
   if (metric == 2) dist = A::sqrt(dist);
+  if (distance) return (double)dist;
   return (double)A::div(C(1), A::add(C(1), dist));
 }
 
@@ -342,7 +467,7 @@ __device__ double canonical_similarity(const CanonArgs& a, const void* rowp, con
   }
   auto gq = [&](int j) -> C { return A::from_double(a.qc[j]); };
   auto term = [&](int j) -> C { return canonical_term<RDT>(a.metric, load_as_double(rowp, a.sdt, j), a.qc[j], nrm, a.sdt); };
-  return canonical_reduce<RDT>(a.metric, term, gq, d);
+  return canonical_reduce<RDT>(a.metric, term, gq, d, a.metric == 2 && a.distance != 0);
 }
 
 __device__ __forceinline__ double canonical_similarity_rt(const CanonArgs& a, int rdt, const void* rowp,

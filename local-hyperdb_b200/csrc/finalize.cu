@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     ca.metric = a.metric;
     ca.qc = a.qb.qc + b * a.m.d;
     ca.qstd = a.qb.qaux ? a.qb.qaux[2 * b] : 1.0;
+    ca.distance = 0;
     const uint32_t row = key_row(surv[tid]);
     const uint32_t* bitrow = a.m.bits ? a.m.bits + (int64_t)row * a.m.words : nullptr;
     double nrm = 1.0, aux2 = 0.0;
@@ -365,12 +366,14 @@ int launch_finalize(const FinalizeArgs& a_in, int64_t nq, cudaStream_t s) {
   if (want > 160 * 1024) want = 160 * 1024;
   if (want < qbytes + row_pitch || a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) want = 0;
   a.smem_bytes = (int)want;
-  static bool attr_set[64] = {};           // the attribute belongs to a device's context: one process may hold shards on several
+  // the attribute belongs to a device's context (one process may hold shards on several) and handles may live on
+  // different host threads: a per-device atomic flag; setting it twice is harmless
+  static std::atomic<bool> attr_set[64];
   int dev = 0;
   HDB_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
     HDB_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   finalize_kernel<<<(unsigned)nq, kFinThreads, (size_t)a.smem_bytes, s>>>(a);
   HDB_LAUNCHED();
@@ -393,6 +396,7 @@ __device__ __forceinline__ CanonArgs canon_args(const MatrixView& m, int metric,
   ca.sdt = m.dtype; ca.d = m.d; ca.qc = qc;
   ca.qbits = qbits; ca.words = m.words; ca.metric = metric;
   ca.qstd = qaux ? qaux[0] : 1.0;
+  ca.distance = 0;
   return ca;
 }
 
@@ -422,6 +426,9 @@ __global__ void full_scores_kernel(MatrixView m, RowFilter f, int metric, int rd
 int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,
                        const uint32_t* qbits, const double* qaux, double* totals, cudaStream_t s) {
   if (m.n == 0) return 0;
+  int handled = 0;
+  HDB_TRY(launch_scores_rowwise(m, f, metric, rdt, qc, qaux, totals, nullptr, 0, s, &handled));     // csrc/rowwise.cu: HBM-rate forms
+  if (handled) return 0;
   int64_t blocks = (m.n + 127) / 128;
   full_scores_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, f, metric, rdt, qc, qbits, qaux, totals);
   HDB_LAUNCHED();
@@ -430,10 +437,12 @@ int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int 
 }
 
 // the metric function's own output: dtype R (uint64 for hamming)
-__global__ void scores_out_kernel(MatrixView m, int metric, int rdt, const double* qc, const uint32_t* qbits, const double* qaux, void* out) {
+__global__ void scores_out_kernel(MatrixView m, int metric, int rdt, const double* qc, const uint32_t* qbits, const double* qaux, void* out,
+                                  int distance) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= m.n) return;
   CanonArgs ca = canon_args(m, metric, qc, qbits, qaux);
+  ca.distance = distance;
   const double v = row_canonical(m, ca, rdt, row);
   if (metric == HDB_HAMMING) reinterpret_cast<unsigned long long*>(out)[row] = (unsigned long long)(long long)v;
   else if (metric == HDB_JACCARD || metric == HDB_PEARSON) reinterpret_cast<double*>(out)[row] = v;      // np.zeros(N) receives the quotients
@@ -443,10 +452,16 @@ __global__ void scores_out_kernel(MatrixView m, int metric, int rdt, const doubl
 }
 
 int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits, const double* qaux, void* out,
-                      cudaStream_t s) {
+                      int distance, cudaStream_t s) {
   if (m.n == 0) return 0;
+  if (metric != HDB_EUCLIDEAN) distance = 0;
+  int handled = 0;
+  RowFilter none;
+  none.mask = nullptr; none.lo = 0; none.hi = m.n; none.decay = nullptr; none.bias = 0.0;
+  HDB_TRY(launch_scores_rowwise(m, none, metric, rdt, qc, qaux, nullptr, out, distance, s, &handled));
+  if (handled) return 0;
   int64_t blocks = (m.n + 127) / 128;
-  scores_out_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, metric, rdt, qc, qbits, qaux, out);
+  scores_out_kernel<<<(unsigned)blocks, 128, 0, s>>>(m, metric, rdt, qc, qbits, qaux, out, distance);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;

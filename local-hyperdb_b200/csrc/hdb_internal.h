@@ -122,12 +122,21 @@ int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s);
 int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,
                        const uint32_t* qbits, const double* qaux, double* totals /*[n], masked rows = -NaN*/, cudaStream_t s);
 int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits, const double* qaux,
-                      void* out /*dtype R, uint64 (hamming) or float64 (jaccard, pearson)*/, cudaStream_t s);
+                      void* out /*dtype R, uint64 (hamming) or float64 (jaccard, pearson)*/, int distance /*euclidean: the distance itself*/,
+                      cudaStream_t s);
 int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
                int64_t* out_idx, double* out_score, int64_t* out_count, void** scratch, size_t* scratch_bytes,
                cudaStream_t s);
 int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, int64_t ls_rec, int64_t ls_cnt, const double* scores, const int64_t* ids,
                       const int64_t* counts, int64_t* out_idx, double* out_score, int64_t* out_count, cudaStream_t s);
+
+// ---- rowwise.cu : the same passes at the HBM rate (warp per row / lane-per-row chains); *handled = 0 -> not covered, use the kernels above
+int launch_row_stats_warp(const MatrixView& m, void* norms, void* inv_norms, float* sqnorms, float* d_stats, int* d_nan, cudaStream_t s,
+                          int* handled);
+int launch_pearson_stats_warp(const MatrixView& m, void* pmean, void* pstd, void* pscale, float* d_stats, cudaStream_t s, int* handled);
+int launch_normalize_rows_warp(int dtype, int64_t n, int64_t d, const void* src, void* dst, cudaStream_t s, int* handled);
+int launch_scores_rowwise(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc, const double* qaux,
+                          double* totals, void* typed, int distance, cudaStream_t s, int* handled);
 
 // ---- batched_tc.cu : tcgen05 batched contraction + threshold select
 struct TcWorkspace {

@@ -74,6 +74,9 @@ __global__ void row_stats_kernel(const void* rows, int64_t n, int64_t d, void* n
 
 int launch_row_stats(const MatrixView& m, void* norms, void* inv_norms, float* sqnorms, float* d_stats, int* d_nan, cudaStream_t s) {
   if (m.n == 0) return 0;
+  int handled = 0;
+  HDB_TRY(launch_row_stats_warp(m, norms, inv_norms, sqnorms, d_stats, d_nan, s, &handled));      // warp per row, HBM rate
+  if (handled) return 0;
   int threads = 128;
   int64_t blocks = (m.n + threads - 1) / threads;
   if (blocks > 0x7fffffff) return fail("row_stats: too many rows");
@@ -139,6 +142,9 @@ __global__ void pearson_stats_kernel(const void* rows, int64_t n, int64_t d, voi
 // d_stats[0], [2] start at the running maxima (0 at first), d_stats[1] at the bits of the running -min std (0xffffffff at first)
 int launch_pearson_stats(const MatrixView& m, void* pmean, void* pstd, void* pscale, float* d_stats, cudaStream_t s) {
   if (m.n == 0) return 0;
+  int handled = 0;
+  HDB_TRY(launch_pearson_stats_warp(m, pmean, pstd, pscale, d_stats, s, &handled));
+  if (handled) return 0;
   int threads = 128;
   int64_t blocks = (m.n + threads - 1) / threads;
   if (blocks > 0x7fffffff) return fail("pearson_stats: too many rows");
@@ -490,6 +496,9 @@ __global__ void normalize_rows_kernel(const void* src, void* dst, int64_t n, int
 }
 int launch_normalize_rows(int dtype, int64_t n, int64_t d, const void* src, void* dst, cudaStream_t s) {
   if (n == 0) return 0;
+  int handled = 0;
+  HDB_TRY(launch_normalize_rows_warp(dtype, n, d, src, dst, s, &handled));
+  if (handled) return 0;
   int64_t blocks = (n + 127) / 128;
   if (dtype == 0) normalize_rows_kernel<0><<<(unsigned)blocks, 128, 0, s>>>(src, dst, n, d);
   else if (dtype == 1) normalize_rows_kernel<1><<<(unsigned)blocks, 128, 0, s>>>(src, dst, n, d);

@@ -19,6 +19,7 @@ METRIC_IDS = {
     "pearson_correlation": 6,
 }
 FLAG_FALLBACK, FLAG_QUERY_NAN, FLAG_TENSOR, FLAG_UNCERTIFIED = 1, 2, 4, 8
+SCORES_DISTANCE = 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libhyperdb_b200.so")
 _lib = None
@@ -51,6 +52,7 @@ SIGNATURES = {
     "hdb_matrix_stage1_recency": (C.c_int, [vp, C.c_double, C.c_double]),
     "hdb_query": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, i64, i64, C.c_double, vp, vp, vp, vp, C.c_int]),
     "hdb_scores": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]),
+    "hdb_scores_ex": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "hdb_normalize_rows": (C.c_int, [C.c_int, C.c_int, i64, i64, vp, C.c_int, vp, C.c_int]),
     "hdb_merge_topk": (C.c_int, [C.c_int, vp, i64, i64, i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]),
     "hdb_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.POINTER(vp)]),

@@ -257,8 +257,9 @@ class DeviceMatrix:
                                   C.c_void_p(out_idx.data_ptr()), C.c_void_p(out_score.data_ptr()),
                                   C.c_void_p(out_count.data_ptr()), C.c_void_p(out_flags.data_ptr()), N.HDB_DEVICE))
 
-    def scores(self, query, metric):
-        """The metric function's own output for every stored row (NumPy result dtype; uint64 for hamming)."""
+    def scores(self, query, metric, distance=False):
+        """The metric function's own output for every stored row (NumPy result dtype; uint64 for hamming).
+        distance=True (euclidean only): the distance itself, euclidean_metric(..., get_similarity_score=False)."""
         mid = N.METRIC_IDS.get(metric)
         if mid is None:
             raise ValueError(f"Unknown metric: {metric}")
@@ -268,8 +269,8 @@ class DeviceMatrix:
         rdt = np.promote_types(self.np_dtype, q.dtype)
         out = np.empty(self.shape[0], np.uint64 if metric == "hamming_distance" else (np.float64 if metric in ("jaccard_similarity", "pearson_correlation") else rdt))
         got = C.c_int()
-        N.check(N.lib().hdb_scores(self._h, mid, C.c_void_p(q.ctypes.data), _NP2HDB[q.dtype], N.HDB_HOST,
-                                   C.c_void_p(out.ctypes.data), N.HDB_HOST, C.byref(got)))
+        N.check(N.lib().hdb_scores_ex(self._h, mid, C.c_void_p(q.ctypes.data), _NP2HDB[q.dtype], N.HDB_HOST,
+                                      C.c_void_p(out.ctypes.data), N.HDB_HOST, C.byref(got), N.SCORES_DISTANCE if distance else 0))
         assert np.dtype(_HDB2NP[got.value]) == out.dtype
         return out
 

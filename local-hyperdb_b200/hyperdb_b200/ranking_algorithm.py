@@ -21,6 +21,13 @@ from . import _native as N
 from .device_matrix import DeviceMatrix, as_float_array
 
 _PATH_MODE = 0
+_DEVICE = 0
+
+
+def set_device(device: int):
+    """CUDA device the stateless functions of this module run on (default 0)."""
+    global _DEVICE
+    _DEVICE = int(device)
 
 
 def set_path_mode(mode: int):
@@ -55,15 +62,15 @@ def get_norm_vector(vector):
     flat = v.reshape(-1, v.shape[-1]) if v.ndim >= 1 and v.size else v.reshape(0, 1)
     out = np.empty_like(flat)
     import ctypes as C
-    N.check(N.lib().hdb_normalize_rows(0, {2: 0, 4: 1, 8: 2}[flat.dtype.itemsize], flat.shape[0], flat.shape[1],
+    N.check(N.lib().hdb_normalize_rows(_DEVICE, {2: 0, 4: 1, 8: 2}[flat.dtype.itemsize], flat.shape[0], flat.shape[1],
                                        C.c_void_p(flat.ctypes.data), N.HDB_HOST, C.c_void_p(out.ctypes.data), N.HDB_HOST))
     return out.reshape(v.shape)
 
 
-def _scores(vectors, query_vector, metric):
-    m = DeviceMatrix(_matrix(vectors))
+def _scores(vectors, query_vector, metric, distance=False):
+    m = DeviceMatrix(_matrix(vectors), device=_DEVICE)
     try:
-        return m.scores(_query_1d(query_vector), metric)
+        return m.scores(_query_1d(query_vector), metric, distance=distance)
     finally:
         m.close()
 
@@ -82,12 +89,9 @@ def cosine_similarity(vectors, query_vector):
 
 
 def euclidean_metric(vectors, query_vector, get_similarity_score=True):
-    """hyperdb/ranking_algorithm.py:44-52 -- 1/(1+||v-q||_2) (or the distance itself)."""
-    sims = _scores(vectors, query_vector, "euclidean_metric")
-    if get_similarity_score:
-        return sims
-    one = sims.dtype.type(1)
-    return one / sims - one
+    """hyperdb/ranking_algorithm.py:44-52 -- 1/(1+||v-q||_2), or with get_similarity_score=False the distance
+    np.linalg.norm(v - q, axis=1) itself (computed by the kernel, never reconstructed from the similarity)."""
+    return _scores(vectors, query_vector, "euclidean_metric", distance=not get_similarity_score)
 
 
 def manhattan_distance(vectors, query_vector):
@@ -145,7 +149,7 @@ def hyperDB_ranking_algorithm_sort(vectors, query_vector, top_k=5, metric='cosin
         raise np.exceptions.AxisError(1, v.ndim)
     if v.shape[0] == 0:
         raise UnboundLocalError("cannot access local variable 'top_indices' where it is not associated with a value")
-    m = DeviceMatrix(v)                                      # NaN in vectors -> ValueError here
+    m = DeviceMatrix(v, device=_DEVICE)                      # NaN in vectors -> ValueError here
     try:
         m.set_path(_PATH_MODE)
         bias = float(recency_bias)

@@ -382,6 +382,9 @@ class GraphedQuery:
         import torch
         self.sm = sharded
         eng = sharded.engine
+        if getattr(eng, "post", None) is not None:
+            # pipelined mode spreads one step over internal streams whose cross-step events cannot be captured
+            raise RuntimeError("GraphedQuery needs the un-pipelined engine: call enable_pipeline(False) first")
         self.q_static = queries_like.clone()
         side = torch.cuda.Stream(device=eng.device)
         side.wait_stream(torch.cuda.current_stream(eng.device))

@@ -163,6 +163,15 @@ def pearson(v, q):
     return out
 
 
+def euclidean_distance(vectors, query):
+    """euclidean_metric(..., get_similarity_score=False), hyperdb/ranking_algorithm.py:49-52: np.linalg.norm(v - q, axis=1)
+    in the promoted dtype (element-wise subtract and square, NumPy's pairwise sum, sqrt)."""
+    v, q = _as_float(vectors), _as_float(query)
+    R = _F[np.dtype(result_dtype(v, q))]
+    with np.errstate(over="ignore", under="ignore", invalid="ignore", divide="ignore"):
+        return row_norm(v.astype(R) - q.astype(R))
+
+
 def scores(vectors, query, metric):
     """Canonical similarity vector in the reference's result dtype (uint64 for hamming)."""
     v, q = _as_float(vectors), _as_float(query)

@@ -32,6 +32,8 @@ def emul(tmp_path_factory):
     lib = C.CDLL(so)
     lib.emul_pairwise_sum.restype = C.c_double
     lib.emul_pairwise_sum.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    lib.emul_pairwise_sum_plan.restype = C.c_double
+    lib.emul_pairwise_sum_plan.argtypes = [C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.emul_norm.restype = C.c_double
     lib.emul_norm.argtypes = [C.c_int, C.c_void_p, C.c_int64]
     lib.emul_mean_std.restype = None

@@ -46,6 +46,16 @@ double emul_pairwise_sum(int dt, const void* x, int n) {
   return pairwise_sum<2>([&](int i) { return load_as_double(x, 2, i); }, n);
 }
 
+// the same sum through the host-built pairwise PLAN the row-wise kernels use (csrc/rowwise.cu); -1 leaves = no plan
+double emul_pairwise_sum_plan(int dt, const void* x, int n, int* nleaves) {
+  PwPlan plan;
+  if (!pw_plan_build(plan, n)) { *nleaves = -1; return 0.0; }
+  *nleaves = plan.nleaves;
+  if (dt == 0) return (double)pairwise_sum_plan_seq<0>([&](int i) { return (float)load_as_double(x, 0, i); }, plan);
+  if (dt == 1) return (double)pairwise_sum_plan_seq<1>([&](int i) { return (float)load_as_double(x, 1, i); }, plan);
+  return pairwise_sum_plan_seq<2>([&](int i) { return load_as_double(x, 2, i); }, plan);
+}
+
 double emul_norm(int dt, const void* x, int64_t d) {
   if (dt == 0) return (double)canonical_norm<0>(x, d);
   if (dt == 1) return (double)canonical_norm<1>(x, d);
@@ -64,7 +74,7 @@ void emul_mean_std(int dt, const void* x, int64_t d, int scalar, double* mean, d
 double emul_similarity(int rdt, int sdt, int metric, const void* row, const double* qc, int64_t d, double nrm, double aux2, double qstd,
                        const uint32_t* bitrow, const uint32_t* qbits, int words) {
   CanonArgs a;
-  a.sdt = sdt; a.d = d; a.qc = qc; a.qbits = qbits; a.words = words; a.metric = metric; a.qstd = qstd;
+  a.sdt = sdt; a.d = d; a.qc = qc; a.qbits = qbits; a.words = words; a.metric = metric; a.qstd = qstd; a.distance = 0;
   return canonical_similarity_rt(a, rdt, row, bitrow, nrm, aux2);
 }
 

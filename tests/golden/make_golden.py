@@ -6,7 +6,8 @@ on the seeded inputs of cases.py.  Run in the build container only (the GPU box 
 
 Files written:
   sort_golden.npz    per case: input digest, the metric function's full output (bytes of the
-                     reference's own dtype), and hyperDB_ranking_algorithm_sort's (indices, scores)
+                     reference's own dtype), and hyperDB_ranking_algorithm_sort's (indices, scores);
+                     euclidean cases also hold euclidean_metric(..., get_similarity_score=False)
   pokemon_c1.npz     BASELINE config C1: demo/pokemon_hyperdb.pickle vectors (fp32, exact) + the
                      reference's cosine top-5 for several stored rows used as queries
   hyperdb_tail.npz   HyperDB.query brute-force tail run through the real HyperDB class (third-party
@@ -84,6 +85,11 @@ def gen_sort(ref):
                 timestamps=ts, recency_bias=case["bias"] if ts is not None else 0)
         rec["sims_dtype"] = str(sims.dtype)
         out[f"sims_{i}"] = np.frombuffer(np.ascontiguousarray(sims).tobytes(), np.uint8)
+        if case["metric"] == "euclidean_metric":         # the distance form, ranking_algorithm.py:49-52 (same dtype as sims)
+            with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+                dist = np.asarray(ref.euclidean_metric(V.copy(), q.copy(), get_similarity_score=False))
+            assert dist.dtype == sims.dtype
+            out[f"dist_{i}"] = np.frombuffer(np.ascontiguousarray(dist).tobytes(), np.uint8)
         out[f"idx_{i}"] = np.asarray(idx, np.int64)
         out[f"sc_{i}"] = np.asarray(sc, np.float64).reshape(-1)
         meta.append(rec)

@@ -19,6 +19,14 @@ def load_sort_golden():
     return out
 
 
+def load_dist_golden():
+    """[(case, distances)] for the euclidean cases: euclidean_metric(V, q, get_similarity_score=False) of the real reference."""
+    z = np.load(os.path.join(GOLD, "sort_golden.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    return [(case, np.frombuffer(bytes(z[f"dist_{i}"]), dtype=np.dtype(case["sims_dtype"])))
+            for i, case in enumerate(meta) if f"dist_{i}" in z.files]
+
+
 def case_id(case):
     return f"{case['metric'][:4]}-{case['vdt']}x{case['qdt']}-{case['n']}x{case['d']}-{case['kind']}-k{case['k']}" + ("-ts" if case["ts"] else "")
 

@@ -40,6 +40,27 @@ def test_pairwise_sum_norm_mean_std(emul):
             assert _same(m.value, float(np.mean(x2, axis=1)[0])) and _same(s.value, float(np.std(x2, axis=1)[0])), (trial, d, dt)
 
 
+def test_pairwise_plan_matches_numpy(emul):
+    """The host-built pairwise PLAN of csrc/rowwise.cu (leaves + post-order addition program) evaluates to np.add.reduce
+    bit for bit for every length, and gives up (no plan) only beyond kPlanLeaves leaves."""
+    rng = np.random.default_rng(19)
+    lengths = list(range(1, 300)) + [383, 384, 385, 511, 512, 513, 767, 768, 769, 1000, 1023, 1024, 1025, 1536, 2047, 2048, 3000, 4096,
+                                      4097, 5000, 8191, 8192]
+    planned = 0
+    for i, d in enumerate(lengths):
+        dt = DTS[i % 3]
+        x = np.ascontiguousarray((rng.standard_normal(d) * float(rng.choice([0.01, 1.0, 40.0])) + float(rng.choice([0.0, 3.0]))).astype(dt))
+        nl = C.c_int()
+        with np.errstate(all="ignore"):
+            got = emul.emul_pairwise_sum_plan(DT[x.dtype], C.c_void_p(x.ctypes.data), d, C.byref(nl))
+            if nl.value < 0:
+                assert d > 4096
+                continue
+            planned += 1
+            assert nl.value >= 1 and _same(got, float(np.add.reduce(x))), (d, dt)
+    assert planned >= len(lengths) - 3
+
+
 def _prepared_query(q, metric):
     """What prep_query stores in qc (float64 carrier) for this metric."""
     with np.errstate(all="ignore"):

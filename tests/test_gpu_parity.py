@@ -97,6 +97,37 @@ def test_metric_functions_golden(hb, entry):
         assert np.all(np.abs(a - b) <= TOL[dt] * np.maximum(np.abs(b), cond))
 
 
+DIST = G.load_dist_golden()
+
+
+@pytest.mark.parametrize("entry", DIST, ids=[G.case_id(e[0]) for e in DIST])
+def test_euclidean_distance_form_golden(hb, entry):
+    """euclidean_metric(V, q, get_similarity_score=False) (hyperdb/ranking_algorithm.py:49-52): the kernel's own distance,
+    bit-equal to the REAL reference's output in every dtype -- not reconstructed from 1/(1+d)."""
+    case, ref_dist = entry
+    V, q, _ts = G.inputs(case)
+    out = hb.euclidean_metric(V, q, get_similarity_score=False)
+    assert out.dtype == ref_dist.dtype and out.shape == ref_dist.shape
+    assert out.tobytes() == ref_dist.tobytes()
+    sims = hb.euclidean_metric(V, q)                         # default form unchanged
+    one = out.dtype.type(1)
+    with np.errstate(all="ignore"):
+        assert sims.tobytes() == (one / (one + ref_dist)).tobytes()
+
+
+def test_euclidean_distance_small_and_zero(hb):
+    """exact matches give exactly 0 and tiny distances keep their relative accuracy (the 1/s - 1 round trip lost both)"""
+    rng = np.random.default_rng(5)
+    for dt in (np.float16, np.float32, np.float64):
+        V = rng.standard_normal((64, 40)).astype(dt)
+        q = V[7].copy()
+        V[9] = q + np.asarray(1e-3, dt)
+        d = hb.euclidean_metric(V, q, get_similarity_score=False)
+        with np.errstate(all="ignore"):
+            want = K.euclidean_distance(V, q)
+        assert d.dtype == np.dtype(dt) and d.tobytes() == want.tobytes() and d[7] == 0
+
+
 def test_get_norm_vector(hb):
     rng = np.random.default_rng(11)
     for dt in (np.float16, np.float32, np.float64):

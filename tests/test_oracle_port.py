@@ -80,3 +80,20 @@ def test_tail_matches_real_hyperdb():
             assert list(ids) == list(z[f"ids_{si}_{qi}"]), (si, qi)
             blas = spec["metric"] in ("dot_product", "cosine_similarity")
             np.testing.assert_allclose(sc, z[f"sc_{si}_{qi}"], rtol=1e-5 if blas else 0, atol=0)
+
+
+DIST = G.load_dist_golden()
+
+
+@pytest.mark.parametrize("entry", DIST, ids=[G.case_id(e[0]) for e in DIST])
+def test_euclidean_distance_form(entry):
+    """euclidean_metric(..., get_similarity_score=False), hyperdb/ranking_algorithm.py:49-52: the port and the
+    explicit-arithmetic spec against the REAL reference's distances, bit for bit (NumPy loops only, no BLAS)."""
+    from oracle import canonical as K
+    case, ref_dist = entry
+    V, q, _ts = G.inputs(case)
+    with np.errstate(all="ignore"):
+        d_port = np.asarray(P.euclidean_scores(V, q, get_similarity_score=False))
+        d_spec = K.euclidean_distance(V, q)
+    assert d_port.dtype == ref_dist.dtype and d_port.tobytes() == ref_dist.tobytes()
+    assert d_spec.dtype == ref_dist.dtype and d_spec.tobytes() == ref_dist.tobytes()
