@@ -45,8 +45,10 @@ enum {
   HDB_FLAG_FALLBACK = 1,   /* the fused select did not certify; the exact full-vector path produced the result */
   HDB_FLAG_QUERY_NAN = 2,  /* the query holds a NaN (reference raises ValueError, ranking_algorithm.py:150-151) */
   HDB_FLAG_TENSOR = 4,     /* candidates came from the tcgen05 batched contraction */
-  HDB_FLAG_UNCERTIFIED = 8 /* device-output mode only: the certificate failed and nothing was recomputed;
-                              the caller must repeat the query with host outputs or path mode 1 */
+  HDB_FLAG_UNCERTIFIED = 8, /* device-output mode only: the certificate failed and nothing was recomputed;
+                               the caller must repeat the query with host outputs or path mode 1 */
+  HDB_FLAG_EXCHANGE_ERROR = 16 /* sharded path: a rank did not deliver its candidates in time; the step holds no results
+                                  (count 0) and the exchange must be rebuilt */
 };
 
 const char* hdb_last_error(void);
@@ -132,6 +134,21 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
               int64_t* out_idx, double* out_score, int64_t* out_count, uint32_t* out_flags,
               int out_space);
 
+/* ---- asynchronous host API: the same query without a synchronisation per call --------------------------------------
+ * hdb_query_submit enqueues the query (host or device `queries`), the copy of the result block to pinned host memory and
+ * a completion event, and returns a ticket; up to 4 tickets may be in flight, so that (with a post stream set, see
+ * hdb_matrix_set_post_stream) the host-to-device copy, the sweep, the certify step and the device-to-host copy of
+ * consecutive queries overlap.  hdb_query_collect waits for one ticket and
+ * writes out_idx / out_score [n_queries x top_k], out_count [n_queries] and out_flags.  Nothing is repaired here: a query
+ * whose flags carry HDB_FLAG_UNCERTIFIED must be repeated through hdb_query with host outputs (the Python host does).
+ * world = 1: results of this shard, out_flags [n_queries].  world > 1 (an exchange is attached, see
+ * hdb_matrix_attach_exchange): every rank submits the same batch; the ticket completes with the MERGED top-k of all
+ * shards and out_flags [world][n_queries] holds every shard's flags. */
+int hdb_query_submit(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q_space, int64_t n_queries,
+                     int64_t top_k, double recency_bias, int world, int64_t* ticket);
+int hdb_query_collect(hdb_matrix* m, int64_t ticket, int64_t* out_idx, double* out_score, int64_t* out_count,
+                      uint32_t* out_flags);
+
 /* ---- full similarity vector: the metric functions themselves, ranking_algorithm.py:24-113,:128-147 */
 /* out holds n_rows values of the NumPy result dtype promote(matrix dtype, q_dtype)
  * (uint64 for HDB_HAMMING, float64 for HDB_JACCARD and HDB_PEARSON, NaN where the reference returns NaN),
@@ -160,7 +177,7 @@ int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t n_que
 
 /* ---- multi-GPU: the same exchange + merge over NVLink peer memory, without a collective library call -------------
  * One process per GPU.  Every rank creates an exchange (a small device buffer of 4 slots x world x max_words 8-byte
- * words plus sequence flags), publishes its CUDA IPC handle (hdb_exchange_handle_bytes() bytes) to the other ranks by
+ * words plus arrival flags and per-reader consumed counters), publishes its CUDA IPC handle (hdb_exchange_handle_bytes() bytes) to the other ranks by
  * any means (the host uses torch.distributed once, at set-up) and connects to all of them.  hdb_exchange_step then
  * enqueues on `cuda_stream`: peer stores of this rank's packed result block
  *     [scores nq*k (f64) | ids nq*k (i64) | counts nq (i64) | flags nq (u32, padded to 8 bytes)]      (`words` words)
@@ -168,6 +185,15 @@ int hdb_merge_topk(int device, void* cuda_stream, int64_t n_lists, int64_t n_que
  * world x k candidates per query by (score desc, global id asc).  out_flags receives [world][nq] per-shard flags.
  * Every rank must call hdb_exchange_step the same number of times with the same (nq, k). */
 int hdb_exchange_create(int device, int world, int rank, int64_t max_words, hdb_exchange** out);
+/* Fused form: after attaching, every device-output hdb_query on `m` (outputs laid out as ONE packed block
+ * [scores | ids | counts | flags]) also delivers its results to every rank of `x` -- stored by the certify kernel itself
+ * where the batch ends in one certify launch, by a push kernel otherwise -- and the caller only enqueues the second half
+ * with hdb_exchange_collect_async (or uses hdb_query_submit / hdb_query_collect).  NULL detaches. */
+int hdb_matrix_attach_exchange(hdb_matrix* m, hdb_exchange* x);
+/* wait + merge of the current step on the exchange's own high-priority stream (hdb_exchange_stream). */
+int hdb_exchange_collect_async(hdb_exchange* x, int64_t n_queries, int64_t k, int64_t* out_idx, double* out_score,
+                               int64_t* out_count, uint32_t* out_flags);
+int hdb_exchange_stream(hdb_exchange* x, void** cuda_stream);
 int hdb_exchange_destroy(hdb_exchange* x);
 int hdb_exchange_handle_bytes(void);
 int hdb_exchange_local_handle(hdb_exchange* x, void* handle_out);
@@ -183,7 +209,9 @@ int hdb_exchange_step(hdb_exchange* x, void* cuda_stream, const void* mine, int6
 int hdb_exchange_push(hdb_exchange* x, void* cuda_stream, const void* mine, int64_t words);
 int hdb_exchange_wait_merge(hdb_exchange* x, void* cuda_stream, int64_t n_queries, int64_t k, int64_t* out_idx, double* out_score,
                             int64_t* out_count, uint32_t* out_flags);
-/* 1 if a wait gave up after 10 s because a peer never delivered (synchronises the device). */
+/* 1 if a wait gave up after 10 s because a peer never delivered (synchronises the device).  The step that timed out
+ * carries HDB_FLAG_UNCERTIFIED | HDB_FLAG_EXCHANGE_ERROR in every out_flags entry and count 0; the error is sticky and
+ * the ranks' step counters may disagree afterwards: destroy and rebuild the exchange. */
 int hdb_exchange_error(hdb_exchange* x, int* error);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
@@ -201,8 +229,9 @@ int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter);
  * durations in milliseconds, and resets the recorder. */
 int hdb_profile_enable(hdb_matrix* m, int max_pairs);
 int hdb_profile_read(hdb_matrix* m, int* n_launches, float* total_ms);
-/* Force a path for testing: 0 = automatic, 1 = always the exact full-vector path,
- * 2 = fused sweep only (fail instead of falling back), 3 = tensor-core batched path when eligible. */
+/* Force a path: 0 = automatic, 1 = always the exact full-vector path, 2 = fused sweep only (fail instead of falling
+ * back), 3 = tensor-core batched path when eligible, 4 = streaming sweep with the WIDE candidate class (128 candidates;
+ * the first repair step for a query the automatic path could not certify). */
 int hdb_matrix_set_path(hdb_matrix* m, int mode);
 
 #ifdef __cplusplus

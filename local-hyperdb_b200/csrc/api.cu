@@ -83,6 +83,21 @@ struct hdb_matrix {
   // per-launch event pairs around the dominant kernel (hdb_profile_*)
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
+  // row-sharded path: device-output queries also push their results to every rank of this exchange
+  hdb_exchange* xchg = nullptr;
+  // asynchronous host API (hdb_query_submit / hdb_query_collect): a ring of tickets, each with its device result
+  // blocks, a pinned host mirror and a completion event
+  struct Ticket {
+    bool busy = false;
+    int64_t nq = 0, k = 0;
+    int world = 1;
+    char* d_mine = nullptr; size_t mine_bytes = 0;     // local packed result [scores | ids | counts | flags]
+    char* d_res = nullptr; char* h_res = nullptr; size_t res_bytes = 0;   // [idx | score | count | flags world*nq]
+    cudaEvent_t ev = nullptr;
+  };
+  static constexpr int kTickets = 4;
+  Ticket tickets[kTickets];
+  int64_t next_ticket = 0;
   // last query (for hdb_time_last_query)
   struct { bool valid = false; int metric = 0, rdt = 0, kp = 0; int64_t nq = 0, k = 0; double bias = 0; } last;
 };
@@ -208,6 +223,12 @@ int hdb_matrix_destroy(hdb_matrix* m) {
                   m->tc.cand_count, m->tc.rec, m->tc.rec_count, m->tc.qsq};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (m->h_block) cudaFreeHost(m->h_block);
+  for (auto& t : m->tickets) {
+    if (t.d_mine) cudaFree(t.d_mine);
+    if (t.d_res) cudaFree(t.d_res);
+    if (t.h_res) cudaFreeHost(t.h_res);
+    if (t.ev) cudaEventDestroy(t.ev);
+  }
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   delete m;
   return 0;
@@ -265,7 +286,7 @@ int hdb_matrix_set_sweep_overlap(hdb_matrix* m, int on) {
 
 int hdb_matrix_set_path(hdb_matrix* m, int mode) {
   if (!m) return fail("null handle");
-  if (mode < 0 || mode > 3) return fail("hdb_matrix_set_path: mode must be 0..3");
+  if (mode < 0 || mode > 4) return fail("hdb_matrix_set_path: mode must be 0..4");
   m->path_mode = mode;
   return 0;
 }
@@ -682,6 +703,7 @@ static int ensure_workspace(hdb_matrix* m, int64_t nq, int64_t k) {
 
 static int pick_kp(const hdb_matrix* m, int64_t k) {
   if (m->path_mode == 1) return 0;
+  if (m->path_mode == 4 && k <= 100) return 128;          // repair mode: the wide candidate class on the streaming sweep
   if (k <= 16) return 32;
   if (k <= 100) return 128;
   return 0;
@@ -690,7 +712,7 @@ static int pick_kp(const hdb_matrix* m, int64_t k) {
 // Enqueue the fused path for queries [b0, b0+cnt) of the prepared batch; results go to (idx, score, count, flags).
 static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int64_t cnt, int64_t k, const RowFilter& f,
                      int64_t* idx, double* score, int64_t* count, uint32_t* flags, cudaStream_t fin_stream = nullptr,
-                     cudaStream_t sweep_stream = nullptr) {
+                     cudaStream_t sweep_stream = nullptr, const PushTarget* push = nullptr) {
   MatrixView v = view_of(m);
   cudaStream_t sw = sweep_stream ? sweep_stream : m->stream;
   if (!(fin_stream && fin_stream != m->stream)) HDB_CUDA(cudaMemsetAsync(m->tau + b0, 0, (size_t)cnt * 8, sw));   // pipelined: prep zeroed it
@@ -715,6 +737,8 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
   a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
   a.uncertified = m->uncertified;
   a.cand_count = nullptr; a.cand_stride = 0; a.tau0 = nullptr; a.extra_flags = 0; a.tau0_negd2 = 0;
+  a.push = PushTarget{};
+  if (push) a.push = *push;          // row-sharded: the certify kernel stores its results into every rank's exchange slot
   if (fin_stream && fin_stream != m->stream) {
     // pipelined: the certify step runs on the post stream, ordered after the sweeps by an event
     HDB_CUDA(cudaEventRecord(m->ev_select, sw));
@@ -778,6 +802,7 @@ static int run_tensor(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, in
   a.out_idx = idx + b0 * k; a.out_score = score + b0 * k; a.out_count = count + b0; a.out_flags = flags ? flags + b0 : nullptr;
   a.uncertified = m->uncertified;
   a.cand_count = m->tc.cand_count; a.cand_stride = m->tc.cap; a.tau0 = m->tc.tau0; a.extra_flags = HDB_FLAG_TENSOR;
+  a.push = PushTarget{};
   a.tau0_negd2 = (metric == HDB_EUCLIDEAN);
   return launch_finalize(a, cnt, m->stream);
 }
@@ -853,6 +878,20 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   int64_t* count = dev_out ? out_count : m->o_count;
   uint32_t* flags = dev_out ? out_flags : m->o_flags;
 
+  // row-sharded path: the local result also goes to every rank of the attached exchange
+  PushTarget push{};
+  bool want_push = false, fused_push = false;
+  const int64_t msg_words = 2 * nq * k + nq + (nq + 1) / 2;
+  if (m->xchg && dev_out) {
+    if (!out_flags || reinterpret_cast<char*>(out_idx) != reinterpret_cast<char*>(out_score) + (size_t)nq * k * 8 ||
+        reinterpret_cast<char*>(out_count) != reinterpret_cast<char*>(out_idx) + (size_t)nq * k * 8 ||
+        reinterpret_cast<char*>(out_flags) != reinterpret_cast<char*>(out_count) + (size_t)nq * 8)
+      return fail("hdb_query: with an exchange attached the device outputs must form one packed block [scores | ids | counts | flags]");
+    if (msg_words > exchange_max_words(m->xchg)) return fail("hdb_query: the batch does not fit the attached exchange buffer");
+    HDB_TRY(exchange_push_target(m->xchg, nq, k, &push));
+    want_push = true;
+  }
+
   int kp = pick_kp(m, k);
   const size_t qsm = (size_t)m->d * (m->dtype == 2 ? 8 : 4);
   if (kp && qsm + 40000 > 200 * 1024) kp = 0;                     // query does not fit next to the lists
@@ -863,7 +902,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   if (k == 0) {
     HDB_CUDA(cudaMemsetAsync(count, 0, (size_t)nq * 8, m->stream));
     if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
-  } else if (kp && m->path_mode != 2 && batched_tc_supported(view_of(m), metric, q_dtype, nq, use_decay)) {
+  } else if (kp && m->path_mode != 2 && m->path_mode != 4 && batched_tc_supported(view_of(m), metric, q_dtype, nq, use_decay)) {
     if (m->dtype == 1) kp = 128;         // tf32 select: wider error band, so certify a wider candidate list
     m->last.kp = kp;
     HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
@@ -883,11 +922,14 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
         sw = m->alt_stream;                                  // odd slots sweep on the alternate stream (see hdb_matrix::alt_stream)
         HDB_CUDA(cudaStreamWaitEvent(sw, m->ev_prep, 0));
       }
-      HDB_TRY(run_fused(m, metric, rdt, kp, b0, cnt, k, f, idx, score, count, flags, hand_over ? m->post_stream : nullptr, sw));
+      fused_push = want_push && nq <= kChunk;              // one certify launch covers the batch: it pushes by itself
+      HDB_TRY(run_fused(m, metric, rdt, kp, b0, cnt, k, f, idx, score, count, flags, hand_over ? m->post_stream : nullptr, sw,
+                        fused_push ? &push : nullptr));
       if (sw) { HDB_CUDA(cudaEventRecord(m->ev_alt, sw)); m->alt_pending = true; }
       on_post = hand_over;
     }
     if (pipelined && on_post) {
+      if (want_push && !fused_push) HDB_TRY(exchange_launch_push(m->xchg, m->post_stream, out_score, msg_words));
       hdb_matrix::QuerySlot& qs = m->slots[m->cur_slot];
       HDB_CUDA(cudaEventRecord(qs.done, m->post_stream));
       qs.pending = true;
@@ -904,6 +946,8 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
     HDB_CUDA(cudaStreamWaitEvent(m->post_stream, m->ev_select, 0));
     slot_store(m);
   }
+  if (want_push && !fused_push)         // tensor-core batches, the exact path, k = 0: push the packed block
+    HDB_TRY(exchange_launch_push(m->xchg, pipelined ? m->post_stream : m->stream, out_score, msg_words));
   if (dev_out) return 0;
 
   // host outputs: ONE device->pinned-host copy of [idx | score | count | flags], one synchronisation;
@@ -924,9 +968,9 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
       if (m->path_mode == 2) return fail("hdb_query: fused path forced but the certificate failed");
       if (fixed.empty()) fixed.assign(h_flags, h_flags + nq);
       bool done = false;
-      if ((h_flags[b] & HDB_FLAG_TENSOR) && k <= 100) {
-        // a query the batched pass could not certify: first retry with the streaming sweep and the wide
-        // candidate class (IEEE fp32 accumulation, 128 candidates), only then pay for the exact path
+      if (((h_flags[b] & HDB_FLAG_TENSOR) || m->last.kp < 128) && k <= 100) {
+        // a query the batched pass, or the narrow candidate class, could not certify: first retry with the streaming
+        // sweep and the wide candidate class (IEEE fp32 accumulation, 128 candidates), only then pay for the exact path
         HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
         HDB_TRY(run_fused(m, metric, rdt, 128, b, 1, k, f, idx, score, count, flags));
         int bad = 0;
@@ -954,6 +998,98 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   }
   memcpy(out_count, h_count, (size_t)nq * 8);
   if (out_flags) memcpy(out_flags, h_flags, (size_t)nq * 4);
+  return 0;
+}
+
+int hdb_matrix_attach_exchange(hdb_matrix* m, hdb_exchange* x) {
+  if (!m) return fail("null handle");
+  if (x && exchange_device(x) != m->device) return fail("hdb_matrix_attach_exchange: the exchange lives on another device");
+  HDB_TRY(quiesce(m));
+  m->xchg = x;
+  return 0;
+}
+
+// ---- asynchronous host API --------------------------------------------------------------------------------------
+static int ticket_reserve(hdb_matrix::Ticket& t, int64_t nq, int64_t k, int world) {
+  const size_t kk = (size_t)(k > 0 ? k : 0);
+  const size_t mine = ((size_t)nq * kk * 16 + (size_t)nq * 8 + (size_t)((nq + 1) / 2) * 8);
+  const size_t res = (size_t)nq * kk * 16 + (size_t)nq * 8 + (((size_t)world * nq * 4 + 7) & ~size_t(7));
+  if (t.mine_bytes < mine) {
+    if (t.d_mine) cudaFree(t.d_mine);
+    t.d_mine = nullptr; t.mine_bytes = 0;
+    HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.d_mine), mine));
+    t.mine_bytes = mine;
+  }
+  const size_t need = res > mine ? res : mine;
+  if (t.res_bytes < need) {
+    if (t.d_res) cudaFree(t.d_res);
+    if (t.h_res) cudaFreeHost(t.h_res);
+    t.d_res = nullptr; t.h_res = nullptr; t.res_bytes = 0;
+    HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.d_res), need));
+    HDB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&t.h_res), need));
+    t.res_bytes = need;
+  }
+  if (!t.ev) HDB_CUDA(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+  t.nq = nq; t.k = (int64_t)kk; t.world = world;
+  return 0;
+}
+
+int hdb_query_submit(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q_space, int64_t nq, int64_t top_k,
+                     double recency_bias, int world, int64_t* ticket) {
+  if (!m || !ticket) return fail("hdb_query_submit: NULL argument");
+  if (nq < 1) return fail("hdb_query_submit: need at least one query");
+  if (world < 1 || (world > 1 && !m->xchg)) return fail("hdb_query_submit: world > 1 needs an attached exchange");
+  HDB_CUDA(cudaSetDevice(m->device));
+  hdb_matrix::Ticket& t = m->tickets[m->next_ticket % hdb_matrix::kTickets];
+  if (t.busy) return fail("hdb_query_submit: too many queries in flight, collect the oldest ticket first");
+  const int64_t k = top_k > 0 ? top_k : 0;
+  HDB_TRY(ticket_reserve(t, nq, k, m->xchg ? world : 1));
+  double* sc = reinterpret_cast<double*>(t.d_mine);
+  int64_t* idx = reinterpret_cast<int64_t*>(t.d_mine + (size_t)nq * k * 8);
+  int64_t* cnt = reinterpret_cast<int64_t*>(t.d_mine + (size_t)nq * k * 16);
+  uint32_t* flg = reinterpret_cast<uint32_t*>(t.d_mine + (size_t)nq * k * 16 + (size_t)nq * 8);
+  HDB_TRY(hdb_query(m, metric, queries, q_dtype, q_space, nq, top_k, recency_bias, idx, sc, cnt, flg, HDB_DEVICE));
+  if (m->xchg) {
+    // the wait + merge kernel is ordered after the pushes through the arrival flags, not through a stream
+    cudaStream_t xs = exchange_stream(m->xchg);
+    int64_t* r_idx = reinterpret_cast<int64_t*>(t.d_res);
+    double* r_sc = reinterpret_cast<double*>(t.d_res + (size_t)nq * k * 8);
+    int64_t* r_cnt = reinterpret_cast<int64_t*>(t.d_res + (size_t)nq * k * 16);
+    uint32_t* r_flg = reinterpret_cast<uint32_t*>(t.d_res + (size_t)nq * k * 16 + (size_t)nq * 8);
+    HDB_TRY(exchange_launch_wait_merge(m->xchg, xs, nq, k, r_idx, r_sc, r_cnt, r_flg));
+    const size_t res = (size_t)nq * k * 16 + (size_t)nq * 8 + (((size_t)t.world * nq * 4 + 7) & ~size_t(7));
+    HDB_CUDA(cudaMemcpyAsync(t.h_res, t.d_res, res, cudaMemcpyDeviceToHost, xs));
+    HDB_CUDA(cudaEventRecord(t.ev, xs));
+  } else {
+    // pipelined mode (a post stream is set): results become valid in post-stream order; else on the handle's stream
+    cudaStream_t rs = m->post_stream ? m->post_stream : m->stream;
+    const size_t mine = (size_t)nq * k * 16 + (size_t)nq * 8 + (size_t)((nq + 1) / 2) * 8;
+    HDB_CUDA(cudaMemcpyAsync(t.h_res, t.d_mine, mine, cudaMemcpyDeviceToHost, rs));
+    HDB_CUDA(cudaEventRecord(t.ev, rs));
+  }
+  t.busy = true;
+  *ticket = m->next_ticket++;
+  return 0;
+}
+
+int hdb_query_collect(hdb_matrix* m, int64_t ticket, int64_t* out_idx, double* out_score, int64_t* out_count, uint32_t* out_flags) {
+  if (!m || !out_count) return fail("hdb_query_collect: NULL argument");
+  if (ticket < 0 || ticket >= m->next_ticket || ticket + hdb_matrix::kTickets < m->next_ticket) return fail("hdb_query_collect: unknown ticket");
+  hdb_matrix::Ticket& t = m->tickets[ticket % hdb_matrix::kTickets];
+  if (!t.busy) return fail("hdb_query_collect: the ticket was already collected");
+  HDB_CUDA(cudaSetDevice(m->device));
+  HDB_CUDA(cudaEventSynchronize(t.ev));
+  t.busy = false;
+  const size_t nk = (size_t)t.nq * t.k;
+  if (m->xchg) {          // [idx | score | count | flags world*nq]
+    if (nk) { memcpy(out_idx, t.h_res, nk * 8); memcpy(out_score, t.h_res + nk * 8, nk * 8); }
+    memcpy(out_count, t.h_res + nk * 16, (size_t)t.nq * 8);
+    if (out_flags) memcpy(out_flags, t.h_res + nk * 16 + (size_t)t.nq * 8, (size_t)t.world * t.nq * 4);
+  } else {                // the local packed block [scores | ids | counts | flags]
+    if (nk) { memcpy(out_score, t.h_res, nk * 8); memcpy(out_idx, t.h_res + nk * 8, nk * 8); }
+    memcpy(out_count, t.h_res + nk * 16, (size_t)t.nq * 8);
+    if (out_flags) memcpy(out_flags, t.h_res + nk * 16 + (size_t)t.nq * 8, (size_t)t.nq * 4);
+  }
   return 0;
 }
 

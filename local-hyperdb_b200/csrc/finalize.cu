@@ -10,6 +10,7 @@
 
 #include "canonical.cuh"
 #include "certificate.cuh"
+#include "hdb_exchange.cuh"
 #include "hdb_internal.h"
 #include "../../include/hyperdb_b200.h"
 
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     }
   }
   if (m < kk || overflow) certified = false;
+  const uint32_t flags_out = qflag | a.extra_flags | (certified ? 0u : kFlagUncertified);
   for (int i = tid; i < a.k; i += kFinThreads) {
     const bool have = i < kk && i < m;
     a.out_idx[b * a.k + i] = have ? (int64_t)o_row[i] + a.m.row_offset : -1;
@@ -351,8 +353,34 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
   }
   if (tid == 0) {
     a.out_count[b] = kk;
-    if (a.out_flags) a.out_flags[b] = qflag | a.extra_flags | (certified ? 0u : kFlagUncertified);
+    if (a.out_flags) a.out_flags[b] = flags_out;
     if (!certified) atomicAdd(a.uncertified, 1);
+  }
+  // ---- fused push (row-sharded path): this query's records go straight into EVERY rank's exchange slot over NVLink
+  //      peer memory; the last CTA of the launch publishes the arrival flags.  No kernel boundary, no packed copy.
+  if (a.push.peer) {
+    __shared__ unsigned long long s_push_step;
+    if (tid == 0) s_push_step = a.push.ctr[kCtrPushStep];
+    __syncthreads();
+    const unsigned long long step = s_push_step;
+    if (tid < a.push.world) push_wait_consumed(a.push, tid, step);
+    __syncthreads();
+    const int64_t nq = a.push.nq, k = a.k;
+    for (int g = 0; g < a.push.world; ++g) {
+      unsigned long long* dst = push_slot(a.push, g, step);
+      for (int i = tid; i < k; i += kFinThreads) {
+        const bool have = i < kk && i < m;
+        reinterpret_cast<double*>(dst)[b * k + i] = have ? o_tot[i] : -INFINITY;
+        reinterpret_cast<int64_t*>(dst)[nq * k + b * k + i] = have ? (int64_t)o_row[i] + a.m.row_offset : -1;
+      }
+      if (tid == 0) {
+        reinterpret_cast<int64_t*>(dst)[2 * nq * k + b] = kk;
+        reinterpret_cast<uint32_t*>(dst + 2 * nq * k + nq)[b] = flags_out;
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) push_publish(a.push, step, gridDim.x);
   }
 }
 

@@ -37,6 +37,21 @@ struct RowFilter {
   double bias;            // recency_bias
 };
 
+// ---- peer-memory exchange (exchange.cu): what a pushing kernel needs to know
+constexpr int kXSlots = 4;                // ring of message slots per (reader, source)
+enum { kCtrPushStep = 0, kCtrWaitStep = 1, kCtrPushDone = 2, kCtrWaitDone = 3, kCtrCount = 4 };
+struct PushTarget {
+  char* const* peer;        // device array [world]: every rank's exchange buffer as mapped here (nullptr = no exchange)
+  int world, rank;
+  int64_t max_words;        // 8-byte words per (slot, source) message
+  size_t data_bytes;        // offset of the arrival flags [kXSlots][world]
+  size_t consumed_off;      // offset of the consumed counters [world]
+  unsigned long long* ctr;  // [kCtr*] device counters of this rank
+  const char* local;        // this rank's own buffer
+  int* error;
+  int64_t nq, k;            // message geometry: scores nq*k (f64) | ids nq*k (i64) | counts nq (i64) | flags nq (u32)
+};
+
 struct QueryBuffers {     // per-batch device buffers written by prep_query
   void* qa;               // [B][d] query in the sweep's accumulate type (float, or double for f64 storage)
   double* qc;             // [B][d] canonical query values (dtype R widened to double)
@@ -117,6 +132,7 @@ struct FinalizeArgs {
   const float* tau0;             // [B] select threshold of the batched pass (rows below it were never appended)
   int tau0_negd2;                // tau0 is -distance^2 (batched euclidean): convert to a similarity before use
   uint32_t extra_flags;          // OR-ed into out_flags (HDB_FLAG_TENSOR)
+  PushTarget push;               // push.peer != nullptr: also store the results into every rank's exchange slot (fused push)
 };
 int launch_finalize(const FinalizeArgs& a, int64_t nq, cudaStream_t s);
 int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int rdt, const double* qc,
@@ -157,4 +173,16 @@ int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t n
 int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const float* qa, const double* qnorm, int64_t nq, int kp, int device,
                       const TcWorkspace& ws, cudaStream_t s);
 
+}  // namespace hdb
+
+// ---- exchange.cu (host side, used by api.cu)
+struct hdb_exchange;
+namespace hdb {
+int exchange_push_target(hdb_exchange* x, int64_t nq, int64_t k, PushTarget* out);
+int64_t exchange_max_words(const hdb_exchange* x);
+int exchange_device(const hdb_exchange* x);
+cudaStream_t exchange_stream(const hdb_exchange* x);
+int exchange_launch_push(hdb_exchange* x, cudaStream_t s, const void* mine, int64_t words);
+int exchange_launch_wait_merge(hdb_exchange* x, cudaStream_t s, int64_t nq, int64_t k, int64_t* out_idx, double* out_score,
+                               int64_t* out_count, uint32_t* out_flags);
 }  // namespace hdb

@@ -18,7 +18,7 @@ METRIC_IDS = {
     "jaccard_similarity": 5,
     "pearson_correlation": 6,
 }
-FLAG_FALLBACK, FLAG_QUERY_NAN, FLAG_TENSOR, FLAG_UNCERTIFIED = 1, 2, 4, 8
+FLAG_FALLBACK, FLAG_QUERY_NAN, FLAG_TENSOR, FLAG_UNCERTIFIED, FLAG_EXCHANGE_ERROR = 1, 2, 4, 8, 16
 SCORES_DISTANCE = 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libhyperdb_b200.so")
@@ -65,6 +65,11 @@ SIGNATURES = {
     "hdb_exchange_step": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]),
     "hdb_exchange_push": (C.c_int, [vp, vp, vp, i64]),
     "hdb_exchange_wait_merge": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp]),
+    "hdb_exchange_collect_async": (C.c_int, [vp, i64, i64, vp, vp, vp, vp]),
+    "hdb_exchange_stream": (C.c_int, [vp, C.POINTER(vp)]),
+    "hdb_matrix_attach_exchange": (C.c_int, [vp, vp]),
+    "hdb_query_submit": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, i64, i64, C.c_double, C.c_int, i64p]),
+    "hdb_query_collect": (C.c_int, [vp, i64, vp, vp, vp, vp]),
     "hdb_exchange_error": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "hdb_launch_count": (C.c_int64, [C.c_int]),
     "hdb_time_last_query": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),

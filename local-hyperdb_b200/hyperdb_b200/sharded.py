@@ -80,8 +80,18 @@ class CudaEngine:
     def set_row_offset(self, off):
         self.m.set_row_offset(off)
 
+    def attach_exchange(self, xchg):
+        """Device-output queries also deliver their results to every rank (fused into the certify kernel)."""
+        N.check(N.lib().hdb_matrix_attach_exchange(self.m._h, xchg._h if xchg is not None else None))
+
+    def set_path(self, mode):
+        if mode != self._path:
+            self.m.set_path(mode)
+            self._path = mode
+
     def local_topk(self, queries, k, metric, bias, exact=False):
-        """-> packed int64 CUDA tensor [packed_len(B, k)] (scores bit-cast)."""
+        """-> packed int64 CUDA tensor [packed_len(B, k)] (scores bit-cast).  exact: False = automatic path,
+        True = exact full-vector path, or a path mode of hdb_matrix_set_path (4 = wide candidate class)."""
         torch = self.torch
         q = queries if torch.is_tensor(queries) else torch.as_tensor(queries)
         if q.device != self.device or not q.is_contiguous():
@@ -90,10 +100,7 @@ class CudaEngine:
         buf = torch.empty(packed_len(b, k), dtype=torch.int64, device=self.device)
         # [scores b*k | ids b*k | counts b | flags]: addresses by arithmetic (this runs once per query: no tensor views)
         base = buf.data_ptr()
-        want = 1 if exact else 0
-        if want != self._path:
-            self.m.set_path(want)
-            self._path = want
+        self.set_path(int(exact))
         N.check(N.lib().hdb_query(self.m._h, N.METRIC_IDS[metric], q.data_ptr(), self._qdt[q.dtype], N.HDB_DEVICE, b, int(k), float(bias),
                                   base + 8 * b * k, base, base + 16 * b * k, base + 16 * b * k + 8 * b, N.HDB_DEVICE))
         return buf
@@ -162,6 +169,17 @@ class PeerExchange:
         N.check(N.lib().hdb_exchange_wait_merge(self._h, C.c_void_p(stream_ptr), b, k, C.c_void_p(out_idx.data_ptr()),
                                                 C.c_void_p(out_score.data_ptr()), C.c_void_p(out_count.data_ptr()),
                                                 C.c_void_p(out_flags.data_ptr())))
+
+    def collect_async(self, b, k, out_ptr):
+        """Second half of a step whose first half was done by an attached DeviceMatrix (hdb_matrix_attach_exchange): wait +
+        merge on the exchange's own stream into the block [idx b*k | score b*k | count b | flags world*b] at out_ptr."""
+        N.check(N.lib().hdb_exchange_collect_async(self._h, b, k, out_ptr, out_ptr + 8 * b * k, out_ptr + 16 * b * k,
+                                                   out_ptr + 16 * b * k + 8 * b))
+
+    def stream_ptr(self) -> int:
+        p = C.c_void_p()
+        N.check(N.lib().hdb_exchange_stream(self._h, C.byref(p)))
+        return p.value
 
     def error(self) -> bool:
         e = C.c_int()
@@ -252,6 +270,9 @@ class ShardedMatrix:
                 raise RuntimeError(f"peer-memory exchange unavailable on rank {self.rank}: {err}")
             raise RuntimeError("peer-memory exchange unavailable on another rank")
         self.xchg = xchg
+        if hasattr(self.engine, "attach_exchange"):
+            self.engine.attach_exchange(xchg)   # the certify kernel now pushes; this side only collects
+            self._xs = torch.cuda.ExternalStream(xchg.stream_ptr(), device=dev)
         return True
 
     def _comm_device(self):
@@ -315,6 +336,17 @@ class ShardedMatrix:
         b = 1 if getattr(queries, "ndim", 1) == 1 else queries.shape[0]
         mine = self.engine.local_topk(queries, k, metric, recency_bias, exact=exact)
         post = getattr(self.engine, "post", None)
+        if self.xchg is not None:
+            # hdb_query already delivered this rank's records to every rank (fused push); wait + merge run on the exchange's
+            # own stream, ordered by the arrival flags.  Batches beyond the exchange buffer fail inside hdb_query.
+            w = self.world
+            if post is not None:
+                mine.record_stream(post)
+            out = torch.empty(2 * b * k + b + (w * b + 1) // 2, dtype=torch.int64, device=mine.device)   # [idx | score | count | flags]
+            out.record_stream(self._xs)
+            self.xchg.collect_async(b, k, out.data_ptr())
+            self.exchanges += 1
+            return StepResult(out, b, k, w)
         if post is not None:
             # pipelined: `mine` is completed on the post stream; exchange and merge follow it there
             mine.record_stream(post)
@@ -324,15 +356,6 @@ class ShardedMatrix:
 
     def _exchange_and_merge(self, mine, b, k, post):
         import torch
-        if self.xchg is not None and mine.numel() <= self.xchg.max_words and k > 0:
-            w = self.world
-            out = torch.empty(2 * b * k + b + (w * b + 1) // 2, dtype=torch.int64, device=mine.device)   # [idx | score | count | flags]
-            base = out.data_ptr()
-            stream = post.cuda_stream if post is not None else torch.cuda.current_stream(mine.device).cuda_stream
-            N.check(N.lib().hdb_exchange_step(self.xchg._h, stream, mine.data_ptr(), mine.numel(), b, k, base, base + 8 * b * k,
-                                              base + 16 * b * k, base + 16 * b * k + 8 * b))
-            self.exchanges += 1
-            return StepResult(out, b, k, w)
         if self.world > 1:
             gathered = torch.empty(self.world * mine.numel(), dtype=mine.dtype, device=mine.device)
             self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
@@ -345,17 +368,73 @@ class ShardedMatrix:
     def wait_results(self):
         """Make the current stream wait for everything enqueued on the pipelined post stream."""
         post = getattr(self.engine, "post", None)
+        if post is None and self.xchg is None:
+            return
+        import torch
+        cur = torch.cuda.current_stream(self.engine.device)
         if post is not None:
-            import torch
-            torch.cuda.current_stream(self.engine.device).wait_stream(post)
+            cur.wait_stream(post)
+        if self.xchg is not None:
+            cur.wait_stream(self._xs)
+
+    # -- asynchronous host API: up to 4 steps in flight, ONE pinned result block per step ---------------------------
+    def submit(self, queries, top_k, metric, recency_bias=0.0, _path=0):
+        """Enqueue one step (host or CUDA queries) and return a ticket; nothing is synchronised.  Collective: every rank
+        submits the same batch in the same order.  Needs the CUDA engine with the peer exchange (or a single rank)."""
+        import numpy as np
+        eng = self.engine
+        if not hasattr(eng, "m") or (self.world > 1 and self.xchg is None):
+            raise RuntimeError("submit/collect need the CUDA engine and, on several ranks, the peer-memory exchange")
+        from .device_matrix import as_float_array, _NP2HDB, _is_torch
+        if _is_torch(queries):
+            q = queries.contiguous()
+            qdt, space = eng._qdt[q.dtype], (N.HDB_DEVICE if q.is_cuda else N.HDB_HOST)
+            ptr, shape = q.data_ptr(), tuple(q.shape)
+        else:
+            q = as_float_array(queries)
+            qdt, space, ptr, shape = _NP2HDB[q.dtype], N.HDB_HOST, q.ctypes.data, q.shape
+        b = 1 if len(shape) == 1 else shape[0]
+        k = max(int(top_k), 0)
+        eng.set_path(_path)
+        t = C.c_int64()
+        N.check(N.lib().hdb_query_submit(eng.m._h, N.METRIC_IDS[metric], C.c_void_p(ptr), qdt, space, b, k, float(recency_bias),
+                                         self.world, C.byref(t)))
+        self.exchanges += 1
+        return (t.value, b, k, q, metric, float(recency_bias), _path)
+
+    def collect(self, ticket):
+        """Wait for one ticket: (idx [B,k], scores [B,k], counts [B]) on the host, identical on every rank.  A step some shard
+        could not certify is repeated -- by every rank alike, they all see every shard's flags -- with the wide candidate
+        class and then on the exact path."""
+        import numpy as np
+        tid, b, k, q, metric, bias, path = ticket
+        idx = np.empty((b, k), np.int64)
+        sc = np.empty((b, k), np.float64)
+        cnt = np.empty(b, np.int64)
+        flags = np.empty((self.world, b), np.uint32)
+        N.check(N.lib().hdb_query_collect(self.engine.m._h, tid, C.c_void_p(idx.ctypes.data), C.c_void_p(sc.ctypes.data),
+                                          C.c_void_p(cnt.ctypes.data), C.c_void_p(flags.ctypes.data)))
+        if (flags & N.FLAG_EXCHANGE_ERROR).any():
+            raise RuntimeError("peer-memory exchange: a rank did not deliver its candidates within 10 s")
+        if (flags & N.FLAG_QUERY_NAN).any():
+            raise ValueError("Vectors and query_vector should not contain NaN values.")
+        if (flags & N.FLAG_UNCERTIFIED).any() and k > 0:
+            nxt = 4 if (path == 0 and k <= 100) else (1 if path != 1 else None)
+            if nxt is None:
+                raise RuntimeError("the exact path reported an uncertified result")
+            try:
+                return self.collect(self.submit(q, k, metric, bias, _path=nxt))
+            finally:
+                self.engine.set_path(0)
+        return idx, sc, cnt
 
     def query(self, queries, top_k, metric, recency_bias=0.0):
         """Host results, identical on every rank: (idx [B,k], scores [B,k], counts [B])."""
+        if hasattr(self.engine, "m") and (self.world == 1 or self.xchg is not None):
+            return self.collect(self.submit(queries, top_k, metric, recency_bias))
         idx, sc, cnt, flags = self.query_async(queries, top_k, metric, recency_bias)
         self.wait_results()
         flags = flags.cpu().numpy()
-        if self.xchg is not None and self.xchg.error():
-            raise RuntimeError("peer-memory exchange: a rank did not deliver its candidates within 10 s")
         if (flags & N.FLAG_QUERY_NAN).any():
             raise ValueError("Vectors and query_vector should not contain NaN values.")
         if (flags & N.FLAG_UNCERTIFIED).any():      # every rank sees every flag after the all-gather: same branch everywhere

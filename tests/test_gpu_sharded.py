@@ -223,3 +223,133 @@ def test_nccl_world(tmp_path):
         pytest.skip("needs >= 2 GPUs")
     mp.spawn(_nccl_worker, args=(world, 29733, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def _one_gpu_ipc_worker(rank, world, port, out_dir):
+    """Two PROCESSES on the SAME GPU: the peer buffers are mapped through CUDA IPC exactly as on a multi-GPU box (the IPC
+    handles travel through gloo), so the driver's single-GPU run exercises hdb_exchange_connect, the fused push of the certify
+    kernel, the flow-controlled slot ring and the wait + merge kernel across process boundaries."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "local-hyperdb_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import hyperdb_b200 as hb
+    from hyperdb_b200.sharded import CudaEngine, ShardedMatrix, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(23)
+    n, d = 90_001, 64
+    V = rng.standard_normal((n, d)).astype(np.float16)
+    V[70_000] = V[11]                                           # a tie across the shard boundary -> lower global id first
+    Q = rng.standard_normal((5, d)).astype(np.float16)
+    Q[1] = V[11]
+    ts = 1.7e9 + rng.uniform(0, 5, n)
+    keep = rng.random(n) < 0.6
+    lo, hi = shard_bounds(n, world, rank)
+    m = hb.DeviceMatrix(V[lo:hi], device=0, row_offset=lo)
+    m.set_timestamps(ts[lo:hi])
+    m.set_mask(keep[lo:hi])
+    sm = ShardedMatrix(CudaEngine(m), n)
+    sm.refresh_decay()
+    assert sm.total_kept() == int(keep.sum())
+    assert sm.enable_peer_exchange(max_batch=8, max_k=128) is True
+    want = {}
+    for metric in ("cosine_similarity", "manhattan_distance", "hamming_distance"):
+        for b in range(len(Q)):
+            want[metric, b] = K.rank(V, Q[b], 10, metric, ts, 0.3, keep)
+    # synchronous host API (submit + collect under the hood): single queries and a batch, 3 metrics, > 4 steps each
+    for metric in ("cosine_similarity", "manhattan_distance", "hamming_distance"):
+        for b in range(len(Q)):
+            idx, sc, cnt = sm.query(Q[b], 10, metric, 0.3)
+            assert list(idx[0]) == list(want[metric, b][0]), (metric, b)
+            np.testing.assert_allclose(sc[0], want[metric, b][1], rtol=1e-14)          # CUDA exp vs NumPy exp: <= 1 ulp
+            assert cnt[0] == 10
+        idx, sc, cnt = sm.query(Q, 10, metric, 0.3)
+        for b in range(len(Q)):
+            assert list(idx[b]) == list(want[metric, b][0])
+            np.testing.assert_allclose(sc[b], want[metric, b][1], rtol=1e-14)
+    # top_k = 100 (wide candidate class) and k = 0 (nothing fused: the push kernel delivers the empty block)
+    idx, sc, cnt = sm.query(Q[0], 100, "cosine_similarity", 0.3)
+    oi, os_ = K.rank(V, Q[0], 100, "cosine_similarity", ts, 0.3, keep)
+    assert list(idx[0]) == list(oi)
+    np.testing.assert_allclose(sc[0], os_, rtol=1e-14)
+    idx, sc, cnt = sm.query(Q[0], 0, "cosine_similarity", 0.3)
+    assert idx.shape == (1, 0) and cnt[0] == 0
+    # asynchronous host API, pipelined: 3 tickets in flight, 12 steps through the 4-slot ring
+    sm.engine.enable_pipeline(True)
+    tickets = []
+    for i in range(12):
+        tickets.append(sm.submit(Q[i % len(Q)], 10, "cosine_similarity", 0.3))
+        if len(tickets) == 3:
+            t = tickets.pop(0)
+            idx, sc, cnt = sm.collect(t)
+            b = (i - 2) % len(Q)
+            assert list(idx[0]) == list(want["cosine_similarity", b][0]), i
+    while tickets:
+        sm.collect(tickets.pop(0))
+    # device-resident, back to back
+    qd = torch.as_tensor(Q).cuda()
+    outs = [sm.query_async(qd[i % len(Q):i % len(Q) + 1], 10, "hamming_distance", 0.3) for i in range(10)]
+    sm.wait_results()
+    torch.cuda.synchronize()
+    assert not sm.xchg.error()
+    for i, (idx, sc, cnt, flags) in enumerate(outs):
+        assert flags.shape == (world, 1)
+        if (flags.cpu().numpy() & 8).any():
+            continue
+        assert list(idx[0].cpu().numpy()) == list(want["hamming_distance", i % len(Q)][0]), i
+    sm.engine.enable_pipeline(False)
+    dist.barrier()
+    sm.xchg.close()
+    m.close()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def test_two_processes_one_gpu_peer_exchange(tmp_path):
+    """SURVEY.md section 8e on ONE GPU: one process per rank, CUDA-IPC peer memory, no NCCL anywhere."""
+    import torch.multiprocessing as mp
+    mp.spawn(_one_gpu_ipc_worker, args=(2, 29741 + (os.getpid() % 100), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_submit_collect_single_gpu():
+    """hdb_query_submit / hdb_query_collect on one shard: pipelined host queries equal the synchronous API."""
+    import hyperdb_b200 as hb
+    from hyperdb_b200.sharded import CudaEngine, ShardedMatrix
+    rng = np.random.default_rng(31)
+    n, d = 150_000, 96
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((9, d)).astype(np.float32)
+    m = hb.DeviceMatrix(V)
+    sm = ShardedMatrix(CudaEngine(m), n)
+    try:
+        for pipelined in (False, True):
+            sm.engine.enable_pipeline(pipelined)
+            for metric in ("cosine_similarity", "euclidean_metric", "hamming_distance"):
+                ref = [m.query(Q[i], 10, metric) for i in range(len(Q))]
+                tickets = [sm.submit(Q[i], 10, metric) for i in range(3)]
+                got = []
+                for i in range(3, len(Q)):
+                    got.append(sm.collect(tickets.pop(0)))
+                    tickets.append(sm.submit(Q[i], 10, metric))
+                got += [sm.collect(t) for t in tickets]
+                for i, (idx, sc, cnt) in enumerate(got):
+                    assert np.array_equal(idx, ref[i][0]) and np.array_equal(sc, ref[i][1]) and cnt[0] == 10, (pipelined, metric, i)
+                # a batch through the same API, and a 5th ticket without collecting is refused
+                idx, sc, cnt = sm.collect(sm.submit(Q[:4], 10, metric))
+                for i in range(4):
+                    assert np.array_equal(idx[i], ref[i][0][0])
+            ts_ = [sm.submit(Q[0], 10, "cosine_similarity") for _ in range(4)]
+            with pytest.raises(Exception):
+                sm.submit(Q[0], 10, "cosine_similarity")
+            for t in ts_:
+                sm.collect(t)
+        sm.engine.enable_pipeline(False)
+    finally:
+        m.close()
