@@ -7,13 +7,20 @@ One "step" = one pass of the hot path over one batch of synthetic queries (B que
 whole stored matrix, top-k out).  Default workload `c3_cosine_b1`: BASELINE.json config C3, the one
 north_star's roofline target is quoted on (10M x 768 fp16, cosine top-10, single query).
   value     whole-job queries/s with matrix, queries and results resident in HBM (CUDA events)
-  e2e       the same through the public host API (DeviceMatrix.query / ShardedMatrix.query): the query
-            starts in pinned HOST memory and the top-k lands in HOST memory every step
-  roofline  the streaming sweep kernel: algorithmic bytes per launch (N*D*sizeof) / its mean duration,
-            measured live with CUDA event pairs around every launch inside the timed region
-  cpu_baseline   the NumPy port of the reference (oracle/reference_port.py) on this box's host cores,
-            on a bounded row subsample, scaled linearly to the full row count
-N > 1 (torchrun): the matrix is row-sharded (strong scaling), one all-gather of candidates per step.
+  e2e       the same through the public host API: every step's query starts in pinned HOST memory and its
+            top-k lands in HOST memory.  `e2e.value` keeps up to 3 steps in flight through
+            ShardedMatrix.submit / collect (hdb_query_submit / hdb_query_collect); `e2e.sync_value` is one
+            blocking DeviceMatrix.query / ShardedMatrix.query call after the other
+  roofline  the dominant kernel: algorithmic bytes (or flops) per launch / its mean duration, measured
+            live with CUDA event pairs around every launch inside the timed region.  With a row mask the
+            bytes are those of the KEPT rows (the full N*D figure is given beside it)
+  cpu_baseline   the NumPy port of the reference (oracle/reference_port.py) on this box's host cores, on a
+            bounded row subsample (median of 3), scaled linearly to the full row count
+  parity_check   outside the timed region: two planted queries (a stored row must come back first) and one
+            random query checked against an independent chunked torch fp32 scoring of every shard
+  extra     short passes of the other BASELINE.json configurations (batched tensor-core path, bit-packed
+            hamming, the multi-query sweep), each with its own e2e and roofline
+N > 1 (torchrun): the matrix is row-sharded (strong scaling), one exchange of candidates per step.
 `--impl reference` times the reference's CPU path (the NumPy port; the reference is pure Python and
 /root/reference does not travel to the GPU box) on the same workload.
 """
@@ -48,15 +55,25 @@ WORKLOADS = {
     "c5_euclid_b1024": dict(n=5_000_000, d=1024, dtype="float32", metric="euclidean_metric", k=10, b=1024),
     "c5_manhattan_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="manhattan_distance", k=10, b=1),
     "c5_hamming_b1": dict(n=5_000_000, d=1024, dtype="float32", metric="hamming_distance", k=10, b=1),
+    # small batches: ONE read of the matrix serves up to 8 queries (multi-query sweep)
+    "c5_manhattan_b8": dict(n=5_000_000, d=1024, dtype="float32", metric="manhattan_distance", k=10, b=8),
+    "c5_euclid_b8": dict(n=5_000_000, d=1024, dtype="float32", metric="euclidean_metric", k=10, b=8),
+    "c5_hamming_b8": dict(n=5_000_000, d=1024, dtype="float32", metric="hamming_distance", k=10, b=8),
+    "c3_cosine_b8": dict(n=10_000_000, d=768, dtype="float16", metric="cosine_similarity", k=10, b=8),
+    "c3_pearson_b8": dict(n=10_000_000, d=768, dtype="float16", metric="pearson_correlation", k=10, b=8),
     "c4_decay_mask_k100": dict(n=100_000_000, d=384, dtype="float16", metric="cosine_similarity", k=100, b=1,
                                decay=True, mask=True),
 }
+# the short passes attached to the default line as "extra" (same matrix as the headline first, then config C5's)
+EXTRAS = ["c3_cosine_b8", "c3_cosine_b64", "c3_cosine_b4096", "c5_hamming_b1", "c5_manhattan_b8"]
 CHUNK = 262_144          # rows per generator chunk: chunk c of the GLOBAL matrix is seeded with (seed, c)
 ITEM = {"float16": 2, "float32": 4, "float64": 8}
+# metadata of the synthetic documents (config C4): one category per row, the filter keeps 4 of the 8 categories
+MASK_CATEGORIES, MASK_KEPT = 8, (1, 3, 5, 6)
 
 
-def algorithmic_bytes(w, rows):
-    if w["metric"] == "hamming_distance":
+def matrix_bytes(w, rows):
+    if w["metric"] in ("hamming_distance", "jaccard_similarity"):
         return rows * ((w["d"] + 127) // 128) * 16          # bit-packed rows, 16-byte granules
     return rows * w["d"] * ITEM[w["dtype"]]
 
@@ -92,6 +109,32 @@ def gen_rows_numpy(n, d, dtype, seed=0):
     v = rng.standard_normal((n, d), dtype=np.float32)
     v /= np.linalg.norm(v, axis=1, keepdims=True)
     return v.astype(dtype)
+
+
+def gen_keep_torch(lo, hi, device):
+    """The metadata predicate of config C4 on synthetic documents: document i carries category
+    hash(i) % 8 (a device-resident int8 column, reproducible per global row id) and the filter keeps the
+    documents whose category is in MASK_KEPT (`filters=[('metadata', {'category': [...]})]` in the reference,
+    hyperdb/hyperdb.py:1218-1257).  Returns the bool keep column of rows [lo, hi)."""
+    import torch
+    ids = torch.arange(lo, hi, device=device, dtype=torch.int64)
+    cat = ((ids * 2654435761 + 40503) >> 7) % MASK_CATEGORIES
+    keep = torch.zeros(hi - lo, dtype=torch.bool, device=device)
+    for c in MASK_KEPT:
+        keep |= cat == c
+    return keep
+
+
+def pack_keep_bits(keep):
+    import torch
+    n = keep.numel()
+    pad = (-n) % 32
+    if pad:
+        keep = torch.cat([keep, torch.zeros(pad, dtype=torch.bool, device=keep.device)])
+    w = keep.view(-1, 32).to(torch.int64) << torch.arange(32, device=keep.device, dtype=torch.int64)
+    bits = w.sum(dim=1)
+    bits = torch.where(bits >= 2**31, bits - 2**32, bits)
+    return bits.to(torch.int32).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -133,13 +176,15 @@ class ClockSampler:
 
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-    `ncu --set full` capture of this workload (profiles/r01_traffic.json); None if it was not captured."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        t = json.load(open(path)).get(workload)
-        return None if t is None else float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
-    except Exception:
-        return None
+    `ncu --set full` captures (profiles/r02_traffic.json, else r01's); None if this workload was not captured."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name))).get(workload)
+            if t is not None:
+                return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+        except Exception:
+            pass
+    return None
 
 
 def measured_peaks():
@@ -149,32 +194,69 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+_TF32_PEAK = None
+
+
+def tf32_peak_tflops(dev):
+    """No tf32 figure is driver-written: measure torch.matmul (cuBLAS, allow_tf32) 8192^3 back to back for ~1 s,
+    the same recipe MEASURED_PEAKS.json states for its sustained bf16 figure."""
+    global _TF32_PEAK
+    if _TF32_PEAK is not None:
+        return _TF32_PEAK
+    import torch
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(400):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        _TF32_PEAK = 400 * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return _TF32_PEAK
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_time_per_query(w, sample_rows, repeats=1):
+    """-> (median seconds of `repeats` full ranking calls, median seconds of the bare metric kernel -- np.dot for the
+    dot/cosine family -- on the same sample)."""
     from oracle import reference_port as P
     v = gen_rows_numpy(sample_rows, w["d"], w["dtype"], seed=0)
-    q = gen_queries(1, w["d"], w["dtype"])[0]
+    qs = gen_queries(repeats, w["d"], w["dtype"])
     ts = None
     if w.get("decay"):
         ts = 1.7e9 + np.random.default_rng(2).uniform(0, 3600, sample_rows)
-    best = float("inf")
-    for _ in range(repeats):
+    full, kern = [], []
+    for r in range(repeats):
         t0 = time.perf_counter()
-        P.rank(v, q, w["k"], w["metric"], ts, 0.3 if ts is not None else 0, canonical=False)
-        best = min(best, time.perf_counter() - t0)
-    return best
+        P.rank(v, qs[r], w["k"], w["metric"], ts, 0.3 if ts is not None else 0, canonical=False)
+        full.append(time.perf_counter() - t0)
+    if w["metric"] in ("cosine_similarity", "dot_product", "pearson_correlation"):
+        for r in range(repeats):
+            t0 = time.perf_counter()
+            np.dot(v, qs[r])
+            kern.append(time.perf_counter() - t0)
+    return float(np.median(full)), (float(np.median(kern)) if kern else None)
 
 
-def cpu_sample_rows(w):
-    # sized for roughly 10-30 s of host work on the survey machine
+def cpu_sample_rows(w, repeats):
+    # sized for roughly 10-30 s of host work in total on the survey machine (SURVEY.md section 6)
     per_row_us = {"float16": 60.0, "float32": 4.5, "float64": 6.0}[w["dtype"]] * w["d"] / 768
     if w["metric"] == "hamming_distance":
         per_row_us = 60.0 * w["d"] / 1024
     if w["metric"] == "dot_product":
         per_row_us *= 0.2
-    return int(max(10_000, min(w["n"], 12e6 / per_row_us)))
+    return int(max(10_000, min(w["n"], 15e6 / per_row_us / repeats)))
 
 
 def run_reference_arm(args, w):
@@ -185,7 +267,7 @@ def run_reference_arm(args, w):
     if rank != 0:
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    per_row_s = cpu_time_per_query(w, 20_000) / 20_000                 # calibration, untimed
+    per_row_s = cpu_time_per_query(w, 20_000)[0] / 20_000                 # calibration, untimed
     sample = int(max(2_000, min(w["n"], 120.0 / (steps + warm) / per_row_s)))
     v = gen_rows_numpy(sample, w["d"], w["dtype"], seed=0)
     qs = gen_queries(steps + warm, w["d"], w["dtype"])
@@ -208,10 +290,341 @@ def run_reference_arm(args, w):
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"each step = 1 query on {sample} of {w['n']} rows ({t_step * 1e3:.1f} ms), scaled linearly by "
                                    f"{w['n'] / sample:.1f}x (and by the batch size); oracle/reference_port.rank = the reference's NumPy "
-                                   f"calls, NumPy {np.__version__}, all threads NumPy/OpenBLAS chooses to use"},
+                                   f"calls (without its per-call NaN scan of the matrix: slightly faster than the reference), "
+                                   f"NumPy {np.__version__}, all threads NumPy/OpenBLAS chooses to use"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# one resident matrix (a row shard per rank) and the workloads measured on it
+# ------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args, world, rank, dev):
+        self.args, self.world, self.rank, self.dev = args, world, rank, dev
+        self.shape = None
+        self.rows = self.m = self.eng = self.sm = None
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def close(self):
+        import gc
+        import torch
+        if self.m is not None:
+            torch.cuda.synchronize()
+            if self.sm.xchg is not None:
+                self.barrier()
+                self.eng.enable_pipeline(False)
+                self.eng.attach_exchange(None)
+                self.sm.xchg.close()
+                self.sm.xchg = None
+            self.m.close()
+        self.rows = self.m = self.eng = self.sm = None
+        self.shape = None
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def prepare(self, w, max_b, max_k):
+        """Generate (or keep) the matrix of workload `w` and configure mask / decay / exchange for it."""
+        import torch
+        import hyperdb_b200 as hb
+        from hyperdb_b200.sharded import CudaEngine, ShardedMatrix, shard_bounds
+        shape = (w["n"], w["d"], w["dtype"], bool(w.get("mask")), bool(w.get("decay")))
+        if shape != self.shape:
+            self.close()
+            self.lo, self.hi = shard_bounds(w["n"], self.world, self.rank)
+            self.rows = gen_rows_torch(self.lo, self.hi, w["d"], w["dtype"], self.dev, seed=0)
+            self.m = hb.DeviceMatrix(self.rows, row_offset=self.lo)
+            self.keep = None
+            if w.get("mask"):
+                self.keep = gen_keep_torch(self.lo, self.hi, self.dev)
+                self.m.set_mask(pack_keep_bits(self.keep))
+            self.eng = CudaEngine(self.m)
+            self.sm = ShardedMatrix(self.eng, w["n"])
+            if self.world > 1 and self.args.exchange == "peer":
+                # CUDA IPC between the ranks' processes; if the box forbids it, every rank fails here alike and the run
+                # continues on the NCCL all-gather (reported in config.exchange)
+                try:
+                    self.sm.enable_peer_exchange(max_batch=max_b, max_k=max_k)
+                except Exception as e:                                   # noqa: BLE001
+                    print(f"bench.py: peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+                    self.sm.xchg = None
+            self.ts = None
+            if w.get("decay"):
+                g = torch.Generator(device=self.dev)
+                g.manual_seed(2_000_003 + self.rank)
+                self.ts = 1.7e9 + 3600.0 * torch.rand(self.hi - self.lo, generator=g, device=self.dev, dtype=torch.float64)
+                self.m.set_timestamps(self.ts)
+                self.sm.refresh_decay()
+            self.shape = shape
+        pipelined = not self.args.no_pipeline and w["b"] < 2
+        self.eng.enable_pipeline(pipelined)      # certify/exchange/merge of query i overlap the sweep of query i+1
+        if pipelined:
+            self.m.set_sweep_overlap(not self.args.no_overlap)     # ... and the head of sweep i+1 fills the tail of sweep i
+        return 0.3 if w.get("decay") else 0.0
+
+    # ---- the measurement of one workload -------------------------------------------------------------------------
+    def measure(self, name, w, steps, warmup, max_b, max_k, want_clocks=True, graph=False):
+        import torch
+        import torch.distributed as dist
+        from hyperdb_b200 import _native as N
+        args, world, rank, dev = self.args, self.world, self.rank, self.dev
+        bias = self.prepare(w, max_b, max_k)
+        m, eng, sm = self.m, self.eng, self.sm
+        lo, hi = self.lo, self.hi
+        b, k = w["b"], w["k"]
+        # a different query (batch) every step; large batches cycle through a pool of 6 batches
+        pool = (warmup + steps + 1) if b == 1 else min(warmup + steps + 1, 6)
+        q_host = gen_queries(pool * b, w["d"], w["dtype"], seed=1 + b)
+        q_dev = torch.as_tensor(q_host).to(dev)
+        q_pin = torch.as_tensor(q_host).pin_memory()
+
+        def qslice(t, i):
+            j = (i % pool) * b
+            return t[j:j + b]
+
+        # ---- device-resident arm (value) ------------------------------------------------------------
+        graphed = None
+        if graph and world == 1 and b <= 64 and eng.post is None:
+            from hyperdb_b200.sharded import GraphedQuery
+            graphed = GraphedQuery(sm, qslice(q_dev, 0), k, w["metric"], bias)
+        step = (lambda q: graphed.replay(q)) if graphed else (lambda q: sm.query_async(q, k, w["metric"], bias))
+        outs, flag_log = [], []
+        for i in range(warmup):
+            outs.append(step(qslice(q_dev, i)))
+        self.barrier()
+        m.profile_enable(steps * b + 8)
+        N.lib().hdb_launch_count(1)
+        sampler = ClockSampler(dev.index)
+        if rank == 0 and want_clocks:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for i in range(steps):
+            o = step(qslice(q_dev, warmup + i))
+            if graphed:
+                flag_log.append(o[3].clone())            # the static outputs are overwritten by the next replay
+            else:
+                outs.append(o)
+        sm.wait_results()                                # pipelined mode: the last certify/exchange/merge run on the post stream
+        e1.record()
+        self.barrier()
+        launches = N.lib().hdb_launch_count(0)
+        clocks = sampler.stop() if (rank == 0 and want_clocks) else None
+        ms_total = e0.elapsed_time(e1)
+        n_sweeps, sweep_ms = m.profile_read()
+        if graphed:
+            # Kernels replayed from a graph cannot be bracketed by event pairs and are not counted by the launch
+            # counter: run K more un-graphed steps of the same workload for the per-launch duration of the dominant
+            # kernel (roofline) and the launch count per step (the graph replays exactly these launches).
+            N.lib().hdb_launch_count(1)
+            for i in range(steps):
+                sm.query_async(qslice(q_dev, warmup + i), k, w["metric"], bias)
+            self.barrier()
+            n_sweeps, sweep_ms = m.profile_read()
+            launches = N.lib().hdb_launch_count(0)
+        m.profile_enable(0)
+        if graphed:
+            uncertified = sum(int(bool((f & N.FLAG_UNCERTIFIED).any())) for f in flag_log)
+        else:
+            uncertified = sum(int(bool((o[3] & N.FLAG_UNCERTIFIED).any())) for o in outs[warmup:])
+        tensor_path = any(int(f) & N.FLAG_TENSOR for o in outs[-1:] for f in o[3].flatten().tolist()) if outs else False
+        del outs, flag_log
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = t.item() / steps
+        value = b / (ms_step * 1e-3)
+
+        # ---- end-to-end arm through the host API ------------------------------------------------------
+        e2e_steps = max(3, min(steps, 20))
+        q_np = q_pin.numpy()
+        use_tickets = world == 1 or sm.xchg is not None
+        # (a) one blocking call after the other: DeviceMatrix.query on one GPU, ShardedMatrix.query on several
+        host_query = (lambda q: m.query(q, k, w["metric"], bias)) if world == 1 else (lambda q: sm.query(q, k, w["metric"], bias))
+        for i in range(2):
+            host_query(qslice(q_np, i))
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            host_query(qslice(q_np, warmup + i))
+        torch.cuda.synchronize()
+        t_sync = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_sync, op=dist.ReduceOp.MAX)
+        sync_qps = b * e2e_steps / t_sync.item()
+        # (b) the asynchronous host API with up to 3 steps in flight (host query in, host top-k out, every step)
+        e2e_qps, depth = sync_qps, 1
+        if use_tickets:
+            depth = 3
+            for i in range(2):
+                sm.collect(sm.submit(qslice(q_np, i), k, w["metric"], bias))
+            self.barrier()
+            t0 = time.perf_counter()
+            tickets = []
+            for i in range(e2e_steps):
+                tickets.append(sm.submit(qslice(q_np, warmup + i), k, w["metric"], bias))
+                if len(tickets) == depth:
+                    sm.collect(tickets.pop(0))
+            while tickets:
+                sm.collect(tickets.pop(0))
+            t_pipe = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_pipe, op=dist.ReduceOp.MAX)
+            e2e_qps = b * e2e_steps / t_pipe.item()
+
+        res = None
+        if rank == 0:
+            peaks, peak_src = measured_peaks()
+            n_kept = m.n_kept
+            full_bytes = matrix_bytes(w, hi - lo)
+            shard_bytes = matrix_bytes(w, n_kept) if w.get("mask") else full_bytes
+            side_bytes = 0
+            if w.get("mask"):
+                side_bytes += (hi - lo) // 8                                      # the keep bits of every row
+            if w["metric"] in ("cosine_similarity", "pearson_correlation"):
+                side_bytes += n_kept * 4 * (2 if w["metric"] == "pearson_correlation" else 1)
+            if w.get("decay"):
+                side_bytes += n_kept * 8
+            sweep_avg_ms = sweep_ms / max(1, n_sweeps)
+            overlapped = eng.post is not None and not args.no_overlap and b < 2
+            if overlapped and n_sweeps:
+                # Overlapping sweeps: an event pair around a launch also spans the time the kernel waited for the previous
+                # query's CTAs to leave the SMs, so the per-launch average is taken as timed region / launches (an upper
+                # bound of the kernel's own duration: the region also holds the small kernels), whichever is smaller.
+                sweep_avg_ms = min(sweep_avg_ms, ms_total / n_sweeps)
+            achieved = shard_bytes / (sweep_avg_ms * 1e-3) / 1e9 if n_sweeps else None
+            # tensor-bound only when the contraction, not the row stream, limits the step: flops per matrix byte above
+            # the machine balance (peak flop/s / peak byte/s)
+            shard_flops = 2.0 * (hi - lo) * w["d"] * b
+            kernel = ("batched_tc_kernel (sample + select passes)" if tensor_path else
+                      ("sweep_hamming_kernel" if w["metric"] in ("hamming_distance", "jaccard_similarity") else "sweep_kernel") +
+                      (f" ({min(b, 8)} queries per pass)" if b > 1 else ""))
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
+                    "traffic": ncu_traffic(name) if world == 1 else None, "kernel": kernel,
+                    "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
+                    "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peak_src,
+                    "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None}
+            if w.get("mask"):
+                roof["bytes_counted"] = "kept rows only (n_kept * d * sizeof); side columns (keep bits, inverse norms, decay) excluded"
+                roof["n_kept"] = int(n_kept)
+                roof["full_matrix_bytes"] = full_bytes
+                roof["side_column_bytes"] = int(side_bytes)
+                roof["frac_if_dropped_rows_counted"] = full_bytes / (sweep_avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if n_sweeps else None
+            if tensor_path and n_sweeps and b >= 256:
+                tf = shard_flops / (sweep_avg_ms * 1e-3) / 1e12
+                if w["dtype"] == "float32":
+                    peak_tf = tf32_peak_tflops(dev)
+                    src = "measured here: torch.matmul fp32 with allow_tf32, 8192^3 x 400 back to back (no tf32 figure in MEASURED_PEAKS.json)"
+                    kind = "kind::tf32"
+                else:
+                    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+                    src = peak_src + " bf16_tflops_sustained (kernel timed inside a long step)"
+                    kind = "kind::f16"
+                roof = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                        "traffic": ncu_traffic(name) if world == 1 else None, "kernel": kernel + " " + kind,
+                        "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms, "algorithmic_flops_per_launch": shard_flops,
+                        "peak_source": src}
+                if w["dtype"] != "float32":
+                    roof["frac_of_burst"] = tf / peaks.get("bf16_tflops", 1667.5)
+                    roof["frac_of_nominal_2250"] = tf / 2250.0
+            res = {
+                "workload": name, "value": value, "unit": "queries/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+                "uncertified_steps": uncertified, "gpu_launches": int(launches), "cuda_graph": bool(graphed),
+                "pipelined": eng.post is not None, "sweep_overlap": bool(overlapped), "clocks": clocks,
+                "shard_gb": full_bytes / 1e9,
+                "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(b * w["d"] * ITEM[w["dtype"]]),
+                        "d2h_bytes_per_step": int(b * k * 16 + b * 8 + world * b * 4), "steps": e2e_steps,
+                        "api": (f"ShardedMatrix.submit/collect (hdb_query_submit/hdb_query_collect), {depth} steps in flight, "
+                                "uncertified steps repaired inside collect") if use_tickets else "ShardedMatrix.query (NCCL all-gather)",
+                        "sync_value": sync_qps,
+                        "sync_api": "DeviceMatrix.query" if world == 1 else "ShardedMatrix.query"},
+                "roofline": roof,
+            }
+        return res
+
+    # ---- answers checked outside the timed region ------------------------------------------------------------------
+    def parity_check(self, w):
+        """Two planted queries (stored rows of two different shards: they must come back first) and one random query
+        against an independent scoring of every shard with plain torch fp32 (chunked matmul + topk), merged over the
+        ranks by (score desc, id asc).  Only for the dot / cosine family; the sharded host API is the path checked."""
+        import torch
+        import torch.distributed as dist
+        from hyperdb_b200.sharded import shard_bounds
+        if w["metric"] not in ("cosine_similarity", "dot_product") or w.get("decay"):
+            return None
+        world, rank, dev = self.world, self.rank, self.dev
+        sm, rows, lo, hi = self.sm, self.rows, self.lo, self.hi
+        n, d, k = w["n"], w["d"], w["k"]
+        plants = [n // 3, (2 * n) // 3 + 1]
+        if self.keep is not None:                        # a planted row must be a kept one: move to the next kept row (rank-local)
+            plants = plants[:0]
+        qs = []
+        for pid in plants:
+            row = torch.zeros(d, dtype=rows.dtype, device=dev)
+            if lo <= pid < hi:
+                row = rows[pid - lo].clone()
+            if world > 1:
+                src = [r for r in range(world) if shard_bounds(n, world, r)[0] <= pid < shard_bounds(n, world, r)[1]][0]
+                dist.broadcast(row, src=src)
+            qs.append(row.cpu().numpy())
+        qs.append(gen_queries(1, d, w["dtype"], seed=777)[0])
+        out = {"queries": len(qs), "planted_first": True, "indices_equal": True, "max_rel_score_err": 0.0, "tolerance_ties": 0}
+        for qi, q in enumerate(qs):
+            idx, sc, cnt = sm.query(q, k, w["metric"], 0.0)[:3]
+            idx, sc = idx[0], sc[0]
+            # independent check
+            qf = torch.as_tensor(q.astype(np.float32)).to(dev)
+            qn = qf / qf.norm().clamp_min(1e-30) if w["metric"] == "cosine_similarity" else qf
+            best_s = torch.empty(0, dtype=torch.float32, device=dev)
+            best_i = torch.empty(0, dtype=torch.int64, device=dev)
+            step = 1 << 20
+            for a in range(0, hi - lo, step):
+                v = rows[a:a + step].float()
+                s = v @ qn
+                if w["metric"] == "cosine_similarity":
+                    nv = v.norm(dim=1)
+                    s = s / torch.where(nv == 0, torch.ones_like(nv), nv)
+                if self.keep is not None:
+                    s = torch.where(self.keep[a:a + step], s, torch.full_like(s, float("-inf")))
+                kk = min(2 * k, s.numel())
+                ts_, ti_ = torch.topk(s, kk)
+                best_s = torch.cat([best_s, ts_])
+                best_i = torch.cat([best_i, ti_ + (lo + a)])
+                del v, s
+            kk = min(2 * k, best_s.numel())
+            ts_, sel = torch.topk(best_s, kk)
+            cand = torch.stack([ts_.double(), best_i[sel].double()])
+            if world > 1:
+                allc = [torch.empty_like(cand) for _ in range(world)]
+                dist.all_gather(allc, cand)
+                cand = torch.cat(allc, dim=1)
+            cs, ci = cand[0].cpu().numpy(), cand[1].cpu().numpy().astype(np.int64)
+            order = np.lexsort((ci, -cs))[:k]
+            want_i, want_s = ci[order], cs[order]
+            if qi < len(plants) and idx[0] != plants[qi]:
+                out["planted_first"] = False
+            rel = np.abs(sc[:len(want_s)] - want_s) / np.maximum(np.abs(want_s), 1e-30)
+            out["max_rel_score_err"] = max(out["max_rel_score_err"], float(rel.max()) if len(rel) else 0.0)
+            if not np.array_equal(idx, want_i):
+                # fp32 torch scores vs the reference's arithmetic: a swap of two rows closer than the tolerance is a tie
+                tol = 1e-3 if w["dtype"] == "float16" else 1e-5
+                if set(idx.tolist()) == set(want_i.tolist()) or float(rel.max()) <= tol:
+                    out["tolerance_ties"] += 1
+                else:
+                    out["indices_equal"] = False
+        tol = 1e-3 if w["dtype"] == "float16" else 1e-5
+        out["ok"] = bool(out["planted_first"] and out["indices_equal"] and out["max_rel_score_err"] <= tol)
+        out["against"] = "torch fp32 chunked matmul + topk per shard, merged by (score desc, id asc); planted rows %s" % plants
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -229,6 +642,8 @@ def main():
                     help="multi-GPU candidate exchange: NVLink peer-memory kernels (default) or the NCCL all-gather")
     ap.add_argument("--no-overlap", action="store_true", help="pipelined mode: do not let consecutive sweeps overlap")
     ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph (single GPU only)")
+    ap.add_argument("--extras", default="auto", choices=["auto", "none", "all"],
+                    help="short passes of the other configurations attached as `extra` (auto: with the default workload)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.rows:
@@ -241,9 +656,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import hyperdb_b200 as hb
-    from hyperdb_b200 import _native as N
-    from hyperdb_b200.sharded import CudaEngine, ShardedMatrix, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -257,177 +669,69 @@ def main():
     if world != args.gpus and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
 
-    lo, hi = shard_bounds(w["n"], world, rank)
-    rows = gen_rows_torch(lo, hi, w["d"], w["dtype"], dev, seed=0)
-    m = hb.DeviceMatrix(rows, row_offset=lo)
-    if w.get("mask"):
-        g = torch.Generator(device=dev)
-        g.manual_seed(3_000_003 + rank)
-        keep_bits = torch.randint(-2**31, 2**31 - 1, ((hi - lo + 31) // 32,), generator=g, device=dev, dtype=torch.int32)
-        m.set_mask(keep_bits)
-    eng = CudaEngine(m)
-    sm = ShardedMatrix(eng, w["n"])
-    if world > 1 and args.exchange == "peer":
-        # CUDA IPC between the ranks' processes; if the box forbids it, every rank fails here alike and the run
-        # continues on the NCCL all-gather (reported in config.exchange)
+    extras = []
+    if args.extras == "all" or (args.extras == "auto" and args.workload == "c3_cosine_b1" and not args.rows):
+        extras = list(EXTRAS)
+        if world == 8 or args.extras == "all":
+            extras.append("c4_decay_mask_k100")
+    same = [e for e in extras if (WORKLOADS[e]["n"], WORKLOADS[e]["d"], WORKLOADS[e]["dtype"]) == (w["n"], w["d"], w["dtype"])]
+    max_b = max([w["b"]] + [WORKLOADS[e]["b"] for e in same])
+    max_k = max([w["k"]] + [WORKLOADS[e]["k"] for e in same])
+
+    bench = Bench(args, world, rank, dev)
+    head = bench.measure(args.workload, w, args.steps, args.warmup, max_b, max_k, graph=args.graph)
+    parity = bench.parity_check(w)
+    extra_lines = []
+    for e in extras:
+        we = dict(WORKLOADS[e])
+        b_same = [x for x in extras if (WORKLOADS[x]["n"], WORKLOADS[x]["d"], WORKLOADS[x]["dtype"]) == (we["n"], we["d"], we["dtype"])]
+        mb = max([w["b"]] + [WORKLOADS[x]["b"] for x in b_same])
+        mk = max([w["k"]] + [WORKLOADS[x]["k"] for x in b_same])
         try:
-            sm.enable_peer_exchange(max_batch=w["b"], max_k=w["k"])
-        except Exception as e:                                   # noqa: BLE001
-            print(f"bench.py: peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
-            sm.xchg = None
-    if not args.no_pipeline and w["b"] < 2:
-        eng.enable_pipeline()            # certify/exchange/merge of query i overlap the sweep of query i+1
-        m.set_sweep_overlap(not args.no_overlap)     # ... and the head of sweep i+1 fills the tail of sweep i
-    bias = 0.0
-    if w.get("decay"):
-        g = torch.Generator(device=dev)
-        g.manual_seed(2_000_003 + rank)
-        ts = 1.7e9 + 3600.0 * torch.rand(hi - lo, generator=g, device=dev, dtype=torch.float64)
-        m.set_timestamps(ts)
-        sm.refresh_decay()
-        bias = 0.3
-    b, k = w["b"], w["k"]
-    # a different query (batch) every step; large batches cycle through a pool of 6 batches
-    pool = (args.warmup + args.steps + 1) if b == 1 else min(args.warmup + args.steps + 1, 6)
-    q_host = gen_queries(pool * b, w["d"], w["dtype"])
-    q_dev = torch.as_tensor(q_host).to(dev)
-    q_pin = torch.as_tensor(q_host).pin_memory()
-
-    def qslice(t, i):
-        j = (i % pool) * b
-        return t[j:j + b]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident arm (value) ------------------------------------------------------------
-    # one captured CUDA graph per step when the step is short enough for host launch overhead to matter
-    graphed = None
-    if args.graph and world == 1 and b <= 64 and eng.post is None:      # opt-in: NCCL collectives captured in a graph stalled at teardown here
-        from hyperdb_b200.sharded import GraphedQuery
-        graphed = GraphedQuery(sm, qslice(q_dev, 0), k, w["metric"], bias)
-    step = (lambda q: graphed.replay(q)) if graphed else (lambda q: sm.query_async(q, k, w["metric"], bias))
-    outs = []
-    flag_log = []
-    for i in range(args.warmup):
-        outs.append(step(qslice(q_dev, i)))
-    barrier()
-    m.profile_enable(args.steps * b + 8)
-    N.lib().hdb_launch_count(1)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        o = step(qslice(q_dev, args.warmup + i))
-        if graphed:
-            flag_log.append(o[3].clone())            # the static outputs are overwritten by the next replay
-        else:
-            outs.append(o)
-    sm.wait_results()                                # pipelined mode: the last certify/exchange/merge run on the post stream
-    e1.record()
-    barrier()
-    launches = N.lib().hdb_launch_count(0)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = e0.elapsed_time(e1)
-    n_sweeps, sweep_ms = m.profile_read()
-    launches_per_step = launches / max(1, args.steps)
-    if graphed:
-        # Kernels replayed from a graph cannot be bracketed by event pairs and are not counted by the launch
-        # counter: run K more un-graphed steps of the same workload for the per-launch duration of the dominant
-        # kernel (roofline) and the launch count per step (the graph replays exactly these launches).
-        N.lib().hdb_launch_count(1)
-        for i in range(args.steps):
-            sm.query_async(qslice(q_dev, args.warmup + i), k, w["metric"], bias)
-        barrier()
-        n_sweeps, sweep_ms = m.profile_read()
-        launches_per_step = N.lib().hdb_launch_count(0) / max(1, args.steps)
-        launches = int(round(launches_per_step * args.steps))
-    m.profile_enable(0)
-    if graphed:
-        uncertified = sum(int(bool((f & N.FLAG_UNCERTIFIED).any())) for f in flag_log)
-    else:
-        uncertified = sum(int(bool((o[3] & N.FLAG_UNCERTIFIED).any())) for o in outs)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
-    value = b / (ms_step * 1e-3)
-
-    # ---- end-to-end arm through the host API ------------------------------------------------------
-    e2e_steps = max(3, min(args.steps, 20))
-    # the call a user makes: DeviceMatrix.query on one GPU, ShardedMatrix.query on several
-    host_query = (lambda q: m.query(q, k, w["metric"], bias)) if world == 1 else (lambda q: sm.query(q, k, w["metric"], bias))
-    q_np = q_pin.numpy()
-    for i in range(2):
-        host_query(qslice(q_np, i))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        host_query(qslice(q_np, args.warmup + i))
-    torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_qps = b * e2e_steps / t_e2e.item()
+            r = bench.measure(e, we, 5 if we["b"] > 1 else 20, 3, mb, mk, want_clocks=False)
+        except Exception as ex:                                   # noqa: BLE001
+            r = {"workload": e, "error": str(ex)[:300]} if rank == 0 else None
+        if r is not None:
+            r.pop("clocks", None)
+            extra_lines.append(r)
 
     if rank == 0:
-        peaks, peak_src = measured_peaks()
-        shard_bytes = algorithmic_bytes(w, hi - lo)
-        sweep_avg_ms = sweep_ms / max(1, n_sweeps)
-        overlapped = eng.post is not None and not args.no_overlap and b < 2
-        if overlapped and n_sweeps:
-            # Overlapping sweeps: an event pair around a launch also spans the time the kernel waited for the previous
-            # query's CTAs to leave the SMs, so the per-launch average is taken as timed region / launches (an upper
-            # bound of the kernel's own duration: the region also holds the small kernels), whichever is smaller.
-            sweep_avg_ms = min(sweep_avg_ms, ms_total / n_sweeps)
-        achieved = shard_bytes / (sweep_avg_ms * 1e-3) / 1e9 if n_sweeps else None
-        tensor_bound = b >= 256 and any(int(f) & N.FLAG_TENSOR for o in outs[-1:] for f in o[3].flatten().tolist())
-        shard_flops = 2.0 * (hi - lo) * w["d"] * b
         line = {
-            "metric": "queries/sec @top-%d" % k, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": "queries/sec @top-%d" % w["k"], "value": head["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"float16": "f16", "float32": "f32", "float64": "f64"}[w["dtype"]] + " storage, f32 accumulate"
             if w["dtype"] != "float64" else "f64",
             "data": "synthetic",
-            "config": {"workload": args.workload, "rows": w["n"], "dim": w["d"], "metric": w["metric"], "top_k": k, "batch": b,
+            "config": {"workload": args.workload, "rows": w["n"], "dim": w["d"], "metric": w["metric"], "top_k": w["k"], "batch": w["b"],
                        "sharding": f"rows/{world}", "l2": "inputs larger than L2 (shard %.2f GB per GPU, a new query every step)"
-                       % (shard_bytes / 1e9), "uncertified_steps": uncertified, "cuda_graph": bool(graphed),
-                       "exchange": ("peer-memory" if sm.xchg is not None else "nccl all-gather") if world > 1 else None,
-                       "pipelined": eng.post is not None, "sweep_overlap": bool(eng.post is not None and not args.no_overlap and b < 2)},
-            "clocks": clocks,
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(b * w["d"] * ITEM[w["dtype"]]),
-                    "d2h_bytes_per_step": int(b * k * 16 + b * 8), "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
-                         "traffic": ncu_traffic(args.workload) if world == 1 else None,
-                         "kernel": "sweep_kernel" if b < 2 else "batched_tc_kernel (sample + select passes)",
-                         "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
-                         "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peak_src,
-                         "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
+                       % head["shard_gb"], "uncertified_steps": head["uncertified_steps"], "cuda_graph": head["cuda_graph"],
+                       "exchange": ("peer-memory" if bench.sm is not None and bench.sm.xchg is not None else "nccl all-gather")
+                       if world > 1 else None,
+                       "pipelined": head["pipelined"], "sweep_overlap": head["sweep_overlap"]},
+            "clocks": head["clocks"],
+            "e2e": head["e2e"],
+            "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"],
         }
-        if tensor_bound and n_sweeps:
-            tf = shard_flops / (sweep_avg_ms * 1e-3) / 1e12
-            peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
-            line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                                "traffic": ncu_traffic(args.workload) if world == 1 else None, "kernel": "batched_tc_kernel (sample + select passes)",
-                                "launches_timed": n_sweeps, "avg_launch_ms": sweep_avg_ms,
-                                "algorithmic_flops_per_launch": shard_flops,
-                                "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
-                                "frac_of_burst": tf / peaks.get("bf16_tflops", 1667.5), "frac_of_nominal_2250": tf / 2250.0}
+        if parity is not None:
+            line["parity_check"] = parity
         if not args.no_cpu_baseline and world == 1:
-            sample = cpu_sample_rows(w)
-            tq = cpu_time_per_query(w, sample)
+            reps = 3
+            sample = cpu_sample_rows(w, reps)
+            tq, tk = cpu_time_per_query(w, sample, repeats=reps)
             line["cpu_baseline"] = {
                 "value": 1.0 / (tq * w["n"] / sample), "unit": "queries/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
-                "sample": f"1 query on {sample} of {w['n']} rows ({tq:.2f} s), scaled linearly by {w['n'] / sample:.1f}x; "
-                          f"oracle/reference_port.rank = the reference's NumPy calls; NumPy {np.__version__}"}
+                "sample": f"median of {reps} queries on {sample} of {w['n']} rows ({tq:.2f} s each), scaled linearly by {w['n'] / sample:.1f}x; "
+                          f"oracle/reference_port.rank = the reference's NumPy calls without its per-call NaN scan of the matrix "
+                          f"(hyperdb/ranking_algorithm.py:150), i.e. slightly faster than the reference itself; NumPy {np.__version__}"}
+            if tk is not None:
+                line["cpu_baseline"]["metric_kernel_only"] = {
+                    "value": 1.0 / (tk * w["n"] / sample), "unit": "queries/s",
+                    "what": f"np.dot(vectors, q) alone on the same sample ({tk:.2f} s), scaled the same way"}
+        if extra_lines:
+            line["extra"] = extra_lines
         print(json.dumps(line))
+    bench.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -194,6 +194,10 @@ int hdb_matrix_attach_exchange(hdb_matrix* m, hdb_exchange* x);
 int hdb_exchange_collect_async(hdb_exchange* x, int64_t n_queries, int64_t k, int64_t* out_idx, double* out_score,
                                int64_t* out_count, uint32_t* out_flags);
 int hdb_exchange_stream(hdb_exchange* x, void** cuda_stream);
+/* Run wait + merge on a CALLER-OWNED stream instead (it must outlive the exchange; give it the highest priority).  For
+ * hosts whose allocator tracks stream uses (torch's record_stream): the exchange's internal stream dies with
+ * hdb_exchange_destroy, a recorded use of it must not.  Call before the first step. */
+int hdb_exchange_set_stream(hdb_exchange* x, void* cuda_stream);
 int hdb_exchange_destroy(hdb_exchange* x);
 int hdb_exchange_handle_bytes(void);
 int hdb_exchange_local_handle(hdb_exchange* x, void* handle_out);
@@ -233,6 +237,10 @@ int hdb_profile_read(hdb_matrix* m, int* n_launches, float* total_ms);
  * back), 3 = tensor-core batched path when eligible, 4 = streaming sweep with the WIDE candidate class (128 candidates;
  * the first repair step for a query the automatic path could not certify). */
 int hdb_matrix_set_path(hdb_matrix* m, int mode);
+/* Small batches on the streaming path share ONE read of the matrix between up to 8 queries (multi-query sweep; the
+ * group size follows from the shape: 8 for fp16/fp32 rows with top_k <= 16, 4 for fp64 rows, top_k <= 100 and the
+ * bit-packed metrics).  This caps the group for A/B measurements and tests: 1 = one pass per query, 0 = no cap. */
+int hdb_matrix_set_max_group(hdb_matrix* m, int max_queries_per_pass);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,7 @@ struct hdb_matrix {
   bool decay_valid = false;
   cudaStream_t stream = nullptr;
   int path_mode = 0;
+  int max_group = 0;                // testing / A-B: cap on the queries per sweep pass (0 = as many as the shape allows)
   int grid = 0;
   // workspaces
   int64_t ws_q = 0;                 // query capacity of the buffers below
@@ -288,6 +289,12 @@ int hdb_matrix_set_path(hdb_matrix* m, int mode) {
   if (!m) return fail("null handle");
   if (mode < 0 || mode > 4) return fail("hdb_matrix_set_path: mode must be 0..4");
   m->path_mode = mode;
+  return 0;
+}
+int hdb_matrix_set_max_group(hdb_matrix* m, int max_queries_per_pass) {
+  if (!m) return fail("null handle");
+  if (max_queries_per_pass < 0) return fail("hdb_matrix_set_max_group: negative");
+  m->max_group = max_queries_per_pass;
   return 0;
 }
 int hdb_matrix_info(const hdb_matrix* m, int* dtype, int64_t* n_rows, int64_t* dim, int64_t* row_offset, int64_t* n_kept) {
@@ -717,7 +724,12 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
   cudaStream_t sw = sweep_stream ? sweep_stream : m->stream;
   if (!(fin_stream && fin_stream != m->stream)) HDB_CUDA(cudaMemsetAsync(m->tau + b0, 0, (size_t)cnt * 8, sw));   // pipelined: prep zeroed it
   const int elt = (m->dtype == 2) ? 8 : 4;
-  for (int64_t i = 0; i < cnt; ++i) {
+  // one pass of the matrix serves up to `gmax` queries (multi-query sweep): a batch of B queries costs ~B / gmax reads
+  const int gmax = m->max_group > 0 ? (m->max_group < sweep_max_group(v, metric, kp) ? m->max_group : sweep_max_group(v, metric, kp))
+                                    : sweep_max_group(v, metric, kp);
+  for (int64_t i = 0; i < cnt;) {
+    int g = 1;
+    while (g * 2 <= gmax && i + g * 2 <= cnt) g *= 2;
     SweepOut so;
     so.cand = m->cand + (size_t)i * m->grid * kp;
     so.tau = m->tau + b0 + i;
@@ -726,8 +738,9 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
     const uint32_t* qbits = m->qb.qbits + (size_t)(b0 + i) * m->words;
     const bool prof = m->prof_used + 2 <= m->prof_ev.size();
     if (prof) HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used], sw));
-    HDB_TRY(launch_sweep(v, metric, qa, qbits, m->qb.qaux + 2 * (b0 + i), f, kp, so, sw));
+    HDB_TRY(launch_sweep(v, metric, qa, qbits, m->qb.qaux + 2 * (b0 + i), f, kp, so, g, sw));
     if (prof) { HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used + 1], sw)); m->prof_used += 2; }
+    i += g;
   }
   FinalizeArgs a;
   a.m = v; a.f = f; a.metric = metric; a.rdt = rdt; a.kp = kp; a.k = (int)k; a.n_kept = m->n_kept; a.grid = m->grid;
@@ -1144,7 +1157,7 @@ int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter) 
       HDB_CUDA(cudaMemsetAsync(m->tau, 0, 8, m->stream));
       SweepOut so; so.cand = m->cand; so.tau = m->tau; so.grid = m->grid;
       (void)elt;
-      HDB_TRY(launch_sweep(v, m->last.metric, m->qb.qa, m->qb.qbits, m->qb.qaux, f, m->last.kp, so, m->stream));
+      HDB_TRY(launch_sweep(v, m->last.metric, m->qb.qa, m->qb.qbits, m->qb.qaux, f, m->last.kp, so, 1, m->stream));
     } else {
       HDB_TRY(run_fused(m, m->last.metric, m->last.rdt, m->last.kp, 0, nq, m->last.k, f, m->o_idx, m->o_score, m->o_count,
                         m->o_flags));

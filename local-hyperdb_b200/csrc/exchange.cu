@@ -147,6 +147,7 @@ struct hdb_exchange {
   unsigned long long* d_ctr = nullptr;   // [kCtr*]: steps pushed, steps merged, CTA arrival counters
   int* d_error = nullptr;                // 1 = a wait timed out (sticky: rebuild the exchange)
   cudaStream_t xs = nullptr;             // wait + merge run here
+  bool xs_owned = true;                  // false: a caller-owned stream (hdb_exchange_set_stream)
   bool connected = false;
 };
 
@@ -227,7 +228,7 @@ int hdb_exchange_destroy(hdb_exchange* x) {
   cudaDeviceSynchronize();
   for (int g = 0; g < x->world; ++g)
     if (x->ipc_opened[g] && x->peer[g]) cudaIpcCloseMemHandle(x->peer[g]);
-  if (x->xs) cudaStreamDestroy(x->xs);
+  if (x->xs && x->xs_owned) cudaStreamDestroy(x->xs);
   if (x->local) cudaFree(x->local);
   if (x->d_peer) cudaFree(x->d_peer);
   if (x->d_ctr) cudaFree(x->d_ctr);
@@ -288,6 +289,18 @@ int hdb_exchange_local_buffer(hdb_exchange* x, void** buffer) {
 int hdb_exchange_stream(hdb_exchange* x, void** cuda_stream) {
   if (!x || !cuda_stream) return fail("hdb_exchange_stream: NULL argument");
   *cuda_stream = x->xs;
+  return 0;
+}
+
+int hdb_exchange_set_stream(hdb_exchange* x, void* cuda_stream) {
+  if (!x || !cuda_stream) return fail("hdb_exchange_set_stream: NULL argument");
+  HDB_CUDA(cudaSetDevice(x->device));
+  if (x->xs) {
+    HDB_CUDA(cudaStreamSynchronize(x->xs));
+    if (x->xs_owned) cudaStreamDestroy(x->xs);
+  }
+  x->xs = reinterpret_cast<cudaStream_t>(cuda_stream);
+  x->xs_owned = false;
   return 0;
 }
 

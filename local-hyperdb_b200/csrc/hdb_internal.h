@@ -102,15 +102,19 @@ int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int met
 int launch_normalize_rows(int dtype, int64_t n, int64_t d, const void* src, void* dst, cudaStream_t s);
 double decode_ordered_double(unsigned long long bits);
 
-// ---- sweep.cu : fused score + select pass (B = 1 per launch)
+// ---- sweep.cu : fused score + select pass, 1 / 2 / 4 / 8 queries per launch (one read of the matrix)
 struct SweepOut {
-  uint64_t* cand;          // [grid][KP] per-CTA candidate keys (descending)
-  unsigned long long* tau; // global running threshold (must be zeroed before the launch)
+  uint64_t* cand;          // [nq][grid][KP] per-CTA candidate keys (descending) of the first query of the pass
+  unsigned long long* tau; // [nq] global running thresholds (must be zeroed before the launch)
   int grid;
 };
 int sweep_grid_size(int device);
-int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const double* qaux /*pearson, this query*/,
-                 const RowFilter& f, int kp, const SweepOut& out, cudaStream_t s);
+// largest query group (1, 2, 4 or 8) one pass can take for this shape / metric / candidate class
+int sweep_max_group(const MatrixView& m, int metric, int kp);
+// qa / qbits / qaux point at the FIRST query of the group; consecutive queries are d accumulate-type elements, `words`
+// sign-bit words and 2 doubles apart (the layout prep_query writes)
+int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const double* qaux /*pearson*/,
+                 const RowFilter& f, int kp, const SweepOut& out, int nq, cudaStream_t s);
 
 // ---- finalize.cu : merge + canonical re-score + certification; exact full-vector path
 struct FinalizeArgs {

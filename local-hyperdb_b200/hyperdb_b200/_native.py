@@ -67,6 +67,7 @@ SIGNATURES = {
     "hdb_exchange_wait_merge": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp]),
     "hdb_exchange_collect_async": (C.c_int, [vp, i64, i64, vp, vp, vp, vp]),
     "hdb_exchange_stream": (C.c_int, [vp, C.POINTER(vp)]),
+    "hdb_exchange_set_stream": (C.c_int, [vp, vp]),
     "hdb_matrix_attach_exchange": (C.c_int, [vp, vp]),
     "hdb_query_submit": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, i64, i64, C.c_double, C.c_int, i64p]),
     "hdb_query_collect": (C.c_int, [vp, i64, vp, vp, vp, vp]),
@@ -74,6 +75,7 @@ SIGNATURES = {
     "hdb_launch_count": (C.c_int64, [C.c_int]),
     "hdb_time_last_query": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "hdb_matrix_set_path": (C.c_int, [vp, C.c_int]),
+    "hdb_matrix_set_max_group": (C.c_int, [vp, C.c_int]),
     "hdb_profile_enable": (C.c_int, [vp, C.c_int]),
     "hdb_profile_read": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
 }

@@ -204,6 +204,10 @@ class DeviceMatrix:
         """0 automatic, 1 exact full-vector path, 2 fused sweep only (error instead of fallback)."""
         N.check(N.lib().hdb_matrix_set_path(self._h, int(mode)))
 
+    def set_max_group(self, n):
+        """Cap on the queries that share one sweep pass (1 = one pass per query; 0 = as many as the shape allows)."""
+        N.check(N.lib().hdb_matrix_set_max_group(self._h, int(n)))
+
     def set_post_stream(self, cuda_stream_ptr):
         """Pipelining of device-output queries: certify on this stream, overlapping the next query's sweep (0 = off)."""
         N.check(N.lib().hdb_matrix_set_post_stream(self._h, C.c_void_p(cuda_stream_ptr)))

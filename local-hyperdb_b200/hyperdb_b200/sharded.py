@@ -176,6 +176,10 @@ class PeerExchange:
         N.check(N.lib().hdb_exchange_collect_async(self._h, b, k, out_ptr, out_ptr + 8 * b * k, out_ptr + 16 * b * k,
                                                    out_ptr + 16 * b * k + 8 * b))
 
+    def set_stream(self, stream_ptr):
+        """Run wait + merge on a caller-owned stream (it must outlive this exchange)."""
+        N.check(N.lib().hdb_exchange_set_stream(self._h, C.c_void_p(stream_ptr)))
+
     def stream_ptr(self) -> int:
         p = C.c_void_p()
         N.check(N.lib().hdb_exchange_stream(self._h, C.byref(p)))
@@ -261,7 +265,7 @@ class ShardedMatrix:
             except Exception as e:                               # noqa: BLE001
                 err = e
         # every rank must take the same decision: one failed mapping switches the whole group back to the all-gather
-        ok = torch.tensor([0 if (err is not None or any(h is None for h in handles)) else 1], dtype=torch.int32, device=dev)
+        ok = torch.tensor([0 if (err is not None or any(h is None for h in handles)) else 1], dtype=torch.int32, device=self._comm_device())
         self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
         if int(ok.item()) == 0:
             if xchg is not None:
@@ -271,11 +275,18 @@ class ShardedMatrix:
             raise RuntimeError("peer-memory exchange unavailable on another rank")
         self.xchg = xchg
         if hasattr(self.engine, "attach_exchange"):
+            # wait + merge run on a torch-owned highest-priority stream: result blocks record their use of it
+            # (record_stream) and may be freed after the exchange is closed, so the stream must outlive the exchange
+            self._xs = torch.cuda.Stream(device=dev, priority=-1)
+            xchg.set_stream(self._xs.cuda_stream)
             self.engine.attach_exchange(xchg)   # the certify kernel now pushes; this side only collects
-            self._xs = torch.cuda.ExternalStream(xchg.stream_ptr(), device=dev)
         return True
 
     def _comm_device(self):
+        """Where the tiny control collectives (decay reference, row counts, set-up handshakes) live: on the GPU under NCCL,
+        on the host under gloo (e.g. several ranks sharing one GPU in the tests)."""
+        if self.dist.is_initialized() and "nccl" not in str(self.dist.get_backend(self.group)):
+            return "cpu"
         return getattr(self.engine, "device", "cpu")
 
     def refresh_decay(self):

@@ -236,6 +236,49 @@ def test_fused_equals_exact(hb, vdt, metric, n, d, kind):
         assert fallbacks == 0, "fused pass should certify on well-separated data"
 
 
+MQ_CASES = [(vdt, metric, n, d) for vdt in ("f16", "f32", "f64")
+            for metric in ("dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance",
+                           "jaccard_similarity", "pearson_correlation")
+            for (n, d) in ((30011, 136), (9001, 33))]
+
+
+@pytest.mark.parametrize("vdt,metric,n,d", MQ_CASES)
+def test_multi_query_sweep(hb, vdt, metric, n, d):
+    """Small batches share ONE read of the matrix (1 / 2 / 4 / 8 queries per sweep pass, SURVEY.md section 7.2 "B <= ~8"): the
+    batched answers must equal, bit for bit, one-query-per-pass answers (hdb_matrix_set_max_group(1)) for every batch size
+    1..11, with and without row mask / time decay, for k = 10 and the wide class k = 100, on aligned (d = 136) and unaligned
+    (d = 33) rows; the B = 5 batch is also checked against the oracle."""
+    import cases as C
+    import zlib
+    case = dict(seed=zlib.crc32(f"mq{vdt}{metric}{n}{d}".encode()) % 100000, n=n, d=d, vdt=vdt, qdt=vdt, kind="gauss", ts=True, ts_span=10.0)
+    V, _q, ts = C.make_inputs(case)
+    rng = np.random.default_rng(case["seed"])
+    Q = rng.standard_normal((11, d)).astype(V.dtype)
+    Q[3] = V[17]                                            # an exact hit
+    Q[6] = Q[2]                                             # two identical queries in one pass
+    keep = rng.random(n) < 0.55
+    m = hb.DeviceMatrix(V)
+    try:
+        for (k, use_ts, use_mask) in ((10, False, False), (100, False, False), (10, True, True)):
+            m.set_mask(keep if use_mask else None)
+            m.set_timestamps(ts if use_ts else None)
+            if use_ts:
+                m.refresh_decay()
+            bias = 0.4 if use_ts else 0.0
+            m.set_max_group(1)
+            ref = m.query(Q, k, metric, bias)
+            m.set_max_group(0)
+            for b in (2, 3, 4, 5, 8, 9, 11):
+                got = m.query(Q[:b], k, metric, bias)
+                assert np.array_equal(got[0], ref[0][:b]), (k, use_ts, use_mask, b)
+                assert np.array_equal(got[1], ref[1][:b]) and np.array_equal(got[2], ref[2][:b])
+            if k == 10:
+                for b in range(5):
+                    check_against_oracle(V, Q[b], ts if use_ts else None, bias, k, metric, ref[0][b], ref[1][b], keep if use_mask else None)
+    finally:
+        m.close()
+
+
 @pytest.mark.parametrize("d", [130, 600, 1100, 2500, 4200])
 def test_hamming_wide_rows(hb, d):
     """every lanes-per-row class of the bit-packed sweep (d <= 4096) and the generic form above it"""
