@@ -63,6 +63,10 @@ WORKLOADS = {
     "c3_pearson_b8": dict(n=10_000_000, d=768, dtype="float16", metric="pearson_correlation", k=10, b=8),
     "c4_decay_mask_k100": dict(n=100_000_000, d=384, dtype="float16", metric="cosine_similarity", k=100, b=1,
                                decay=True, mask=True),
+    # the same store CLUSTERED by the filtered metadata key at ingest (hdb_matrix_set_row_order): same ids, ties and answers,
+    # but the kept rows form contiguous runs
+    "c4_decay_mask_k100_clustered": dict(n=100_000_000, d=384, dtype="float16", metric="cosine_similarity", k=100, b=1,
+                                         decay=True, mask=True, cluster=True),
 }
 # the short passes attached to the default line as "extra" (same matrix as the headline first, then config C5's)
 EXTRAS = ["c3_cosine_b8", "c3_cosine_b64", "c3_cosine_b4096", "c5_hamming_b1", "c5_manhattan_b8"]
@@ -81,7 +85,9 @@ def matrix_bytes(w, rows):
 # ------------------------------------------------------------------------------------------------
 # synthetic data: unit-norm Gaussian rows, fixed seeds, any shard reproducible
 # ------------------------------------------------------------------------------------------------
-def gen_rows_torch(lo, hi, d, dtype, device, seed=0):
+def gen_rows_torch(lo, hi, d, dtype, device, seed=0, dest=None):
+    """Rows lo..hi of the global synthetic matrix.  dest (int64 CUDA tensor [hi - lo]): row lo + i is stored at position
+    dest[i] (a clustered physical layout) instead of position i."""
     import torch
     tdt = getattr(torch, dtype)
     out = torch.empty((hi - lo, d), dtype=tdt, device=device)
@@ -92,7 +98,10 @@ def gen_rows_torch(lo, hi, d, dtype, device, seed=0):
         x = torch.randn((CHUNK, d), generator=g, device=device, dtype=torch.float32)
         x /= x.norm(dim=1, keepdim=True).clamp_min(1e-30)
         a, b = max(lo, c * CHUNK), min(hi, (c + 1) * CHUNK)
-        out[a - lo:b - lo] = x[a - c * CHUNK:b - c * CHUNK].to(tdt)
+        if dest is None:
+            out[a - lo:b - lo] = x[a - c * CHUNK:b - c * CHUNK].to(tdt)
+        else:
+            out[dest[a - lo:b - lo]] = x[a - c * CHUNK:b - c * CHUNK].to(tdt)
         del x
     return out
 
@@ -109,6 +118,12 @@ def gen_rows_numpy(n, d, dtype, seed=0):
     v = rng.standard_normal((n, d), dtype=np.float32)
     v /= np.linalg.norm(v, axis=1, keepdims=True)
     return v.astype(dtype)
+
+
+def gen_category_torch(lo, hi, device):
+    import torch
+    ids = torch.arange(lo, hi, device=device, dtype=torch.int64)
+    return ((ids * 2654435761 + 40503) >> 7) % MASK_CATEGORIES
 
 
 def gen_keep_torch(lo, hi, device):
@@ -304,7 +319,7 @@ class Bench:
     def __init__(self, args, world, rank, dev):
         self.args, self.world, self.rank, self.dev = args, world, rank, dev
         self.shape = None
-        self.rows = self.m = self.eng = self.sm = None
+        self.rows = self.m = self.eng = self.sm = self.perm = self.keep = self.ts = None
 
     def barrier(self):
         import torch
@@ -325,7 +340,7 @@ class Bench:
                 self.sm.xchg.close()
                 self.sm.xchg = None
             self.m.close()
-        self.rows = self.m = self.eng = self.sm = None
+        self.rows = self.m = self.eng = self.sm = self.perm = self.keep = self.ts = None
         self.shape = None
         gc.collect()
         torch.cuda.empty_cache()
@@ -335,15 +350,33 @@ class Bench:
         import torch
         import hyperdb_b200 as hb
         from hyperdb_b200.sharded import CudaEngine, ShardedMatrix, shard_bounds
-        shape = (w["n"], w["d"], w["dtype"], bool(w.get("mask")), bool(w.get("decay")))
+        shape = (w["n"], w["d"], w["dtype"], bool(w.get("mask")), bool(w.get("decay")), bool(w.get("cluster")))
         if shape != self.shape:
             self.close()
             self.lo, self.hi = shard_bounds(w["n"], self.world, self.rank)
-            self.rows = gen_rows_torch(self.lo, self.hi, w["d"], w["dtype"], self.dev, seed=0)
+            self.perm = None
+            if w.get("cluster"):
+                # ingest clusters the shard by the documents' category (stable): physical row p holds document lo + perm[p]
+                cat = gen_category_torch(self.lo, self.hi, self.dev)
+                self.perm = torch.sort(cat, stable=True).indices
+                dest = torch.empty_like(self.perm)
+                dest[self.perm] = torch.arange(self.hi - self.lo, device=self.dev, dtype=torch.int64)
+                self.rows = gen_rows_torch(self.lo, self.hi, w["d"], w["dtype"], self.dev, seed=0, dest=dest)
+                del cat, dest
+            else:
+                self.rows = gen_rows_torch(self.lo, self.hi, w["d"], w["dtype"], self.dev, seed=0)
             self.m = hb.DeviceMatrix(self.rows, row_offset=self.lo)
+            if self.perm is not None:
+                self.m.set_row_order(self.perm.to(torch.int32))
             self.keep = None
             if w.get("mask"):
                 self.keep = gen_keep_torch(self.lo, self.hi, self.dev)
+                if os.environ.get("HDB_BENCH_MASK") == "random":          # A/B only: round 1's mask (independent random bits)
+                    g = torch.Generator(device=self.dev)
+                    g.manual_seed(3_000_003 + self.rank)
+                    self.keep = torch.rand(self.hi - self.lo, generator=g, device=self.dev) < 0.5
+                if self.perm is not None:
+                    self.keep = self.keep[self.perm]                  # per-row inputs travel in physical order
                 self.m.set_mask(pack_keep_bits(self.keep))
             self.eng = CudaEngine(self.m)
             self.sm = ShardedMatrix(self.eng, w["n"])
@@ -360,9 +393,15 @@ class Bench:
                 g = torch.Generator(device=self.dev)
                 g.manual_seed(2_000_003 + self.rank)
                 self.ts = 1.7e9 + 3600.0 * torch.rand(self.hi - self.lo, generator=g, device=self.dev, dtype=torch.float64)
+                if self.perm is not None:
+                    self.ts = self.ts[self.perm]
                 self.m.set_timestamps(self.ts)
                 self.sm.refresh_decay()
             self.shape = shape
+        if self.args.path:
+            self.eng.set_path(self.args.path)
+            self.eng.set_path = lambda mode: None              # keep the forced path for the whole run
+        self.m.set_max_group(self.args.max_group)
         pipelined = not self.args.no_pipeline and w["b"] < 2
         self.eng.enable_pipeline(pipelined)      # certify/exchange/merge of query i overlap the sweep of query i+1
         if pipelined:
@@ -642,6 +681,8 @@ def main():
                     help="multi-GPU candidate exchange: NVLink peer-memory kernels (default) or the NCCL all-gather")
     ap.add_argument("--no-overlap", action="store_true", help="pipelined mode: do not let consecutive sweeps overlap")
     ap.add_argument("--graph", action="store_true", help="capture the step in a CUDA graph (single GPU only)")
+    ap.add_argument("--path", type=int, default=0, help="A/B: hdb_matrix_set_path mode (2 = streaming sweep only, no tensor-core path)")
+    ap.add_argument("--max-group", type=int, default=0, help="A/B: cap on the queries per sweep pass (1 = one pass per query)")
     ap.add_argument("--extras", default="auto", choices=["auto", "none", "all"],
                     help="short passes of the other configurations attached as `extra` (auto: with the default workload)")
     args = ap.parse_args()
@@ -673,7 +714,7 @@ def main():
     if args.extras == "all" or (args.extras == "auto" and args.workload == "c3_cosine_b1" and not args.rows):
         extras = list(EXTRAS)
         if world == 8 or args.extras == "all":
-            extras.append("c4_decay_mask_k100")
+            extras += ["c4_decay_mask_k100", "c4_decay_mask_k100_clustered"]
     same = [e for e in extras if (WORKLOADS[e]["n"], WORKLOADS[e]["d"], WORKLOADS[e]["dtype"]) == (w["n"], w["d"], w["dtype"])]
     max_b = max([w["b"]] + [WORKLOADS[e]["b"] for e in same])
     max_k = max([w["k"]] + [WORKLOADS[e]["k"] for e in same])

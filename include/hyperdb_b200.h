@@ -106,6 +106,14 @@ int hdb_matrix_set_row_offset(hdb_matrix* m, int64_t row_offset);
 /* ---- row subset: replaces the filters' output (hyperdb/hyperdb.py:1119-1134, :1218-1308) ---- */
 /* Keep only rows whose bit is set (bit i of word i/32, LSB first, local row ids); NULL keeps all. */
 int hdb_matrix_set_mask(hdb_matrix* m, const uint32_t* bits, int src_space);
+/* Row order: the shard's rows are STORED in another order than the caller numbers them -- typically clustered by a
+ * metadata key at ingest, so that a metadata filter keeps a few contiguous runs of rows and the masked sweep streams them
+ * at the full HBM rate instead of skipping every other 768-byte row.  order[p] = the caller's local index of physical row
+ * p (a permutation of 0 .. n_rows-1; host or device).  Reported ids are row_offset + order[p] and ties resolve on them
+ * (lower index first), exactly as if the rows were stored in the caller's order; mask bits, the kept range, timestamps
+ * and uploads stay in PHYSICAL order.  NULL clears.  With an order set the shard cannot be mutated, hdb_scores is
+ * refused and batches run on the streaming sweeps (no tensor-core path). */
+int hdb_matrix_set_row_order(hdb_matrix* m, const uint32_t* order, int src_space);
 /* Keep only local rows in [lo, hi) (apply_skip_doc keeps one contiguous range); (0, n_rows) keeps all. */
 int hdb_matrix_set_range(hdb_matrix* m, int64_t lo, int64_t hi);
 
@@ -217,6 +225,13 @@ int hdb_exchange_wait_merge(hdb_exchange* x, void* cuda_stream, int64_t n_querie
  * carries HDB_FLAG_UNCERTIFIED | HDB_FLAG_EXCHANGE_ERROR in every out_flags entry and count 0; the error is sticky and
  * the ranks' step counters may disagree afterwards: destroy and rebuild the exchange. */
 int hdb_exchange_error(hdb_exchange* x, int* error);
+
+/* ---- query-side front end ------------------------------------------ */
+/* 128-bit digest of each query's VALUES (as float64, -0.0 == +0.0): the key of HyperDB's query cache, replacing
+ * `tuple(query_input.tolist())` (hyperdb/hyperdb.py:1368-1379) -- a CUDA-tensor query is hashed where it lives (one tiny
+ * kernel, 16 bytes per query back to the host), a host query on the host with the same function.  digest_out: HOST,
+ * 2 words per query.  Device queries are read on the handle's stream. */
+int hdb_query_digest(hdb_matrix* m, const void* queries, int q_dtype, int q_space, int64_t n_queries, uint64_t* digest_out);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */

@@ -39,6 +39,7 @@ struct hdb_matrix {
   float max_pratio = 0.f, max_cratio = 0.f, min_pstd = 0.f;
   bool finalized = false;
   uint32_t* mask = nullptr;
+  uint32_t* ord = nullptr; uint32_t* inv = nullptr;     // row order (hdb_matrix_set_row_order), both [n] or both null
   int64_t lo = 0, hi = 0, n_kept = 0;
   double* ts = nullptr;
   double* decay = nullptr;
@@ -61,6 +62,7 @@ struct hdb_matrix {
   void* sort_scratch = nullptr; size_t sort_scratch_bytes = 0;
   void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;      // row removal
   unsigned long long* misc = nullptr;   // [2] ordered max bits, count
+  unsigned long long* digest = nullptr; int64_t digest_cap = 0;   // hdb_query_digest: 2 words per query
   float* stats = nullptr; int* nan_flag = nullptr;
   // query pipelining (hdb_matrix_set_post_stream): the per-query workspaces exist twice so that the certify step of
   // query i (post stream) can overlap the sweep of query i+1 (main stream)
@@ -121,11 +123,13 @@ static MatrixView view_of(const hdb_matrix* m) {
   v.pmean = m->pmean; v.pstd = m->pstd; v.pscale = m->pscale; v.max_pratio = m->max_pratio; v.max_cratio = m->max_cratio; v.min_pstd = m->min_pstd;
   return v;
 }
+static int quiesce(hdb_matrix* m);
 static RowFilter filter_of(const hdb_matrix* m, double bias, bool use_decay) {
   RowFilter f;
   f.mask = m->mask; f.lo = m->lo; f.hi = m->hi;
   f.decay = use_decay ? m->decay : nullptr;
   f.bias = bias;
+  f.ord = m->ord; f.inv = m->inv;
   return f;
 }
 
@@ -205,6 +209,8 @@ int hdb_matrix_destroy(hdb_matrix* m) {
   if (m->alt_stream) cudaStreamSynchronize(m->alt_stream);
   if (m->post_stream) cudaStreamSynchronize(m->post_stream);
   if (m->owns_rows) cudaFree(m->rows);
+  if (m->ord) cudaFree(m->ord);
+  if (m->inv) cudaFree(m->inv);
   slot_store(m);
   {
     hdb_matrix::QuerySlot& other = m->slots[m->cur_slot ^ 1];
@@ -224,6 +230,7 @@ int hdb_matrix_destroy(hdb_matrix* m) {
                   m->tc.cand_count, m->tc.rec, m->tc.rec_count, m->tc.qsq};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (m->h_block) cudaFreeHost(m->h_block);
+  if (m->digest) cudaFree(m->digest);
   for (auto& t : m->tickets) {
     if (t.d_mine) cudaFree(t.d_mine);
     if (t.d_res) cudaFree(t.d_res);
@@ -427,6 +434,36 @@ int hdb_matrix_set_mask(hdb_matrix* m, const uint32_t* bits, int src_space) {
   return refresh_kept(m);
 }
 
+int hdb_matrix_set_row_order(hdb_matrix* m, const uint32_t* order, int src_space) {
+  if (!m) return fail("null handle");
+  if (!m->finalized) return fail("hdb_matrix_set_row_order: call hdb_matrix_finalize first");
+  HDB_CUDA(cudaSetDevice(m->device));
+  HDB_TRY(quiesce(m));
+  if (!order) {
+    if (m->ord) { cudaFree(m->ord); m->ord = nullptr; }
+    if (m->inv) { cudaFree(m->inv); m->inv = nullptr; }
+    return 0;
+  }
+  if (m->n >= (int64_t(1) << 32)) return fail("hdb_matrix_set_row_order: more than 2^32 rows per shard");
+  if (!m->ord) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->ord), (size_t)cap_rows(m) * 4));
+  if (!m->inv) HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->inv), (size_t)cap_rows(m) * 4));
+  HDB_CUDA(cudaMemcpyAsync(m->ord, order, (size_t)m->n * 4, src_space == HDB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                           m->stream));
+  int bad = 0;
+  int rc = launch_invert_order(m->ord, m->inv, m->n, m->nan_flag, m->stream);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(&bad, m->nan_flag, 4, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "hdb_matrix_set_row_order");
+  }
+  if (!rc && bad) rc = fail("hdb_matrix_set_row_order: `order` is not a permutation of 0 .. n_rows-1");
+  if (rc) {
+    cudaFree(m->ord); cudaFree(m->inv);
+    m->ord = nullptr; m->inv = nullptr;
+  }
+  return rc;
+}
+
 int hdb_matrix_set_range(hdb_matrix* m, int64_t lo, int64_t hi) {
   if (!m) return fail("null handle");
   if (lo < 0) lo = 0;
@@ -566,6 +603,7 @@ extern "C" int hdb_matrix_append(hdb_matrix* m, int64_t n_rows, const void* src,
   if (!m) return fail("null handle");
   if (!m->finalized) return fail("hdb_matrix_append: call hdb_matrix_finalize first");
   if (m->rows && !m->owns_rows) return fail("hdb_matrix_append: the shard uses adopted memory");
+  if (m->ord) return fail("hdb_matrix_append: a row order is set (rebuild the shard, or clear the order first)");
   if (n_rows < 0) return fail("hdb_matrix_append: negative row count");
   if (n_rows == 0) return 0;
   if (!src) return fail("hdb_matrix_append: src is NULL");
@@ -610,6 +648,7 @@ extern "C" int hdb_matrix_remove_rows(hdb_matrix* m, const int64_t* local_rows, 
   if (!m) return fail("null handle");
   if (!m->finalized) return fail("hdb_matrix_remove_rows: call hdb_matrix_finalize first");
   if (m->rows && !m->owns_rows) return fail("hdb_matrix_remove_rows: the shard uses adopted memory");
+  if (m->ord) return fail("hdb_matrix_remove_rows: a row order is set (rebuild the shard, or clear the order first)");
   if (count < 0) return fail("hdb_matrix_remove_rows: negative count");
   if (count == 0 || m->n == 0) return count == 0 ? 0 : fail("hdb_matrix_remove_rows: row index out of range");
   if (m->n > 0x7fffffff) return fail("hdb_matrix_remove_rows: more than 2^31 rows per shard");
@@ -824,7 +863,7 @@ static int run_exact(hdb_matrix* m, int metric, int rdt, int64_t b, int64_t k, c
                      int64_t* count) {
   MatrixView v = view_of(m);
   HDB_TRY(launch_full_scores(v, f, metric, rdt, m->qb.qc + b * m->d, m->qb.qbits + b * m->words, m->qb.qaux + 2 * b, m->totals, m->stream));
-  return exact_topk(m->device, m->totals, m->n, m->row_offset, k, m->n_kept, idx + b * k, score + b * k, count + b,
+  return exact_topk(m->device, m->totals, m->inv, m->n, m->row_offset, k, m->n_kept, idx + b * k, score + b * k, count + b,
                     &m->sort_scratch, &m->sort_scratch_bytes, m->stream);
 }
 
@@ -915,7 +954,7 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   if (k == 0) {
     HDB_CUDA(cudaMemsetAsync(count, 0, (size_t)nq * 8, m->stream));
     if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
-  } else if (kp && m->path_mode != 2 && m->path_mode != 4 && batched_tc_supported(view_of(m), metric, q_dtype, nq, use_decay)) {
+  } else if (kp && m->path_mode != 2 && m->path_mode != 4 && !m->ord && batched_tc_supported(view_of(m), metric, q_dtype, nq, use_decay)) {
     if (m->dtype == 1) kp = 128;         // tf32 select: wider error band, so certify a wider candidate list
     m->last.kp = kp;
     HDB_CUDA(cudaMemsetAsync(m->uncertified, 0, 4, m->stream));
@@ -1185,6 +1224,7 @@ int hdb_scores_ex(hdb_matrix* m, int metric, const void* query, int q_dtype, int
   if (metric < 0 || metric > 6) return fail("Unknown metric");
   if (q_dtype < 0 || q_dtype > 2) return fail("hdb_scores: q_dtype must be HDB_F16/F32/F64");
   if (!query || !out) return fail("hdb_scores: NULL argument");
+  if (m->ord) return fail("hdb_scores: a row order is set (the full score vector is defined on the caller's row order)");
   HDB_CUDA(cudaSetDevice(m->device));
   HDB_TRY(join_alt(m));
   HDB_TRY(ensure_workspace(m, 1, 1));
@@ -1220,6 +1260,28 @@ int hdb_scores_ex(hdb_matrix* m, int metric, const void* query, int q_dtype, int
   }
   if (tmp) cudaFree(tmp);
   return rc;
+}
+
+int hdb_query_digest(hdb_matrix* m, const void* queries, int q_dtype, int q_space, int64_t n_queries, uint64_t* digest_out) {
+  if (!m) return fail("null handle");
+  if (!queries || !digest_out) return fail("hdb_query_digest: NULL argument");
+  if (q_dtype < 0 || q_dtype > 2) return fail("hdb_query_digest: bad dtype");
+  if (n_queries <= 0) return 0;
+  if (q_space == HDB_HOST) {
+    query_digest_host(queries, q_dtype, n_queries, m->d, reinterpret_cast<unsigned long long*>(digest_out));
+    return 0;
+  }
+  HDB_CUDA(cudaSetDevice(m->device));
+  if (m->digest_cap < n_queries) {
+    if (m->digest) cudaFree(m->digest);
+    m->digest = nullptr; m->digest_cap = 0;
+    HDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->digest), (size_t)n_queries * 16));
+    m->digest_cap = n_queries;
+  }
+  HDB_TRY(launch_query_digest(queries, q_dtype, n_queries, m->d, m->digest, m->stream));
+  HDB_CUDA(cudaMemcpyAsync(digest_out, m->digest, (size_t)n_queries * 16, cudaMemcpyDeviceToHost, m->stream));
+  HDB_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
 }
 
 int hdb_normalize_rows(int device, int dtype, int64_t n_rows, int64_t dim, const void* src, int src_space, void* dst,

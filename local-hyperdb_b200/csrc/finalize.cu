@@ -20,6 +20,9 @@ constexpr int kSurvCap = 2048;      // candidate keys >= the final threshold tha
 constexpr int kFinThreads = 512;
 constexpr uint32_t kFlagUncertified = 8u;
 
+// row order (RowFilter::ord / inv): a key carries the caller's row index; the data live at the physical row
+__device__ __forceinline__ uint32_t phys_row(const RowFilter& f, uint32_t idx) { return f.inv ? f.inv[idx] : idx; }
+
 template <typename CS> __device__ __forceinline__ CS to_carrier(__half x) { return (CS)__half2float(x); }
 template <typename CS> __device__ __forceinline__ CS to_carrier(float x) { return (CS)x; }
 template <typename CS> __device__ __forceinline__ CS to_carrier(double x) { return (CS)x; }
@@ -74,7 +77,7 @@ __device__ void rescore_smem(const FinalizeArgs& a, int64_t b, const uint64_t* s
     __syncthreads();
     // ---- phase A
     for (int r = warp; r < nb; r += kFinThreads / 32) {
-      const uint32_t row = key_row(surv[base + r]);
+      const uint32_t row = phys_row(a.f, key_row(surv[base + r]));
       const T* src = grows + (int64_t)row * d;
       CS nrm = CS(1);
       if (metric == HDB_COSINE) nrm = SDT == 2 ? (CS) reinterpret_cast<const double*>(a.m.norms)[row]
@@ -109,15 +112,17 @@ __device__ void rescore_smem(const FinalizeArgs& a, int64_t b, const uint64_t* s
     if (metric <= 1) {
       const int t = tid - base;
       if (t >= 0 && t < nb) {
-        const uint32_t row = key_row(surv[tid]);
+        const uint32_t idx = key_row(surv[tid]);
+        const uint32_t row = phys_row(a.f, idx);
         const C* terms = s_terms + (size_t)t * pitch;
         const double sim = canonical_reduce<RDT>(metric, [&](int j) { return terms[j]; }, [&](int j) { return s_q[j]; }, d);
         c_tot[tid] = total_score(sim, a.f.decay, a.f.bias, row);
-        c_row[tid] = row;
+        c_row[tid] = idx;
       }
     } else {
       for (int r = warp; r < nb; r += kFinThreads / 32) {
-        const uint32_t row = key_row(surv[base + r]);
+        const uint32_t idx = key_row(surv[base + r]);
+        const uint32_t row = phys_row(a.f, idx);
         const C* terms = s_terms + (size_t)r * pitch;
         C dist = pairwise_sum_warp<RDT>([&](int j) { return terms[j]; }, d, lane, &s_pw[warp]);
         double sim;
@@ -130,7 +135,7 @@ __device__ void rescore_smem(const FinalizeArgs& a, int64_t b, const uint64_t* s
         }
         if (lane == 0) {
           c_tot[base + r] = total_score(sim, a.f.decay, a.f.bias, row);
-          c_row[base + r] = row;
+          c_row[base + r] = idx;
         }
       }
     }
@@ -286,7 +291,8 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
     ca.qc = a.qb.qc + b * a.m.d;
     ca.qstd = a.qb.qaux ? a.qb.qaux[2 * b] : 1.0;
     ca.distance = 0;
-    const uint32_t row = key_row(surv[tid]);
+    const uint32_t idx = key_row(surv[tid]);
+    const uint32_t row = phys_row(a.f, idx);
     const uint32_t* bitrow = a.m.bits ? a.m.bits + (int64_t)row * a.m.words : nullptr;
     double nrm = 1.0, aux2 = 0.0;
     if (a.metric == HDB_COSINE)
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
       sim = canonical_similarity_rt(ca, a.rdt, rowp, bitrow, nrm, aux2);
     }
     c_tot[tid] = total_score(sim, a.f.decay, a.f.bias, row);
-    c_row[tid] = row;
+    c_row[tid] = idx;
   }
   __syncthreads();
   if (tid < m) {
@@ -508,7 +514,13 @@ __global__ void take_topk_kernel(const double* keys, const int64_t* vals, int64_
 }
 
 // Stable descending radix sort of (total, row): equal totals keep ascending row order.
-int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
+__global__ void gather_totals_kernel(const double* totals, const uint32_t* inv, int64_t n, double* out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = totals[inv[i]];
+}
+
+// inv (row order set): the totals arrive in PHYSICAL row order and are first brought into the caller's order, so that the
+// stable sort resolves ties on the caller's row index and the sorted values ARE the reported ids.
+int exact_topk(int device, const double* totals, const uint32_t* inv, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
                int64_t* out_idx, double* out_score, int64_t* out_count, void** scratch, size_t* scratch_bytes,
                cudaStream_t s) {
   (void)device;
@@ -518,7 +530,7 @@ int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, 
   HDB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, temp, (const double*)nullptr, (double*)nullptr,
                                                      (const int64_t*)nullptr, (int64_t*)nullptr, (int)n, 0, 64, s));
   const size_t arr = ((size_t)n * 8 + 255) & ~size_t(255);
-  const size_t need = 3 * arr + temp + 256;
+  const size_t need = (inv ? 4 : 3) * arr + temp + 256;
   if (*scratch_bytes < need) {
     if (*scratch) HDB_CUDA(cudaFree(*scratch));
     *scratch = nullptr; *scratch_bytes = 0;
@@ -529,10 +541,16 @@ int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, 
   double* keys_out = reinterpret_cast<double*>(base);
   int64_t* vals_in = reinterpret_cast<int64_t*>(base + arr);
   int64_t* vals_out = reinterpret_cast<int64_t*>(base + 2 * arr);
-  void* tmp = base + 3 * arr;
+  void* tmp = base + (inv ? 4 : 3) * arr;
   if (n > 0) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    if (inv) {
+      double* ordered = reinterpret_cast<double*>(base + 3 * arr);
+      gather_totals_kernel<<<(unsigned)blocks, 256, 0, s>>>(totals, inv, n, ordered);
+      HDB_LAUNCHED();
+      totals = ordered;
+    }
     iota_kernel<<<(unsigned)blocks, 256, 0, s>>>(vals_in, n);
     HDB_LAUNCHED();
     HDB_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, temp, totals, keys_out, vals_in, vals_out, (int)n, 0, 64, s));

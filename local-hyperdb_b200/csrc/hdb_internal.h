@@ -35,6 +35,12 @@ struct RowFilter {
   int64_t lo, hi;         // kept range [lo, hi)
   const double* decay;    // exp(ts - max ts) per row, or nullptr
   double bias;            // recency_bias
+  // Row order (hdb_matrix_set_row_order): the rows are STORED in another order than the caller numbers them (e.g.
+  // clustered by a metadata key so that a filter keeps a few contiguous runs).  ord[p] = the caller's local index of
+  // physical row p, inv = its inverse.  Selection keys, ties (lower index first) and reported ids use ord; mask, range,
+  // timestamps and every other per-row column are in PHYSICAL order.  nullptr = identity.
+  const uint32_t* ord = nullptr;
+  const uint32_t* inv = nullptr;
 };
 
 // ---- peer-memory exchange (exchange.cu): what a pushing kernel needs to know
@@ -99,6 +105,10 @@ int launch_decay(const double* ts, double* decay, int64_t n, double ts_max, cuda
 int launch_stage1(double* ts, int64_t n, double bias1, double ts_max, cudaStream_t s);
 int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int metric, int sdt, int words,
                       const QueryBuffers& qb, unsigned long long* tau /*zeroed per query, or nullptr*/, cudaStream_t s);
+int launch_invert_order(const uint32_t* ord, uint32_t* inv, int64_t n, int* d_bad, cudaStream_t s);
+// 128-bit value digest of each query (HyperDB's cache key): device kernel and its host twin
+int launch_query_digest(const void* q, int q_dtype, int64_t nq, int64_t d, unsigned long long* out, cudaStream_t s);
+void query_digest_host(const void* q, int q_dtype, int64_t nq, int64_t d, unsigned long long* out);
 int launch_normalize_rows(int dtype, int64_t n, int64_t d, const void* src, void* dst, cudaStream_t s);
 double decode_ordered_double(unsigned long long bits);
 
@@ -144,7 +154,7 @@ int launch_full_scores(const MatrixView& m, const RowFilter& f, int metric, int 
 int launch_scores_out(const MatrixView& m, int metric, int rdt, const double* qc, const uint32_t* qbits, const double* qaux,
                       void* out /*dtype R, uint64 (hamming) or float64 (jaccard, pearson)*/, int distance /*euclidean: the distance itself*/,
                       cudaStream_t s);
-int exact_topk(int device, const double* totals, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
+int exact_topk(int device, const double* totals, const uint32_t* inv, int64_t n, int64_t row_offset, int64_t k, int64_t n_kept,
                int64_t* out_idx, double* out_score, int64_t* out_count, void** scratch, size_t* scratch_bytes,
                cudaStream_t s);
 int launch_merge_topk(int64_t n_lists, int64_t nq, int64_t k, int64_t ls_rec, int64_t ls_cnt, const double* scores, const int64_t* ids,

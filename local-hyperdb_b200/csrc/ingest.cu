@@ -10,6 +10,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "canonical.cuh"
+#include <cstring>
 #include "hdb_internal.h"
 #include "../../include/hyperdb_b200.h"
 
@@ -385,6 +386,94 @@ int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int met
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row order: inv = ord^-1, with a permutation check (every target hit exactly once, every value in range).
+// ---------------------------------------------------------------------------------------------
+__global__ void invert_order_kernel(const uint32_t* ord, uint32_t* inv, int64_t n, int* bad, int phase) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (phase == 0) inv[i] = 0xffffffffu;
+    else if (phase == 1) {
+      const uint32_t o = ord[i];
+      if ((int64_t)o >= n) *bad = 1;
+      else inv[o] = (uint32_t)i;
+    } else if (inv[i] == 0xffffffffu || ord[inv[i]] != (uint32_t)i) *bad = 1;     // a value was missing (another one repeated)
+  }
+}
+int launch_invert_order(const uint32_t* ord, uint32_t* inv, int64_t n, int* d_bad, cudaStream_t s) {
+  HDB_CUDA(cudaMemsetAsync(d_bad, 0, 4, s));
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  for (int phase = 0; phase < 3; ++phase) {
+    invert_order_kernel<<<(unsigned)blocks, 256, 0, s>>>(ord, inv, n, d_bad, phase);
+    HDB_LAUNCHED();
+  }
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit digest of a query's VALUES (the key of HyperDB's query cache, hyperdb/hyperdb.py:1368-1379: the reference
+// keys its LRU on tuple(query.tolist()), i.e. on the float64 values -- value-equal float16/32/64 queries share an
+// entry, -0.0 == 0.0).  h0 = sum_j mix(bits_j + (j+1) * C0), h1 = sum_j mix((bits_j ^ C2) + (j+1) * C1) (mod 2^64)
+// with bits_j the float64 bit pattern (-0.0 -> +0.0) and mix = splitmix64's finaliser: position-keyed, order-free, so
+// one CTA per query reduces it with shuffles.  hyperdb_b200/hyperdb.py::query_digest_host is the NumPy statement.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long digest_mix(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+constexpr unsigned long long kDigestC0 = 0x9e3779b97f4a7c15ull, kDigestC1 = 0xd1b54a32d192ed03ull, kDigestC2 = 0xa0761d6478bd642full;
+
+__global__ void query_digest_kernel(const void* queries, int qdt, int64_t d, unsigned long long* out) {
+  __shared__ unsigned long long s_h[2][8];
+  const int64_t b = blockIdx.x;
+  const char* q = reinterpret_cast<const char*>(queries) + b * d * dtype_size(qdt);
+  unsigned long long h0 = 0, h1 = 0;
+  for (int64_t j = threadIdx.x; j < d; j += blockDim.x) {
+    double v = load_as_double(q, qdt, j);
+    if (v == 0.0) v = 0.0;                                       // -0.0 and +0.0 are the same tuple element
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    h0 += digest_mix(bits + (unsigned long long)(j + 1) * kDigestC0);
+    h1 += digest_mix((bits ^ kDigestC2) + (unsigned long long)(j + 1) * kDigestC1);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { h0 += __shfl_xor_sync(kFull, h0, o); h1 += __shfl_xor_sync(kFull, h1, o); }
+  if ((threadIdx.x & 31) == 0) { s_h[0][threadIdx.x >> 5] = h0; s_h[1][threadIdx.x >> 5] = h1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t0 = 0, t1 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t0 += s_h[0][w]; t1 += s_h[1][w]; }
+    out[2 * b] = t0; out[2 * b + 1] = t1;
+  }
+}
+
+int launch_query_digest(const void* q, int q_dtype, int64_t nq, int64_t d, unsigned long long* out, cudaStream_t s) {
+  if (nq == 0) return 0;
+  query_digest_kernel<<<(unsigned)nq, 256, 0, s>>>(q, q_dtype, d, out);
+  HDB_LAUNCHED();
+  HDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void query_digest_host(const void* q, int q_dtype, int64_t nq, int64_t d, unsigned long long* out) {
+  for (int64_t b = 0; b < nq; ++b) {
+    unsigned long long h0 = 0, h1 = 0;
+    for (int64_t j = 0; j < d; ++j) {
+      const int64_t i = b * d + j;
+      double v = q_dtype == 0 ? (double)__half2float(reinterpret_cast<const __half*>(q)[i])
+                              : (q_dtype == 1 ? (double)reinterpret_cast<const float*>(q)[i] : reinterpret_cast<const double*>(q)[i]);
+      if (v == 0.0) v = 0.0;
+      unsigned long long bits;
+      memcpy(&bits, &v, 8);
+      h0 += digest_mix(bits + (unsigned long long)(j + 1) * kDigestC0);
+      h1 += digest_mix((bits ^ kDigestC2) + (unsigned long long)(j + 1) * kDigestC1);
+    }
+    out[2 * b] = h0; out[2 * b + 1] = h1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,8 +16,10 @@
 
 namespace hdb {
 
-// the nine (storage type, metric class) instantiations of csrc/sweep_inst.cu
-#define HDB_DECL_SWEEP(name) int name(const SweepParams& p, bool vec, int kp, int nq, int grid, size_t smem, cudaStream_t s)
+// the 18 (storage type, metric class, candidate class) instantiations of csrc/sweep_inst.cu
+#define HDB_DECL_SWEEP(name) \
+  int name##_kp32(const SweepParams& p, bool vec, int nq, int grid, size_t smem, cudaStream_t s); \
+  int name##_kp128(const SweepParams& p, bool vec, int nq, int grid, size_t smem, cudaStream_t s)
 HDB_DECL_SWEEP(sweep_f16_mc0); HDB_DECL_SWEEP(sweep_f16_mc1); HDB_DECL_SWEEP(sweep_f16_mc2);
 HDB_DECL_SWEEP(sweep_f32_mc0); HDB_DECL_SWEEP(sweep_f32_mc1); HDB_DECL_SWEEP(sweep_f32_mc2);
 HDB_DECL_SWEEP(sweep_f64_mc0); HDB_DECL_SWEEP(sweep_f64_mc1); HDB_DECL_SWEEP(sweep_f64_mc2);
@@ -86,11 +88,13 @@ int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t
   const int mc = (metric == HDB_DOT || metric == HDB_COSINE || metric == HDB_PEARSON) ? 0 : (metric == HDB_EUCLIDEAN ? 1 : 2);
   const size_t smem = float_sweep_smem(m, kp, nq, vec);
   if (smem > 200 * 1024) return fail("sweep: dimension too large for the fused pass");
-  typedef int (*Fn)(const SweepParams&, bool, int, int, int, size_t, cudaStream_t);
-  static const Fn table[3][3] = {{sweep_f16_mc0, sweep_f16_mc1, sweep_f16_mc2},
-                                 {sweep_f32_mc0, sweep_f32_mc1, sweep_f32_mc2},
-                                 {sweep_f64_mc0, sweep_f64_mc1, sweep_f64_mc2}};
-  return table[m.dtype][mc](p, vec, kp, nq, out.grid, smem, s);
+  typedef int (*Fn)(const SweepParams&, bool, int, int, size_t, cudaStream_t);
+#define HDB_PAIR(name) {name##_kp32, name##_kp128}
+  static const Fn table[3][3][2] = {{HDB_PAIR(sweep_f16_mc0), HDB_PAIR(sweep_f16_mc1), HDB_PAIR(sweep_f16_mc2)},
+                                    {HDB_PAIR(sweep_f32_mc0), HDB_PAIR(sweep_f32_mc1), HDB_PAIR(sweep_f32_mc2)},
+                                    {HDB_PAIR(sweep_f64_mc0), HDB_PAIR(sweep_f64_mc1), HDB_PAIR(sweep_f64_mc2)}};
+#undef HDB_PAIR
+  return table[m.dtype][mc][kp <= 32 ? 0 : 1](p, vec, nq, out.grid, smem, s);
 }
 
 }  // namespace hdb

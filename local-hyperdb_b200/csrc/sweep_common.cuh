@@ -167,6 +167,15 @@ __device__ __forceinline__ void cta_merge_and_store(uint64_t* s_lists, WarpList<
   }
 }
 
+// Selection key of physical row `row`.  With a row order set the key carries the row's index in the CALLER's numbering
+// (ties -> lower index there); that index is only loaded for rows whose score alone could still pass the threshold
+// (make_key(score, 0) is the largest key the score can give), i.e. for a handful of rows per warp.  0 never passes.
+__device__ __forceinline__ uint64_t ordered_key(const RowFilter& f, float score, uint32_t row, bool alive, uint64_t tau) {
+  if (f.ord == nullptr) return make_key(score, row);
+  if (!alive || make_key(score, 0u) <= tau) return 0;
+  return make_key(score, f.ord[row]);
+}
+
 // keep bits of the 32-row window w (rows 32w .. 32w+31): mask word AND kept range AND row count
 __device__ __forceinline__ uint32_t window_keep_bits(const RowFilter& f, int64_t w, int64_t n) {
   uint32_t bits = f.mask ? f.mask[w] : 0xffffffffu;

@@ -8,13 +8,13 @@ namespace hdb {
 // ---------------------------------------------------------------------------------------------
 // float sweeps: NQ queries per pass (one read of the matrix, NQ score streams)
 // ---------------------------------------------------------------------------------------------
-// A warp keeps R rows in flight and NQ queries: R*NQ accumulators per lane (8x1, 8x2, 8x4, 4x8).  After the column
+// A warp keeps R rows in flight and NQ queries: R*NQ accumulators per lane (8x1, 8x2, 4x4, 4x8).  After the column
 // loop a TRANSPOSING butterfly leaves every lane with the full sum of ONE (query, row) pair -- value index
 // v = lane >> log2(32 / (R*NQ)), query = v / R, row = v % R -- so the epilogue, the key and the threshold test of all
 // pairs run in parallel and each query feeds its own candidate list.
 template <int NQ> struct MqCfg {
-  static constexpr int kR = (NQ <= 4) ? 8 : 4;
-  static constexpr int kV = kR * NQ;                       // 8, 16, 32, 32
+  static constexpr int kR = (NQ <= 2) ? 8 : 4;
+  static constexpr int kV = kR * NQ;                       // 8, 16, 16, 32
   static constexpr int kRepShift = (kV == 8) ? 2 : (kV == 16 ? 1 : 0);
   static constexpr int kLanesPerQuery = 32 / NQ;
 };
@@ -169,9 +169,9 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < NQ) s_tau[threadIdx.x] = 0;
-  // Query tile.  VEC: piece-major so that the 32 lanes of a warp read 32 CONSECUTIVE 16-byte pieces (conflict-free
+  // Query tile.  VEC with several queries: piece-major so that the 32 lanes of a warp read 32 CONSECUTIVE 16-byte pieces (conflict-free
   // LDS.128): piece p = e4 * NQ + j of column step `st` for lane l sits at ((st * NP + p) * 32 + l).  Scalar path: [NQ][d].
-  if (VEC) {
+  if (VEC && NQ > 1) {
     const int steps = (p.nvec + 31) / 32;
     constexpr int kPE = PieceOf<Acc>::kElems;
     for (int i = threadIdx.x; i < steps * NP * 32 * kPE; i += kSweepThreads) {
@@ -257,9 +257,70 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[i] = Acc(0);
 
-      if (VEC) {
+      if (VEC && NQ >= 4) {
+        // NQ * R * kPerVec accumulate operations per lane and column step: the step is long enough to hide one HBM round
+        // trip, so the rows of step st + 1 are requested before step st is consumed.  Two register buffers used in turn
+        // (no copies), one 64-bit pointer per row advanced once per pair of steps (the loads use immediate offsets), full
+        // steps without any predicate: a row slot that holds no kept row reads the window's first row (valid memory, its
+        // sums are never pushed).  Only the last, partial step (d not a multiple of 32 vectors) zero-fills by lane.
+        const char* rp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) rp[r] = base + ro[r] + (uint32_t)lane * 16u;
+        const int nsteps = (p.nvec + 31) >> 5, full = p.nvec >> 5;
+        auto load = [&](uint4 (&dst)[R], int step, int byte_off) {
+          if (step < full) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) dst[r] = ld_stream16(rp[r] + byte_off);
+          } else {
+            const bool ok = step * 32 + lane < p.nvec;
+#pragma unroll
+            for (int r = 0; r < R; ++r) dst[r] = ok ? ld_stream16(rp[r] + byte_off) : make_uint4(0, 0, 0, 0);
+          }
+        };
+        auto compute = [&](const uint4 (&src)[R], int step) {
+          const Piece* qp = s_q4 + (size_t)step * NP * 32 + lane;
+#pragma unroll
+          for (int e4 = 0; e4 < kE4; ++e4) {
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+              const Piece q = qp[(e4 * NQ + j) * 32];
+#pragma unroll
+              for (int r = 0; r < R; ++r) accum_piece<MC>(acc[j * R + r], src[r], e4, q, T());
+            }
+          }
+        };
+        uint4 b0[R], b1[R];
+        load(b0, 0, 0);
         int st = 0;
-#pragma unroll(NQ == 1 ? 2 : 1)
+#pragma unroll 1
+        for (; st + 2 <= nsteps; st += 2) {
+          load(b1, st + 1, 512);
+          compute(b0, st);
+          if (st + 2 < nsteps) load(b0, st + 2, 1024);
+          compute(b1, st + 1);
+#pragma unroll
+          for (int r = 0; r < R; ++r) rp[r] += 1024;
+        }
+        if (st < nsteps) compute(b0, st);
+      } else if (VEC && NQ == 1) {
+        // one query: plain [d] query tile, two column steps (16 independent 16-byte loads per lane) in flight
+#pragma unroll 2
+        for (int c = lane; c < p.nvec; c += 32) {
+          uint4 raw[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if ((keep >> r) & 1u) raw[r] = ld_stream16(base + (ro[r] + (uint32_t)c * 16u));
+            else raw[r] = make_uint4(0, 0, 0, 0);
+          }
+          Acc q[kPerVec];
+#pragma unroll
+          for (int i = 0; i < kPerVec; ++i) q[i] = s_q[c * kPerVec + i];
+#pragma unroll
+          for (int r = 0; r < R; ++r) accum_vec<MC>(acc[r], raw[r], q, T());
+        }
+      } else if (VEC) {
+        int st = 0;
+#pragma unroll 1
         for (int c = lane; c < p.nvec; c += 32, ++st) {
           uint4 raw[R];
 #pragma unroll
@@ -306,7 +367,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
         if (p.f.decay) score = (float)((double)sim + p.f.bias * my_decay);
         else score = (float)sim;
       }
-      const uint64_t key = make_key(score, (uint32_t)mrow);
+      const uint64_t key = ordered_key(p.f, score, (uint32_t)mrow, rep && mine_kept, wl.tau);
       wl.push(rep && mine_kept && key > wl.tau, key, lane, s_tau, p.tau);
     }
   }
@@ -336,9 +397,5 @@ static int launch_nq(const SweepParams& p, int nq, int grid, size_t smem, cudaSt
 template <typename T, int MC, int KP>
 static int launch_vec(const SweepParams& p, bool vec, int nq, int grid, size_t smem, cudaStream_t s) {
   return vec ? launch_nq<T, MC, KP, true>(p, nq, grid, smem, s) : launch_nq<T, MC, KP, false>(p, nq, grid, smem, s);
-}
-template <typename T, int MC>
-static int launch_kp(const SweepParams& p, bool vec, int kp, int nq, int grid, size_t smem, cudaStream_t s) {
-  return kp <= 32 ? launch_vec<T, MC, 32>(p, vec, nq, grid, smem, s) : launch_vec<T, MC, 128>(p, vec, nq, grid, smem, s);
 }
 }  // namespace hdb

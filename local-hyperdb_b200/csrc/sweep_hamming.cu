@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_kernel(Hamming
       double exact = p.jaccard ? (double)(dsum & 0xffff) / (double)(dsum >> 16) : (double)((int)p.d - dsum);
       if (p.f.decay && kept[r] && sub == 0) exact += p.f.bias * p.f.decay[row];
       const float score = (float)exact;
-      const uint64_t key = make_key(score, (uint32_t)row);
+      const uint64_t key = ordered_key(p.f, score, (uint32_t)row, sub == 0 && kept[r], wl.tau);
       wl.push(sub == 0 && kept[r] && key > wl.tau, key, lane, s_tau, p.tau);
     }
   }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_lpr_kernel(Ham
           double exact = JAC ? (double)(diff & 0xffff) / (double)(diff >> 16) : (double)((int)p.d - diff);
           if (p.f.decay) exact += p.f.bias * my_decay;
           const float score = (float)exact;
-          const uint64_t key = make_key(score, (uint32_t)(row0 + my_loc));
+          const uint64_t key = ordered_key(p.f, score, (uint32_t)(row0 + my_loc), rep && my_kept, wl[j].tau);
           wl[j].push(rep && my_kept && key > wl[j].tau, key, lane, s_tau + j, p.tau + j);
         }
       }
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_hamming_staged_kernel(
         }
         double exact = JAC ? (double)a / (double)b : (double)((int)p.d - a);
         if (p.f.decay) exact += p.f.bias * my_decay;
-        const uint64_t key = make_key((float)exact, (uint32_t)row);
+        const uint64_t key = ordered_key(p.f, (float)exact, (uint32_t)row, kept, wl[j].tau);
         wl[j].push(kept && key > wl[j].tau, key, lane, s_tau + j, p.tau + j);
       }
     }

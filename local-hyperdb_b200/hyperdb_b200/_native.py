@@ -45,6 +45,7 @@ SIGNATURES = {
     "hdb_matrix_set_sweep_overlap": (C.c_int, [vp, C.c_int]),
     "hdb_matrix_info": (C.c_int, [vp, C.POINTER(C.c_int), i64p, i64p, i64p, i64p]),
     "hdb_matrix_set_mask": (C.c_int, [vp, vp, C.c_int]),
+    "hdb_matrix_set_row_order": (C.c_int, [vp, vp, C.c_int]),
     "hdb_matrix_set_range": (C.c_int, [vp, i64, i64]),
     "hdb_matrix_set_timestamps": (C.c_int, [vp, vp, C.c_int]),
     "hdb_matrix_kept_ts_max": (C.c_int, [vp, f64p, i64p]),
@@ -53,6 +54,7 @@ SIGNATURES = {
     "hdb_query": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, i64, i64, C.c_double, vp, vp, vp, vp, C.c_int]),
     "hdb_scores": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]),
     "hdb_scores_ex": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "hdb_query_digest": (C.c_int, [vp, vp, C.c_int, C.c_int, i64, vp]),
     "hdb_normalize_rows": (C.c_int, [C.c_int, C.c_int, i64, i64, vp, C.c_int, vp, C.c_int]),
     "hdb_merge_topk": (C.c_int, [C.c_int, vp, i64, i64, i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]),
     "hdb_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.POINTER(vp)]),

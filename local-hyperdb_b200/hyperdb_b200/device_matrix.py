@@ -156,6 +156,24 @@ class DeviceMatrix:
             bits = np.ascontiguousarray(keep, np.uint32)
         N.check(N.lib().hdb_matrix_set_mask(self._h, C.c_void_p(bits.ctypes.data), N.HDB_HOST))
 
+    def set_row_order(self, order):
+        """order[p] = the caller's local index of physical row p (uint32 permutation; NumPy array or CUDA tensor), or None.
+        Ids and ties then follow the caller's numbering although the rows are stored clustered (hdb_matrix_set_row_order)."""
+        if order is None:
+            N.check(N.lib().hdb_matrix_set_row_order(self._h, None, N.HDB_HOST))
+        elif _is_torch(order):
+            import torch
+            t = order.contiguous()
+            if t.dtype not in (torch.int32, torch.uint32) or t.numel() != self.shape[0]:
+                raise ValueError("row order must be a 32-bit permutation with one entry per row")
+            p, space = _ptr(t)
+            N.check(N.lib().hdb_matrix_set_row_order(self._h, p, space))
+        else:
+            o = np.ascontiguousarray(order, np.uint32)
+            if o.shape != (self.shape[0],):
+                raise ValueError("row order must have one entry per row")
+            N.check(N.lib().hdb_matrix_set_row_order(self._h, C.c_void_p(o.ctypes.data), N.HDB_HOST))
+
     def set_range(self, lo, hi):
         N.check(N.lib().hdb_matrix_set_range(self._h, int(lo), int(hi)))
 

@@ -429,14 +429,23 @@ class ShardedMatrix:
             raise RuntimeError("peer-memory exchange: a rank did not deliver its candidates within 10 s")
         if (flags & N.FLAG_QUERY_NAN).any():
             raise ValueError("Vectors and query_vector should not contain NaN values.")
-        if (flags & N.FLAG_UNCERTIFIED).any() and k > 0:
+        bad = np.nonzero((flags & N.FLAG_UNCERTIFIED).any(axis=0))[0] if k > 0 else ()
+        if len(bad):
+            # only the queries some shard could not certify are repeated (a batch of 4096 typically has a handful)
             nxt = 4 if (path == 0 and k <= 100) else (1 if path != 1 else None)
             if nxt is None:
                 raise RuntimeError("the exact path reported an uncertified result")
+            if len(bad) == b:
+                sub = q
+            elif isinstance(q, np.ndarray):
+                sub = np.ascontiguousarray(q[bad])
+            else:
+                sub = q[[int(i) for i in bad]].contiguous()
             try:
-                return self.collect(self.submit(q, k, metric, bias, _path=nxt))
+                r_idx, r_sc, r_cnt = self.collect(self.submit(sub, k, metric, bias, _path=nxt))
             finally:
                 self.engine.set_path(0)
+            idx[bad], sc[bad], cnt[bad] = r_idx, r_sc, r_cnt
         return idx, sc, cnt
 
     def query(self, queries, top_k, metric, recency_bias=0.0):

@@ -129,3 +129,89 @@ def test_fullsize_properties(name, n, d, dtype, metrics, k):
         m.close()
         del rows
         torch.cuda.empty_cache()
+
+
+BATCH_CONFIGS = [  # name, rows, dim, dtype, metric, k, batch  (BASELINE.json's batched configurations + the multi-query sweep)
+    ("C2_b1024", 1_000_000, 384, "float32", "cosine_similarity", 10, 1024),
+    ("C3_b64", 10_000_000, 768, "float16", "cosine_similarity", 10, 64),
+    ("C3_b4096", 10_000_000, 768, "float16", "cosine_similarity", 10, 4096),
+    ("C3_dot_b8", 10_000_000, 768, "float16", "dot_product", 10, 8),
+    ("C5_euclid_b1024", 5_000_000, 1024, "float32", "euclidean_metric", 10, 1024),
+    ("C5_manhattan_b8", 5_000_000, 1024, "float32", "manhattan_distance", 10, 8),
+    ("C5_hamming_b8", 5_000_000, 1024, "float32", "hamming_distance", 10, 8),
+]
+
+
+def plant_batch(rows, Q, per_query, rng, torch):
+    """For every query b overwrite `per_query` rows with unit(q_b + 0.05*(i+1)*noise_i), i = 0..per_query-1, at random
+    distinct positions (the positions of one query are NOT sorted by rank): cos(q_b, planted_i) = 1/sqrt(1 + (0.05(i+1))^2) is
+    far above anything a random unit row reaches, so query b must return its plants first, in plant order."""
+    n, d = rows.shape
+    b = Q.shape[0]
+    pos = rng.choice(n, size=b * per_query, replace=False).reshape(b, per_query)
+    Qf = torch.as_tensor(Q.astype(np.float32), device=rows.device)
+    for i in range(per_query):
+        noise = torch.as_tensor(rng.standard_normal((b, d)).astype(np.float32), device=rows.device)
+        noise = noise - ((noise * Qf).sum(1, keepdim=True) / (Qf * Qf).sum(1, keepdim=True)) * Qf
+        noise = noise / noise.norm(dim=1, keepdim=True) * Qf.norm(dim=1, keepdim=True)
+        v = Qf + 0.05 * (i + 1) * noise
+        v = v / v.norm(dim=1, keepdim=True)
+        rows[torch.as_tensor(pos[:, i], device=rows.device)] = v.to(rows.dtype)
+    return pos
+
+
+@pytest.mark.parametrize("name,n,d,dtype,metric,k,b", BATCH_CONFIGS, ids=[c[0] for c in BATCH_CONFIGS])
+def test_fullsize_batches(name, n, d, dtype, metric, k, b):
+    """BASELINE.json's batched configurations at full size (tensor-core path for the wide batches, multi-query sweep for the
+    small ones): per-query planted rows come back first and in plant order, every returned score equals the oracle's score of
+    that row (bit for bit where NumPy is deterministic), no row of a random sample beats a query's k-th score, ties go to the
+    lower index, and the batched answer equals the single-query answer for a subset of the queries."""
+    import torch
+    import bench
+    import hyperdb_b200 as hb
+    free, _total = torch.cuda.mem_get_info()
+    if free < n * d * bench.ITEM[dtype] * 1.35 + (4 << 30):
+        pytest.skip("not enough free HBM for this configuration")
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(777)
+    rows = bench.gen_rows_torch(0, n, d, dtype, dev, seed=0)
+    Q = bench.gen_queries(b, d, dtype, seed=4242)
+    per_query = 3
+    pos = plant_batch(rows, Q, per_query, rng, torch)
+    m = hb.DeviceMatrix(rows)
+    try:
+        idx, sc, cnt, flags = m.query(Q, k, metric)
+        assert idx.shape == (b, k) and np.all(cnt == k)
+        assert np.all(np.diff(sc, axis=1) <= 0)
+        if metric != "hamming_distance":             # sign bits of the planted rows are not ordered by construction
+            assert np.array_equal(idx[:, :per_query], pos), np.nonzero((idx[:, :per_query] != pos).any(axis=1))[0][:10]
+        # ties -> lower index
+        tie = sc[:, :-1] == sc[:, 1:]
+        assert np.all(idx[:, :-1][tie] < idx[:, 1:][tie])
+        # the oracle's score of every returned row (rows copied back in one gather)
+        got = rows[torch.as_tensor(idx.reshape(-1), device=dev)].cpu().numpy().reshape(b, k, d)
+        check = range(b) if b <= 64 else list(range(0, b, max(1, b // 192)))
+        exact = EXACT[dtype] or metric in ("euclidean_metric", "manhattan_distance", "hamming_distance")
+        for qi in check:
+            osc = K.total_scores(got[qi], Q[qi], metric)
+            if exact:
+                assert np.array_equal(osc, sc[qi]), (qi, osc, sc[qi])
+            else:
+                np.testing.assert_allclose(osc, sc[qi], rtol=1e-5)
+        # a random sample of rows must not beat any query's k-th score (oracle arithmetic on a subset of the queries)
+        samp = rng.choice(n, size=2048, replace=False)
+        srows = rows[torch.as_tensor(samp, device=dev)].cpu().numpy()
+        for qi in list(check)[:24]:
+            ssc = K.total_scores(srows, Q[qi], metric)
+            inside = np.isin(samp, idx[qi])
+            assert np.all(ssc[~inside] <= sc[qi, -1]), qi
+            tied = (~inside) & (ssc == sc[qi, -1])
+            assert np.all(samp[tied] > idx[qi, -1])
+        # batched == one query at a time
+        for qi in list(check)[:6]:
+            i1, s1, _, _ = m.query(Q[qi], k, metric)
+            assert np.array_equal(i1[0], idx[qi]) and np.array_equal(s1[0], sc[qi]), qi
+    finally:
+        m.close()
+        del rows
+        torch.cuda.empty_cache()

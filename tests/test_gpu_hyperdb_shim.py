@@ -84,3 +84,226 @@ def test_query_cache_semantics(capsys):
         nocache.close()
     finally:
         db.close()
+
+
+def test_query_side_front_end_f4():
+    """SURVEY.md section 8(f) rank 4, the query-side front end (hyperdb/hyperdb.py:311-337, :1112-1117, :1368-1388):
+    a CUDA-tensor query is hashed on the device (hdb_query_digest == its NumPy statement, for every stored dtype), ranked
+    without a host copy of the vector and served from the same cache entry as the value-equal host query; `query_batch`
+    takes the embedding model's output tile (a CUDA tensor) and returns, per row, exactly what `query` returns."""
+    import ctypes as C
+    import torch
+    from hyperdb_b200 import _native as N
+    from hyperdb_b200.hyperdb import HyperDB, query_digest_host
+    rng = np.random.default_rng(17)
+    n, d = 5000, 96
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    docs = [{"id": i, "group": "ab"[i % 2], "timestamp": 1.7e9 + i} for i in range(n)]
+    db = HyperDB(documents=docs, vectors=V, metadata_keys=["group", "timestamp"], cache_size=8)
+    try:
+        # the device digest is the host digest, for float16 / float32 / float64 queries, -0.0 folded onto +0.0
+        for dt, tdt in ((np.float16, torch.float16), (np.float32, torch.float32), (np.float64, torch.float64)):
+            q = rng.standard_normal(d).astype(dt)
+            q[3] = -0.0
+            out = (C.c_uint64 * 2)()
+            t = torch.as_tensor(q).cuda()
+            N.check(N.lib().hdb_query_digest(db._matrix._h, C.c_void_p(t.data_ptr()), {np.float16: 0, np.float32: 1, np.float64: 2}[dt],
+                                             N.HDB_DEVICE, 1, out))
+            assert (int(out[0]), int(out[1])) == query_digest_host(q)
+            q[3] = 0.0
+            assert (int(out[0]), int(out[1])) == query_digest_host(q)
+            host = (C.c_uint64 * 2)()
+            N.check(N.lib().hdb_query_digest(db._matrix._h, C.c_void_p(q.ctypes.data), {np.float16: 0, np.float32: 1, np.float64: 2}[dt],
+                                             N.HDB_HOST, 1, host))
+            assert (int(host[0]), int(host[1])) == query_digest_host(q)
+        # CUDA-tensor query == ndarray query (ids, scores), and they share one cache entry
+        q = rng.standard_normal(d).astype(np.float32)
+        qt = torch.as_tensor(q).cuda()
+        r_host = db.query(q, top_k=7, filters=[("metadata", {"group": "a"})], recency_bias=0.2, timestamp_key="timestamp")
+        assert (db.cache_hits, db.cache_misses) == (0, 1)
+        r_dev = db.query(qt, top_k=7, filters=[("metadata", {"group": "a"})], recency_bias=0.2, timestamp_key="timestamp")
+        assert r_dev is r_host and (db.cache_hits, db.cache_misses) == (1, 1)
+        db.clear_cache()
+        r_dev = db.query(qt, top_k=7, filters=[("metadata", {"group": "a"})], recency_bias=0.2, timestamp_key="timestamp")
+        assert [x[0]["id"] for x in r_dev] == [x[0]["id"] for x in r_host]
+        assert [x[1] for x in r_dev] == [x[1] for x in r_host]
+        # a batch tile on the device: per row what `query` returns (multi-query sweep: 5, 40 = 5 passes of 8, 3 bit-packed)
+        for b, metric in ((5, "manhattan_distance"), (40, "cosine_similarity"), (3, "hamming_distance")):
+            Q = rng.standard_normal((b, d)).astype(np.float32)
+            got = db.query_batch(torch.as_tensor(Q).cuda(), top_k=6, metric=metric, filters=[("skip_doc", 10)])
+            assert len(got) == b
+            for i in range(b):
+                one = db.query(Q[i], top_k=6, metric=metric, filters=[("skip_doc", 10)])
+                assert [x[0]["id"] for x in got[i]] == [x[0]["id"] for x in one], (metric, i)
+                np.testing.assert_allclose([x[1] for x in got[i]], [x[1] for x in one], rtol=1e-12)
+        # texts through the embedding function: its CUDA output tile is the query tile
+        table = {f"text {i}": torch.as_tensor(V[100 + i]).cuda() for i in range(4)}
+        db.embedding_function = lambda texts: torch.stack([table[t] for t in texts])
+        got = db.query_batch(list(table), top_k=1)
+        assert [g[0][0]["id"] for g in got] == [100, 101, 102, 103]
+        assert db.query("text 2", top_k=1)[0][0]["id"] == 102
+    finally:
+        db.close()
+
+
+def test_reference_filter_and_result_semantics():
+    """Behaviours of the reference's brute-force branch the shim mirrors: only the FIRST skip_doc filter
+    acts (hyperdb/hyperdb.py:1474-1481 breaks after it, :1285 skips the rest); a hit resolves its source index through
+    documents.index(document), i.e. the FIRST equal document (:1567); top_k <= 0 raises what max([]) raises (:1558)."""
+    from hyperdb_b200.hyperdb import HyperDB
+    rng = np.random.default_rng(3)
+    V = rng.standard_normal((40, 8)).astype(np.float32)
+    docs = [{"id": i} for i in range(40)]
+    docs[25] = {"id": 7}                                         # equal to documents[7]
+    db = HyperDB(documents=docs, vectors=V)
+    try:
+        res = db.query(V[25], top_k=1)
+        assert res[0][0] == {"id": 7} and res[0][2] == 7          # the row is 25, the reported source index is the first equal document's
+        both = db.query(V[3], top_k=40, filters=[("skip_doc", 5), ("skip_doc", -5)])
+        assert len(both) == 35 and {r[0]["id"] for r in both} >= {38, 39}     # the second skip_doc did nothing
+        with pytest.raises(ValueError, match="empty sequence"):
+            db.query(V[3], top_k=0)
+    finally:
+        db.close()
+
+
+def test_repeated_recency_queries_reuse_device_state():
+    """The row subset and the two-stage decay are only rebuilt when (filters, timestamp_key, recency_bias) change: the second
+    query with the same settings issues no row-wise kernel, and the answers stay those of a fresh store."""
+    from hyperdb_b200 import _native as N
+    from hyperdb_b200.hyperdb import HyperDB
+    rng = np.random.default_rng(9)
+    n, d = 20000, 32
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    docs = [{"id": i, "meta": {"lang": ["en", "fr", "de"][i % 3]}, "timestamp": 1.7e9 + float(rng.uniform(0, 50))} for i in range(n)]
+    kw = dict(top_k=9, filters=[("metadata", {"meta.lang": "fr"}), ("skip_doc", 100)], recency_bias=0.4, timestamp_key="timestamp")
+    db = HyperDB(documents=docs, vectors=V, metadata_keys=["meta.lang", "timestamp"], cache_size=0)
+    try:
+        Q = rng.standard_normal((3, d)).astype(np.float32)
+        first = db.query(Q[0], **kw)
+        N.lib().hdb_launch_count(1)
+        second = db.query(Q[1], **kw)
+        warm_launches = N.lib().hdb_launch_count(0)
+        db.query(Q[1], top_k=9, recency_bias=0.1, timestamp_key="timestamp")      # other settings: state is rebuilt
+        N.lib().hdb_launch_count(1)
+        again = db.query(Q[0], **kw)
+        cold_launches = N.lib().hdb_launch_count(0)
+        assert warm_launches < cold_launches and warm_launches <= 4
+        assert [r[0]["id"] for r in again] == [r[0]["id"] for r in first] and [r[1] for r in again] == [r[1] for r in first]
+        fresh = HyperDB(documents=docs, vectors=V, metadata_keys=["meta.lang", "timestamp"], cache_size=0)
+        ref = fresh.query(Q[1], **kw)
+        fresh.close()
+        assert [r[0]["id"] for r in second] == [r[0]["id"] for r in ref] and [r[1] for r in second] == [r[1] for r in ref]
+        assert all(r[0]["meta"]["lang"] == "fr" and r[0]["id"] >= 100 for r in second)
+    finally:
+        db.close()
+
+
+def _sharded_hyperdb_worker(rank, world, port, out_dir):
+    import os
+    import torch
+    import torch.distributed as dist
+    from hyperdb_b200.hyperdb import HyperDB
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(41)
+    n, d = 30_011, 48
+    V = rng.standard_normal((n, d)).astype(np.float16)
+    V[20_000] = V[5]                                             # a cross-shard tie
+    ts = 1.7e9 + rng.uniform(0, 20, n)
+    docs = [{"id": i, "group": "xyz"[i % 3], "timestamp": float(ts[i])} for i in range(n)]
+    Q = rng.standard_normal((4, d)).astype(np.float16)
+    Q[1] = V[5]
+    single = HyperDB(documents=docs, vectors=V, metadata_keys=["group", "timestamp"], fp_precision="float16", sharded=False, device=0)
+    shard = HyperDB(documents=docs, vectors=V, metadata_keys=["group", "timestamp"], fp_precision="float16", device=0)
+    assert shard._world == world and shard._sm is not None and shard._matrix.shape[0] < n
+    cases = [dict(top_k=10), dict(top_k=10, metric="hamming_distance"), dict(top_k=100, metric="euclidean_metric"),
+             dict(top_k=7, filters=[("metadata", {"group": "y"}), ("skip_doc", -1000)], recency_bias=0.3, timestamp_key="timestamp"),
+             dict(top_k=5, filters=[("skip_doc", 16_000)], metric="manhattan_distance")]
+    for kw in cases:
+        for i in range(len(Q)):
+            a, b = single.query(Q[i], **kw), shard.query(Q[i], **kw)
+            assert [x[0]["id"] for x in a] == [x[0]["id"] for x in b], (kw, i)
+            np.testing.assert_allclose([x[1] for x in a], [x[1] for x in b], rtol=1e-14)
+    clus = HyperDB(documents=docs, vectors=V, metadata_keys=["group", "timestamp"], fp_precision="float16", device=0, cluster_by="group")
+    for kw in cases:
+        a, b = single.query(Q[1], **kw), clus.query(Q[1], **kw)
+        assert [x[0]["id"] for x in a] == [x[0]["id"] for x in b], ("clustered", kw)
+        np.testing.assert_allclose([x[1] for x in a], [x[1] for x in b], rtol=1e-14)
+    dist.barrier()
+    clus.close()
+    got = shard.query_batch(Q, top_k=4, metric="manhattan_distance")
+    for i in range(len(Q)):
+        assert [x[0]["id"] for x in got[i]] == [x[0]["id"] for x in single.query(Q[i], top_k=4, metric="manhattan_distance")]
+    # mutation: the new rows join the last shard, a removal renumbers the shards
+    extra = rng.standard_normal((3, d)).astype(np.float16)
+    for db in (single, shard):
+        db.add([{"id": n + j, "group": "x", "timestamp": 1.7e9} for j in range(3)], vectors=extra)
+        db.remove_document(5)
+    a, b = single.query(Q[1], top_k=6), shard.query(Q[1], top_k=6)
+    assert [x[0]["id"] for x in a] == [x[0]["id"] for x in b] and a[0][0]["id"] == 20_000
+    assert shard.query(extra[2], top_k=1)[0][0]["id"] == n + 2
+    dist.barrier()
+    shard.close()
+    single.close()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def test_sharded_hyperdb_two_processes_one_gpu(tmp_path):
+    """HyperDB over a row-sharded store (`HyperDB.query` on several GPUs): two ranks -- here two
+    processes sharing one GPU, CUDA-IPC peer exchange, gloo for the control plane -- each keep half of the rows and
+    answer every query exactly like the single-shard store: metadata mask, skip_doc range, double recency, wide k, a
+    cross-shard tie, a batch, add and remove_document."""
+    import os
+    import torch.multiprocessing as mp
+    mp.spawn(_sharded_hyperdb_worker, args=(2, 29851 + (os.getpid() % 100), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_cluster_by_layout_is_invisible():
+    """HyperDB(cluster_by=key): documents with equal values of a metadata key are stored next to each other on the device
+    (hdb_matrix_set_row_order) so that a filter on that key keeps contiguous runs of rows; ids, scores, ties and every
+    filter / recency combination must be exactly those of the unclustered store, also after add and remove_document."""
+    from hyperdb_b200.hyperdb import HyperDB
+    rng = np.random.default_rng(77)
+    n, d = 12_000, 40
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    V[9000] = V[30]                                              # equal rows in different clusters: the tie goes to id 30
+    docs = [{"id": i, "cat": int(rng.integers(0, 5)), "timestamp": 1.7e9 + float(rng.uniform(0, 30))} for i in range(n)]
+    docs[9000]["cat"], docs[30]["cat"] = 0, 4
+    plain = HyperDB(documents=docs, vectors=V, metadata_keys=["cat", "timestamp"], cache_size=0)
+    clus = HyperDB(documents=docs, vectors=V, metadata_keys=["cat", "timestamp"], cache_size=0, cluster_by="cat")
+    assert clus._perm is not None
+    try:
+        Q = rng.standard_normal((3, d)).astype(np.float32)
+        Q[1] = V[30]
+        cases = [dict(top_k=8), dict(top_k=8, filters=[("metadata", {"cat": 2})]), dict(top_k=120, metric="euclidean_metric"),
+                 dict(top_k=6, filters=[("metadata", {"cat": 3}), ("skip_doc", 2000)], recency_bias=0.5, timestamp_key="timestamp"),
+                 dict(top_k=5, filters=[("skip_doc", -3000)], metric="hamming_distance"),
+                 dict(top_k=9, metric="manhattan_distance", recency_bias=0.2, timestamp_key="timestamp")]
+
+        def same(kw, q):
+            a, b = plain.query(q, **kw), clus.query(q, **kw)
+            assert [x[0]["id"] for x in a] == [x[0]["id"] for x in b], kw
+            assert [x[1] for x in a] == [x[1] for x in b] and [x[2] for x in a] == [x[2] for x in b]
+        for kw in cases:
+            for q in Q:
+                same(kw, q)
+        got = clus.query_batch(Q, top_k=4, filters=[("metadata", {"cat": 1})])
+        for i in range(len(Q)):
+            assert [x[0]["id"] for x in got[i]] == [x[0]["id"] for x in plain.query(Q[i], top_k=4, filters=[("metadata", {"cat": 1})])]
+        extra = rng.standard_normal((4, d)).astype(np.float32)
+        for db in (plain, clus):
+            db.add([{"id": n + j, "cat": j % 5, "timestamp": 1.7e9 + 40.0} for j in range(4)], vectors=extra)
+            db.remove_document(30)
+        assert clus.size() == n + 3
+        for kw in cases[:4]:
+            for q in Q:
+                same(kw, q)
+        assert clus.query(extra[1], top_k=1)[0][0]["id"] == n + 1
+    finally:
+        plain.close()
+        clus.close()

@@ -378,3 +378,64 @@ def test_batched_tensor_path(hb, metric, nq, sdt):
             assert list(i1[b] - 1000) == list(oi) and np.array_equal(s1[b], os_)
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("vdt", ["f16", "f32", "f64"])
+@pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance",
+                                    "jaccard_similarity", "pearson_correlation"])
+def test_row_order_clustered_storage(hb, vdt, metric):
+    """hdb_matrix_set_row_order: the rows are STORED clustered by a metadata key (here also: in a random order) while ids and
+    ties follow the caller's numbering.  Every answer -- fused sweeps with 1 and 5 queries per pass, the wide candidate
+    class, the exact path, top_k > 100, with mask + time decay, with a row offset -- must equal, bit for bit, the answer of
+    the same rows stored in the caller's order; duplicates across clusters pin the tie rule (lower ORIGINAL index first)."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"ro{vdt}{metric}".encode()))
+    n, d = 20_011, 72
+    dt = {"f16": np.float16, "f32": np.float32, "f64": np.float64}[vdt]
+    V = rng.standard_normal((n, d)).astype(dt)
+    for a, b in ((17, 15_000), (18, 9_001), (19_000, 23)):      # duplicates in different clusters
+        V[b] = V[a]
+    Q = rng.standard_normal((5, d)).astype(dt)
+    Q[1] = V[17]
+    Q[2] = V[23]
+    ts = 1.7e9 + rng.uniform(0, 8, n)
+    keep = rng.random(n) < 0.5
+    cat = rng.integers(0, 6, n)
+    for perm in (np.argsort(cat, kind="stable"), rng.permutation(n)):
+        perm = perm.astype(np.uint32)                            # physical row p holds the caller's row perm[p]
+        ref = hb.DeviceMatrix(V, row_offset=1000)
+        m = hb.DeviceMatrix(np.ascontiguousarray(V[perm]), row_offset=1000)
+        m.set_row_order(perm)
+        try:
+            for (k, use_ts, use_mask, path) in ((10, False, False, 0), (100, False, False, 0), (10, True, True, 0), (10, False, True, 1),
+                                                (150, True, False, 0)):
+                ref.set_mask(keep if use_mask else None)
+                m.set_mask(keep[perm] if use_mask else None)
+                ref.set_timestamps(ts if use_ts else None)
+                m.set_timestamps(ts[perm] if use_ts else None)
+                if use_ts:
+                    ref.refresh_decay()
+                    m.refresh_decay()
+                bias = 0.25 if use_ts else 0.0
+                ref.set_path(path)
+                m.set_path(path)
+                for q in (Q[0], Q[1], Q):
+                    want = ref.query(q, k, metric, bias)
+                    got = m.query(q, k, metric, bias)
+                    assert np.array_equal(got[0], want[0]), (k, use_ts, use_mask, path, np.shape(q))
+                    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+            ref.set_path(0)
+            m.set_path(0)
+            with pytest.raises(Exception):
+                m.append(V[:2])
+            with pytest.raises(Exception):
+                m.set_row_order(np.zeros(n, np.uint32))           # not a permutation
+            m.set_row_order(None)                                 # back to the physical numbering
+            got = m.query(Q[0], 5, metric)
+            ref.set_mask(None); ref.set_timestamps(None)
+            m.set_mask(None); m.set_timestamps(None)
+            want = ref.query(Q[0], 5, metric)
+            assert np.array_equal(np.sort(perm[got[0][0] - 1000].astype(np.int64)), np.sort(want[0][0] - 1000)) or metric in ("hamming_distance", "jaccard_similarity")
+        finally:
+            m.close()
+            ref.close()

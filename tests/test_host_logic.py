@@ -20,6 +20,11 @@ def test_cache_key_is_value_based_and_hashable():
     assert key(q32, 5, True, f1, 0.3, "timestamp", "dot_product", 5) == key(q32, 5, True, f2, 0.3, "timestamp", "dot_product", 5)
     hash(key(q32, 5, True, f1, 0.3, "timestamp", "dot_product", 5))
     assert key("some text", 5, True, None, 0, None, "cosine_similarity", 5)[0] == "some text"
+    # -0.0 and +0.0 are the same tuple element in the reference's key; element order matters; float16 values compare by value
+    z = np.array([0.0, 1.0, -2.0])
+    assert key(z, 5, True, None, 0, None, "dot_product", 5) == key(np.array([-0.0, 1.0, -2.0]), 5, True, None, 0, None, "dot_product", 5)
+    assert key(z, 5, True, None, 0, None, "dot_product", 5) != key(z[::-1].copy(), 5, True, None, 0, None, "dot_product", 5)
+    assert key(z.astype(np.float16), 5, True, None, 0, None, "dot_product", 5) == key(z, 5, True, None, 0, None, "dot_product", 5)
 
 
 def test_step_result_views():
