@@ -121,9 +121,13 @@ def gen_rows_numpy(n, d, dtype, seed=0):
 
 
 def gen_category_torch(lo, hi, device):
+    """category of document i = splitmix64(i) % 8 (int64 arithmetic wraps): reproducible per global id, no visible period"""
     import torch
-    ids = torch.arange(lo, hi, device=device, dtype=torch.int64)
-    return ((ids * 2654435761 + 40503) >> 7) % MASK_CATEGORIES
+    z = torch.arange(lo, hi, device=device, dtype=torch.int64) + 0x1234567
+    z = (z ^ ((z >> 30) & 0x3FFFFFFFF)) * -4658895280553007687          # 0xbf58476d1ce4e5b9
+    z = (z ^ ((z >> 27) & 0x1FFFFFFFFF)) * -7723592293110705685         # 0x94d049bb133111eb
+    z = z ^ ((z >> 31) & 0x1FFFFFFFF)
+    return (z & 0x7FFFFFFF) % MASK_CATEGORIES
 
 
 def gen_keep_torch(lo, hi, device):
@@ -132,8 +136,7 @@ def gen_keep_torch(lo, hi, device):
     documents whose category is in MASK_KEPT (`filters=[('metadata', {'category': [...]})]` in the reference,
     hyperdb/hyperdb.py:1218-1257).  Returns the bool keep column of rows [lo, hi)."""
     import torch
-    ids = torch.arange(lo, hi, device=device, dtype=torch.int64)
-    cat = ((ids * 2654435761 + 40503) >> 7) % MASK_CATEGORIES
+    cat = gen_category_torch(lo, hi, device)
     keep = torch.zeros(hi - lo, dtype=torch.bool, device=device)
     for c in MASK_KEPT:
         keep |= cat == c

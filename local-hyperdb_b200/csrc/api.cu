@@ -41,6 +41,7 @@ struct hdb_matrix {
   uint32_t* mask = nullptr;
   uint32_t* ord = nullptr; uint32_t* inv = nullptr;     // row order (hdb_matrix_set_row_order), both [n] or both null
   int64_t lo = 0, hi = 0, n_kept = 0;
+  int64_t kept_windows = 0;         // 32-row windows with at least one kept row
   double* ts = nullptr;
   double* decay = nullptr;
   bool decay_valid = false;
@@ -130,6 +131,8 @@ static RowFilter filter_of(const hdb_matrix* m, double bias, bool use_decay) {
   f.decay = use_decay ? m->decay : nullptr;
   f.bias = bias;
   f.ord = m->ord; f.inv = m->inv;
+  // at least 3 of 4 rows of the windows that are visited at all are kept
+  f.tile_dense = (m->mask == nullptr) || (m->kept_windows > 0 && m->n_kept * 4 >= m->kept_windows * 32 * 3);
   return f;
 }
 
@@ -158,11 +161,12 @@ static int join_alt(hdb_matrix* m) {
 static int refresh_kept(hdb_matrix* m) {
   HDB_TRY(join_alt(m));
   RowFilter f = filter_of(m, 0.0, false);
-  HDB_TRY(launch_kept_ts_max(nullptr, f, m->n, m->misc, m->misc + 1, m->stream));
-  unsigned long long host[2];
-  HDB_CUDA(cudaMemcpyAsync(host, m->misc, 16, cudaMemcpyDeviceToHost, m->stream));
+  HDB_TRY(launch_kept_ts_max(nullptr, f, m->n, m->misc, m->misc + 1, m->misc + 2, m->stream));
+  unsigned long long host[3];
+  HDB_CUDA(cudaMemcpyAsync(host, m->misc, 24, cudaMemcpyDeviceToHost, m->stream));
   HDB_CUDA(cudaStreamSynchronize(m->stream));
   m->n_kept = (int64_t)host[1];
+  m->kept_windows = (int64_t)host[2];
   return 0;
 }
 
@@ -191,7 +195,7 @@ int hdb_matrix_create(int device, int dtype, int64_t n_rows, int64_t dim, int64_
   m->cap = n_rows;
   m->lo = 0; m->hi = n_rows; m->n_kept = n_rows;
   m->grid = sweep_grid_size(device);
-  int rc = dev_alloc(&m->misc, 2);
+  int rc = dev_alloc(&m->misc, 4);
   if (!rc) rc = dev_alloc(&m->stats, 4);
   if (!rc) rc = dev_alloc(&m->nan_flag, 1);
   if (!rc) rc = dev_alloc(&m->uncertified, 1);
@@ -499,13 +503,14 @@ int hdb_matrix_kept_ts_max(hdb_matrix* m, double* ts_max, int64_t* n_kept) {
   HDB_CUDA(cudaSetDevice(m->device));
   HDB_TRY(join_alt(m));
   RowFilter f = filter_of(m, 0.0, false);
-  HDB_TRY(launch_kept_ts_max(m->ts, f, m->n, m->misc, m->misc + 1, m->stream));
-  unsigned long long host[2];
-  HDB_CUDA(cudaMemcpyAsync(host, m->misc, 16, cudaMemcpyDeviceToHost, m->stream));
+  HDB_TRY(launch_kept_ts_max(m->ts, f, m->n, m->misc, m->misc + 1, m->misc + 2, m->stream));
+  unsigned long long host[3];
+  HDB_CUDA(cudaMemcpyAsync(host, m->misc, 24, cudaMemcpyDeviceToHost, m->stream));
   HDB_CUDA(cudaStreamSynchronize(m->stream));
   if (ts_max) *ts_max = host[1] ? decode_ordered_double(host[0]) : -INFINITY;
   if (n_kept) *n_kept = (int64_t)host[1];
   m->n_kept = (int64_t)host[1];
+  m->kept_windows = (int64_t)host[2];
   return 0;
 }
 
@@ -777,7 +782,7 @@ static int run_fused(hdb_matrix* m, int metric, int rdt, int kp, int64_t b0, int
     const uint32_t* qbits = m->qb.qbits + (size_t)(b0 + i) * m->words;
     const bool prof = m->prof_used + 2 <= m->prof_ev.size();
     if (prof) HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used], sw));
-    HDB_TRY(launch_sweep(v, metric, qa, qbits, m->qb.qaux + 2 * (b0 + i), f, kp, so, g, sw));
+    HDB_TRY(launch_sweep(v, metric, rdt, qa, qbits, m->qb.qaux + 2 * (b0 + i), f, kp, so, g, sw));
     if (prof) { HDB_CUDA(cudaEventRecord(m->prof_ev[m->prof_used + 1], sw)); m->prof_used += 2; }
     i += g;
   }
@@ -1196,7 +1201,7 @@ int hdb_time_last_query(hdb_matrix* m, int what, int iters, float* ms_per_iter) 
       HDB_CUDA(cudaMemsetAsync(m->tau, 0, 8, m->stream));
       SweepOut so; so.cand = m->cand; so.tau = m->tau; so.grid = m->grid;
       (void)elt;
-      HDB_TRY(launch_sweep(v, m->last.metric, m->qb.qa, m->qb.qbits, m->qb.qaux, f, m->last.kp, so, 1, m->stream));
+      HDB_TRY(launch_sweep(v, m->last.metric, m->last.rdt, m->qb.qa, m->qb.qbits, m->qb.qaux, f, m->last.kp, so, 1, m->stream));
     } else {
       HDB_TRY(run_fused(m, m->last.metric, m->last.rdt, m->last.kp, 0, nq, m->last.k, f, m->o_idx, m->o_score, m->o_count,
                         m->o_flags));

@@ -148,6 +148,11 @@ struct hdb_exchange {
   int* d_error = nullptr;                // 1 = a wait timed out (sticky: rebuild the exchange)
   cudaStream_t xs = nullptr;             // wait + merge run here
   bool xs_owned = true;                  // false: a caller-owned stream (hdb_exchange_set_stream)
+  // A push KERNEL (large batches: tensor-core path, chunked sweeps) must have run before this rank's waiters start: a
+  // batch of thousands of queries means thousands of spinning wait CTAs on the high-priority stream, enough to keep the
+  // push kernel off the SMs for good -- every rank then waits for every other rank's push (seen at 8 GPUs, B = 4096).
+  cudaEvent_t ev_push = nullptr;
+  bool push_pending = false;
   bool connected = false;
 };
 
@@ -172,6 +177,9 @@ int exchange_launch_push(hdb_exchange* x, cudaStream_t s, const void* mine, int6
   exchange_push_kernel<<<x->world, 512, 0, s>>>(t, reinterpret_cast<const unsigned long long*>(mine), words);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
+  if (!x->ev_push) HDB_CUDA(cudaEventCreateWithFlags(&x->ev_push, cudaEventDisableTiming));
+  HDB_CUDA(cudaEventRecord(x->ev_push, s));
+  x->push_pending = true;
   return 0;
 }
 int exchange_launch_wait_merge(hdb_exchange* x, cudaStream_t s, int64_t nq, int64_t k, int64_t* out_idx, double* out_score,
@@ -179,6 +187,10 @@ int exchange_launch_wait_merge(hdb_exchange* x, cudaStream_t s, int64_t nq, int6
   PushTarget t;
   HDB_TRY(exchange_push_target(x, nq, k, &t));
   if (nq <= 0 || k < 0 || 2 * nq * k + nq + (nq + 1) / 2 > x->max_words) return fail("hdb_exchange_wait_merge: bad sizes");
+  if (x->push_pending) {                 // the waiters start after this rank's own push kernel (no-op on the push's stream)
+    HDB_CUDA(cudaStreamWaitEvent(s, x->ev_push, 0));
+    x->push_pending = false;
+  }
   exchange_wait_merge_kernel<<<(unsigned)nq, 256, 0, s>>>(t, nq, k, out_idx, out_score, out_count, out_flags);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
@@ -229,6 +241,7 @@ int hdb_exchange_destroy(hdb_exchange* x) {
   for (int g = 0; g < x->world; ++g)
     if (x->ipc_opened[g] && x->peer[g]) cudaIpcCloseMemHandle(x->peer[g]);
   if (x->xs && x->xs_owned) cudaStreamDestroy(x->xs);
+  if (x->ev_push) cudaEventDestroy(x->ev_push);
   if (x->local) cudaFree(x->local);
   if (x->d_peer) cudaFree(x->d_peer);
   if (x->d_ctr) cudaFree(x->d_ctr);

@@ -41,6 +41,9 @@ struct RowFilter {
   // timestamps and every other per-row column are in PHYSICAL order.  nullptr = identity.
   const uint32_t* ord = nullptr;
   const uint32_t* inv = nullptr;
+  // host-side hint: 1 = the subset keeps (nearly) whole 32-row windows -- no mask, or a clustered store -- so kernels that
+  // load whole tiles waste nothing; 0 = a sparse mask (rows are skipped one by one)
+  int tile_dense = 1;
 };
 
 // ---- peer-memory exchange (exchange.cu): what a pushing kernel needs to know
@@ -100,7 +103,7 @@ int launch_plan_removal(int64_t n, const int64_t* d_rows, int64_t count, uint32_
 int launch_compact_column(void* column, int64_t row_bytes, int64_t n_new, const uint32_t* src, void* bounce, size_t bounce_bytes,
                           cudaStream_t s);
 int launch_kept_ts_max(const double* ts, const RowFilter& f, int64_t n, unsigned long long* d_max_bits,
-                       unsigned long long* d_count, cudaStream_t s);
+                       unsigned long long* d_count, unsigned long long* d_windows /*may be null*/, cudaStream_t s);
 int launch_decay(const double* ts, double* decay, int64_t n, double ts_max, cudaStream_t s);
 int launch_stage1(double* ts, int64_t n, double bias1, double ts_max, cudaStream_t s);
 int launch_prep_query(const void* q, int q_dtype, int64_t nq, int64_t d, int metric, int sdt, int words,
@@ -123,8 +126,8 @@ int sweep_grid_size(int device);
 int sweep_max_group(const MatrixView& m, int metric, int kp);
 // qa / qbits / qaux point at the FIRST query of the group; consecutive queries are d accumulate-type elements, `words`
 // sign-bit words and 2 doubles apart (the layout prep_query writes)
-int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const double* qaux /*pearson*/,
-                 const RowFilter& f, int kp, const SweepOut& out, int nq, cudaStream_t s);
+int launch_sweep(const MatrixView& m, int metric, int rdt /*result dtype = max(storage, query)*/, const void* qa, const uint32_t* qbits,
+                 const double* qaux /*pearson*/, const RowFilter& f, int kp, const SweepOut& out, int nq, cudaStream_t s);
 
 // ---- finalize.cu : merge + canonical re-score + certification; exact full-vector path
 struct FinalizeArgs {

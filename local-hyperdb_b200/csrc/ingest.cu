@@ -193,13 +193,21 @@ __device__ __forceinline__ bool row_kept(const RowFilter& f, int64_t row) {
 }
 
 __global__ void kept_ts_max_kernel(const double* ts, RowFilter f, int64_t n, unsigned long long* max_bits,
-                                   unsigned long long* count) {
-  unsigned long long best = 0, cnt = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if (row_kept(f, i)) {
+                                   unsigned long long* count, unsigned long long* windows) {
+  // a warp visits whole 32-row windows (one mask word): kept rows, their newest timestamp, and the number of windows that
+  // keep at least one row (how tile-dense the subset is: the staged sweep loads whole tiles)
+  unsigned long long best = 0, cnt = 0, win = 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const int64_t i = base + lane;
+    const bool kept = i < n && row_kept(f, i);
+    if (kept) {
       ++cnt;
       if (ts) { unsigned long long o = order_f64(ts[i]); best = o > best ? o : best; }
     }
+    if (__any_sync(kFull, kept) && lane == 0) ++win;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
@@ -207,20 +215,22 @@ __global__ void kept_ts_max_kernel(const double* ts, RowFilter f, int64_t n, uns
     best = b2 > best ? b2 : best;
     cnt += __shfl_xor_sync(kFull, cnt, o);
   }
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     if (best) atomicMax(max_bits, best);
     if (cnt) atomicAdd(count, cnt);
+    if (win && windows) atomicAdd(windows, win);
   }
 }
 
 int launch_kept_ts_max(const double* ts, const RowFilter& f, int64_t n, unsigned long long* d_max_bits,
-                       unsigned long long* d_count, cudaStream_t s) {
+                       unsigned long long* d_count, unsigned long long* d_windows, cudaStream_t s) {
   HDB_CUDA(cudaMemsetAsync(d_max_bits, 0, 8, s));
   HDB_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+  if (d_windows) HDB_CUDA(cudaMemsetAsync(d_windows, 0, 8, s));
   if (n == 0) return 0;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  kept_ts_max_kernel<<<(unsigned)blocks, 256, 0, s>>>(ts, f, n, d_max_bits, d_count);
+  kept_ts_max_kernel<<<(unsigned)blocks, 256, 0, s>>>(ts, f, n, d_max_bits, d_count, d_windows);
   HDB_LAUNCHED();
   HDB_CUDA(cudaGetLastError());
   return 0;

@@ -16,6 +16,8 @@
 
 namespace hdb {
 
+constexpr int kStagedDefaultLimit = 1024;
+
 // the 18 (storage type, metric class, candidate class) instantiations of csrc/sweep_inst.cu
 #define HDB_DECL_SWEEP(name) \
   int name##_kp32(const SweepParams& p, bool vec, int nq, int grid, size_t smem, cudaStream_t s); \
@@ -24,6 +26,21 @@ HDB_DECL_SWEEP(sweep_f16_mc0); HDB_DECL_SWEEP(sweep_f16_mc1); HDB_DECL_SWEEP(swe
 HDB_DECL_SWEEP(sweep_f32_mc0); HDB_DECL_SWEEP(sweep_f32_mc1); HDB_DECL_SWEEP(sweep_f32_mc2);
 HDB_DECL_SWEEP(sweep_f64_mc0); HDB_DECL_SWEEP(sweep_f64_mc1); HDB_DECL_SWEEP(sweep_f64_mc2);
 #undef HDB_DECL_SWEEP
+// the six instantiations of csrc/sweep_staged_inst.cu (TMA-staged row tiles, one query per pass)
+#define HDB_DECL_STAGED(name) int name(const SweepParams& p, int kp, int grid, cudaStream_t s)
+HDB_DECL_STAGED(staged_f16_mc0); HDB_DECL_STAGED(staged_f16_mc1); HDB_DECL_STAGED(staged_f16_mc2);
+HDB_DECL_STAGED(staged_f32_mc0); HDB_DECL_STAGED(staged_f32_mc1); HDB_DECL_STAGED(staged_f32_mc2);
+#undef HDB_DECL_STAGED
+
+// Which single-query passes take the TMA-staged kernel: rows of at most `limit` bytes whose subset is tile-dense.
+// HDB_SWEEP_STAGED (A/B switch): 0 = never, N > 0 = rows of at most N bytes.  Default: see DESIGN.md section 4.1b.
+static int64_t staged_row_limit() {
+  static const int64_t limit = [] {
+    const char* e = getenv("HDB_SWEEP_STAGED");
+    return e ? (int64_t)atoll(e) : (int64_t)kStagedDefaultLimit;
+  }();
+  return limit;
+}
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -65,8 +82,8 @@ int sweep_max_group(const MatrixView& m, int metric, int kp) {
   return best;
 }
 
-int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t* qbits, const double* qaux, const RowFilter& f, int kp,
-                 const SweepOut& out, int nq, cudaStream_t s) {
+int launch_sweep(const MatrixView& m, int metric, int rdt, const void* qa, const uint32_t* qbits, const double* qaux, const RowFilter& f,
+                 int kp, const SweepOut& out, int nq, cudaStream_t s) {
   if (nq != 1 && nq != 2 && nq != 4 && nq != 8) return fail("sweep: a pass takes 1, 2, 4 or 8 queries");
   if (nq > sweep_max_group(m, metric, kp)) return fail("sweep: query group too large for this shape");
   if (m.n >= (int64_t(1) << 32)) return fail("sweep: more than 2^32 rows per shard");
@@ -84,10 +101,19 @@ int launch_sweep(const MatrixView& m, int metric, const void* qa, const uint32_t
   p.qaux = (metric == HDB_PEARSON) ? qaux : nullptr;
   if (metric == HDB_PEARSON && (!m.pscale || !m.pmean || !qaux)) return fail("sweep: pearson columns missing");
   p.f = f; p.cand = out.cand; p.tau = out.tau; p.metric = metric;
+  // result dtype float16 <=> rows and queries are float16: the prepared query values are float16 numbers
+  static const bool no_fhfma = getenv("HDB_NO_FHFMA") != nullptr;          // A/B switch
+  p.q_half = (m.dtype == 0 && rdt == 0 && !no_fhfma) ? 1 : 0;
   p.cand_stride = (int64_t)out.grid * kp;
   const int mc = (metric == HDB_DOT || metric == HDB_COSINE || metric == HDB_PEARSON) ? 0 : (metric == HDB_EUCLIDEAN ? 1 : 2);
   const size_t smem = float_sweep_smem(m, kp, nq, vec);
   if (smem > 200 * 1024) return fail("sweep: dimension too large for the fused pass");
+  if (nq == 1 && m.dtype != 2 && vec && f.tile_dense && p.row_bytes <= staged_row_limit() && p.row_bytes <= 4096 &&
+      (reinterpret_cast<uintptr_t>(m.rows) & 15) == 0 && m.n >= 4096) {
+    typedef int (*SFn)(const SweepParams&, int, int, cudaStream_t);
+    static const SFn staged[2][3] = {{staged_f16_mc0, staged_f16_mc1, staged_f16_mc2}, {staged_f32_mc0, staged_f32_mc1, staged_f32_mc2}};
+    return staged[m.dtype][mc](p, kp, out.grid, s);
+  }
   typedef int (*Fn)(const SweepParams&, bool, int, int, size_t, cudaStream_t);
 #define HDB_PAIR(name) {name##_kp32, name##_kp128}
   static const Fn table[3][3][2] = {{HDB_PAIR(sweep_f16_mc0), HDB_PAIR(sweep_f16_mc1), HDB_PAIR(sweep_f16_mc2)},

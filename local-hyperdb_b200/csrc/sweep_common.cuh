@@ -25,6 +25,9 @@ struct SweepParams {
   const double* qaux;       // pearson: {np.std(q), sum_j (q_j - mean)} of this query, else nullptr
   RowFilter f;
   uint64_t* cand;
+  // 1: float16 rows AND float16 queries on the dot / cosine / pearson class: the prepared query values are float16 numbers,
+  // so the sweep keeps them as float16 in shared memory and multiplies with the mixed-precision FMA (see accum_hh)
+  int q_half;
   unsigned long long* tau;  // [NQ] running thresholds of the queries of this pass
   int64_t cand_stride;      // keys between the candidate blocks of consecutive queries (grid * KP)
   int metric;
@@ -69,6 +72,19 @@ __device__ __forceinline__ void accum_vec(double& a, const uint4& raw, const dou
   const double* v = reinterpret_cast<const double*>(&raw);
 #pragma unroll
   for (int i = 0; i < 2; ++i) accum<MC, double>(a, v[i], q[i]);
+}
+
+// float16 x float16 + float32 -> float32 in ONE instruction (PTX fma.rn.f32.f16, SASS FHFMA with .H0/.H1 operand selectors):
+// the product of two float16 numbers is exact in float32, so this is bit-for-bit fmaf(float(v), float(q), a) without the two
+// conversions -- the instruction count of the float16 dot sweep halves.  8 elements of a stored vector against 8 query
+// elements, in element order.
+__device__ __forceinline__ void accum_hh(float& a, const uint4& v, const uint4& q) {
+  asm("{\n\t.reg .b16 vl, vh, ql, qh;\n\t"
+      "mov.b32 {vl, vh}, %1;\n\tmov.b32 {ql, qh}, %5;\n\tfma.rn.f32.f16 %0, vl, ql, %0;\n\tfma.rn.f32.f16 %0, vh, qh, %0;\n\t"
+      "mov.b32 {vl, vh}, %2;\n\tmov.b32 {ql, qh}, %6;\n\tfma.rn.f32.f16 %0, vl, ql, %0;\n\tfma.rn.f32.f16 %0, vh, qh, %0;\n\t"
+      "mov.b32 {vl, vh}, %3;\n\tmov.b32 {ql, qh}, %7;\n\tfma.rn.f32.f16 %0, vl, ql, %0;\n\tfma.rn.f32.f16 %0, vh, qh, %0;\n\t"
+      "mov.b32 {vl, vh}, %4;\n\tmov.b32 {ql, qh}, %8;\n\tfma.rn.f32.f16 %0, vl, ql, %0;\n\tfma.rn.f32.f16 %0, vh, qh, %0;\n\t}"
+      : "+f"(a) : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w));
 }
 
 // 8 per-lane partial sums -> every lane holds the full sum of row ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)

@@ -1,6 +1,7 @@
 // The streaming sweep over float16 / float32 / float64 rows: NQ queries per pass.  Included by csrc/sweep_inst.cu, which
 // the Makefile compiles once per (storage type, metric class) so that the instantiations build in parallel.
 #pragma once
+#include <type_traits>
 #include "sweep_common.cuh"
 
 namespace hdb {
@@ -171,7 +172,18 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
   if (threadIdx.x < NQ) s_tau[threadIdx.x] = 0;
   // Query tile.  VEC with several queries: piece-major so that the 32 lanes of a warp read 32 CONSECUTIVE 16-byte pieces (conflict-free
   // LDS.128): piece p = e4 * NQ + j of column step `st` for lane l sits at ((st * NP + p) * 32 + l).  Scalar path: [NQ][d].
-  if (VEC && NQ > 1) {
+  constexpr bool kHalfDot = std::is_same<T, __half>::value && MC == 0 && VEC;
+  const bool qh = kHalfDot && p.q_half != 0;                 // float16 query tile + mixed-precision FMA (accum_hh)
+  if (qh) {
+    // [step][query][lane] pieces of 8 float16 values (one stored vector's worth): conflict-free LDS.128, one per 8 elements
+    __half* s_qh = reinterpret_cast<__half*>(s_q);
+    const int steps = (p.nvec + 31) / 32;
+    for (int i = threadIdx.x; i < steps * NQ * 32 * 8; i += kSweepThreads) {
+      const int t = i % 8, l = (i / 8) % 32, j = (i / 256) % NQ, st = i / (256 * NQ);
+      const int c = st * 32 + l;
+      s_qh[i] = (c < p.nvec) ? __float2half_rn((float)reinterpret_cast<const Acc*>(p.qa)[(int64_t)j * p.d + (int64_t)c * 8 + t]) : __float2half_rn(0.f);
+    }
+  } else if (VEC && NQ > 1) {
     const int steps = (p.nvec + 31) / 32;
     constexpr int kPE = PieceOf<Acc>::kElems;
     for (int i = threadIdx.x; i < steps * NP * 32 * kPE; i += kSweepThreads) {
@@ -278,6 +290,18 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
           }
         };
         auto compute = [&](const uint4 (&src)[R], int step) {
+          if (qh) {
+            const uint4* qp = reinterpret_cast<const uint4*>(s_q) + (size_t)step * NQ * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+              const uint4 q = qp[j * 32];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                if constexpr (kHalfDot) accum_hh(acc[j * R + r], src[r], q);
+              }
+            }
+            return;
+          }
           const Piece* qp = s_q4 + (size_t)step * NP * 32 + lane;
 #pragma unroll
           for (int e4 = 0; e4 < kE4; ++e4) {
@@ -302,6 +326,23 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
           for (int r = 0; r < R; ++r) rp[r] += 1024;
         }
         if (st < nsteps) compute(b0, st);
+      } else if (VEC && NQ == 1 && qh) {
+        // one float16 query against float16 rows: 8 mixed-precision FMAs per 16-byte vector, no conversions
+        const uint4* s_qv = reinterpret_cast<const uint4*>(s_q);
+#pragma unroll 2
+        for (int c = lane; c < p.nvec; c += 32) {
+          uint4 raw[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if ((keep >> r) & 1u) raw[r] = ld_stream16(base + (ro[r] + (uint32_t)c * 16u));
+            else raw[r] = make_uint4(0, 0, 0, 0);
+          }
+          const uint4 q = s_qv[c];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if constexpr (kHalfDot) accum_hh(acc[r], raw[r], q);
+          }
+        }
       } else if (VEC && NQ == 1) {
         // one query: plain [d] query tile, two column steps (16 independent 16-byte loads per lane) in flight
 #pragma unroll 2
@@ -327,6 +368,18 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_kernel(SweepParams p) 
           for (int r = 0; r < R; ++r) {
             if ((keep >> r) & 1u) raw[r] = ld_stream16(base + (ro[r] + (uint32_t)c * 16u));
             else raw[r] = make_uint4(0, 0, 0, 0);
+          }
+          if (qh) {
+            const uint4* qv = reinterpret_cast<const uint4*>(s_q) + (size_t)st * NQ * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+              const uint4 q = qv[j * 32];
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                if constexpr (kHalfDot) accum_hh(acc[j * R + r], raw[r], q);
+              }
+            }
+            continue;
           }
           const Piece* qp = s_q4 + (size_t)st * NP * 32 + lane;
 #pragma unroll

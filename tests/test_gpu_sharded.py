@@ -353,3 +353,58 @@ def test_submit_collect_single_gpu():
         sm.engine.enable_pipeline(False)
     finally:
         m.close()
+
+
+def _one_gpu_large_batch_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    import hyperdb_b200 as hb
+    from hyperdb_b200 import _native as N
+    from hyperdb_b200.sharded import CudaEngine, ShardedMatrix, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(29)
+    n, d, b = 1_200_000, 64, 2048                                  # shards of 600k rows: the tensor-core batched path
+    V = rng.standard_normal((n, d)).astype(np.float16)
+    Q = rng.standard_normal((b, d)).astype(np.float16)
+    Q[7] = V[900_123]
+    lo, hi = shard_bounds(n, world, rank)
+    m = hb.DeviceMatrix(V[lo:hi], device=0, row_offset=lo)
+    sm = ShardedMatrix(CudaEngine(m), n)
+    assert sm.enable_peer_exchange(max_batch=b, max_k=10) is True
+    # device-resident: thousands of wait CTAs per step must not keep this rank's own push kernel off the SMs
+    qd = torch.as_tensor(Q).cuda()
+    for _ in range(3):
+        idx, sc, cnt, flags = sm.query_async(qd, 10, "cosine_similarity")
+        sm.wait_results()
+        torch.cuda.synchronize()
+        assert not sm.xchg.error()
+        assert (flags.cpu().numpy() & N.FLAG_TENSOR).all() and not (flags.cpu().numpy() & N.FLAG_EXCHANGE_ERROR).any()
+    # host API (submit / collect repairs the few uncertified queries by itself)
+    idx, sc, cnt = sm.query(Q, 10, "cosine_similarity")
+    assert idx[7, 0] == 900_123
+    for qi in (0, 7, 513, 2047):
+        oi, os_ = K.rank(V, Q[qi], 10, "cosine_similarity")
+        assert list(idx[qi]) == list(oi), qi
+        assert np.array_equal(sc[qi], os_)
+    # a chunked sweep batch (manhattan: no tensor form) through the push kernel as well
+    idx, sc, cnt = sm.query(Q[:130], 10, "manhattan_distance")
+    oi, os_ = K.rank(V, Q[129], 10, "manhattan_distance")
+    assert list(idx[129]) == list(oi) and np.array_equal(sc[129], os_)
+    dist.barrier()
+    sm.xchg.close()
+    m.close()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def test_two_processes_large_batch_exchange(tmp_path):
+    """Round 2's 8-GPU run lost every B = 4096 step to the exchange's 10 s timeout: 4096 spinning wait CTAs on the
+    high-priority stream kept the rank's own push kernel off the SMs, on every rank at once.  The waiters are now ordered
+    after the local push kernel; this drives a 2048-query batch through the tensor-core path and the push kernel with two
+    ranks sharing ONE GPU (CUDA IPC), where the same starvation would hang both."""
+    import torch.multiprocessing as mp
+    mp.spawn(_one_gpu_large_batch_worker, args=(2, 29941 + (os.getpid() % 100), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
