@@ -18,8 +18,9 @@ north_star's roofline target is quoted on (10M x 768 fp16, cosine top-10, single
             bounded row subsample (median of 3), scaled linearly to the full row count
   parity_check   outside the timed region: two planted queries (a stored row must come back first) and one
             random query checked against an independent chunked torch fp32 scoring of every shard
-  extra     short passes of the other BASELINE.json configurations (batched tensor-core path, bit-packed
-            hamming, the multi-query sweep), each with its own e2e and roofline
+  extra     short passes of the other BASELINE.json configurations (batched tensor-core path f16 / tf32, bit-packed
+            hamming, the multi-query sweep, the 100M-row masked + decayed config C4 plain and clustered), each with its own
+            e2e and roofline
 N > 1 (torchrun): the matrix is row-sharded (strong scaling), one exchange of candidates per step.
 `--impl reference` times the reference's CPU path (the NumPy port; the reference is pure Python and
 /root/reference does not travel to the GPU box) on the same workload.
@@ -69,7 +70,8 @@ WORKLOADS = {
                                          decay=True, mask=True, cluster=True),
 }
 # the short passes attached to the default line as "extra" (same matrix as the headline first, then config C5's)
-EXTRAS = ["c3_cosine_b8", "c3_cosine_b64", "c3_cosine_b4096", "c5_hamming_b1", "c5_manhattan_b8"]
+EXTRAS = ["c3_cosine_b8", "c3_cosine_b64", "c3_cosine_b4096", "c5_hamming_b1", "c5_manhattan_b8", "c2_cosine_b1024",
+          "c4_decay_mask_k100", "c4_decay_mask_k100_clustered"]
 CHUNK = 262_144          # rows per generator chunk: chunk c of the GLOBAL matrix is seeded with (seed, c)
 ITEM = {"float16": 2, "float32": 4, "float64": 8}
 # metadata of the synthetic documents (config C4): one category per row, the filter keeps 4 of the 8 categories
@@ -716,8 +718,6 @@ def main():
     extras = []
     if args.extras == "all" or (args.extras == "auto" and args.workload == "c3_cosine_b1" and not args.rows):
         extras = list(EXTRAS)
-        if world == 8 or args.extras == "all":
-            extras += ["c4_decay_mask_k100", "c4_decay_mask_k100_clustered"]
     same = [e for e in extras if (WORKLOADS[e]["n"], WORKLOADS[e]["d"], WORKLOADS[e]["dtype"]) == (w["n"], w["d"], w["dtype"])]
     max_b = max([w["b"]] + [WORKLOADS[e]["b"] for e in same])
     max_k = max([w["k"]] + [WORKLOADS[e]["k"] for e in same])

@@ -114,19 +114,29 @@ __global__ void __launch_bounds__(kStagedThreads, 2) sweep_staged_kernel(SweepPa
   const bool simple = p.f.mask == nullptr && p.f.lo <= 0 && p.f.hi >= p.n;
   const uint32_t all_rows = TR == 32 ? 0xffffffffu : ((1u << TR) - 1u);
   if (warp == kSweepWarps) {
-    // ---- producer: one lane walks this CTA's tiles and keeps the ring full
-    if (lane == 0) {
-      int s = 0;
-      uint32_t wait_parity = 1;            // a fresh mbarrier passes a wait on parity 1: the first round finds every slot free
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        if (!simple && tile_keep_bits<TR>(p.f, t, p.n) == 0) continue;
-        st_mbar_wait(&s_empty[s], wait_parity);
-        const int64_t row0 = t * TR;
-        const uint32_t bytes = (t == ntiles - 1) ? (uint32_t)((p.n - row0) * p.row_bytes) : tile_bytes;
-        st_mbar_expect_tx(&s_full[s], bytes);
-        st_bulk_load(s_stage + (size_t)s * geo.stage_bytes, p.rows + row0 * p.row_bytes, bytes, &s_full[s]);
-        if (++s == geo.stages) { s = 0; wait_parity ^= 1u; }
+    // ---- producer: the warp fetches the keep bits of 32 of this CTA's tiles at once (one per lane: with a mask every word
+    //      is a global load, and a chain of one load per tile would pace the ring), then one lane issues the non-empty ones
+    int s = 0;
+    uint32_t wait_parity = 1;              // a fresh mbarrier passes a wait on parity 1: the first round finds every slot free
+    for (int64_t t0 = blockIdx.x; t0 < ntiles; t0 += 32 * (int64_t)gridDim.x) {
+      const int64_t tl = t0 + (int64_t)lane * gridDim.x;
+      uint32_t mybits = 0;
+      if (tl < ntiles) mybits = (simple && tl != ntiles - 1) ? all_rows : tile_keep_bits<TR>(p.f, tl, p.n);
+      unsigned nonempty = __ballot_sync(kFull, mybits != 0);
+      if (lane == 0) {
+        while (nonempty) {
+          const int j = __ffs(nonempty) - 1;
+          nonempty &= nonempty - 1;
+          const int64_t t = t0 + (int64_t)j * gridDim.x;
+          st_mbar_wait(&s_empty[s], wait_parity);
+          const int64_t row0 = t * TR;
+          const uint32_t bytes = (t == ntiles - 1) ? (uint32_t)((p.n - row0) * p.row_bytes) : tile_bytes;
+          st_mbar_expect_tx(&s_full[s], bytes);
+          st_bulk_load(s_stage + (size_t)s * geo.stage_bytes, p.rows + row0 * p.row_bytes, bytes, &s_full[s]);
+          if (++s == geo.stages) { s = 0; wait_parity ^= 1u; }
+        }
       }
+      __syncwarp();
     }
   } else {
     // ---- consumers
@@ -147,15 +157,17 @@ __global__ void __launch_bounds__(kStagedThreads, 2) sweep_staged_kernel(SweepPa
     uint32_t parity = 0;
     const uint32_t my_rows_off = (uint32_t)(warp * RPW) * (uint32_t)p.row_bytes;
     const int my_local = warp * RPW + my_v;
-    uint32_t next_bits = simple ? all_rows : ((blockIdx.x < ntiles) ? tile_keep_bits<TR>(p.f, blockIdx.x, p.n) : 0u);
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      uint32_t bits = next_bits;
-      if (simple) {
-        if (t == ntiles - 1) bits = tile_keep_bits<TR>(p.f, t, p.n);
-      } else {
-        next_bits = (t + gridDim.x < ntiles) ? tile_keep_bits<TR>(p.f, t + gridDim.x, p.n) : 0u;
-        if (bits == 0) continue;
-      }
+    // the keep bits of 32 tiles at once (one per lane), then the non-empty ones in order: an empty tile costs nothing
+    for (int64_t t0 = blockIdx.x; t0 < ntiles; t0 += 32 * (int64_t)gridDim.x) {
+      const int64_t tl = t0 + (int64_t)lane * gridDim.x;
+      uint32_t mybits = 0;
+      if (tl < ntiles) mybits = (simple && tl != ntiles - 1) ? all_rows : tile_keep_bits<TR>(p.f, tl, p.n);
+      unsigned nonempty = __ballot_sync(kFull, mybits != 0);
+      while (nonempty) {
+      const int jt = __ffs(nonempty) - 1;
+      nonempty &= nonempty - 1;
+      const uint32_t bits = __shfl_sync(kFull, mybits, jt);
+      const int64_t t = t0 + (int64_t)jt * gridDim.x;
       const int cur = s;
       const uint32_t cur_parity = parity;
       if (++s == geo.stages) { s = 0; parity ^= 1u; }
@@ -225,6 +237,7 @@ __global__ void __launch_bounds__(kStagedThreads, 2) sweep_staged_kernel(SweepPa
       }
       const uint64_t key = ordered_key(p.f, score, (uint32_t)mrow, rep && mine_kept, wl.tau);
       wl.push(rep && mine_kept && key > wl.tau, key, lane, s_tau, p.tau);
+      }
     }
     // every warp's list sorted, at most KP valid entries, zeros after
     wl.compact(lane, s_tau, p.tau);
