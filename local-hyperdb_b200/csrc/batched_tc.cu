@@ -708,7 +708,7 @@ int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t n
   if (m.dtype == 2) return 0;                                  // no fp64 tensor path
   if (q_dtype > m.dtype) return 0;                             // the B operand has the storage precision: exact only then
   if ((m.d * dtype_size(m.dtype)) % 16 != 0 || (reinterpret_cast<uintptr_t>(m.rows) & 15)) return 0;
-  if (m.n < 8 * 65536 || nq < 2) return 0;                     // one query, or a small shard: the streaming sweep
+  if (m.n < 65536 || nq < 2) return 0;                         // one query, or a tiny shard (sample = n / 8 rows < 8192): the streaming sweep
   if (m.n >= (int64_t(1) << 31)) return 0;
   return 1;
 }

@@ -4,7 +4,7 @@
 set -u
 OUT=${1:-gpurun_out/r02/prof}
 mkdir -p $OUT
-B="python bench.py --no-cpu-baseline"
+B="python bench.py --no-cpu-baseline --extras none"
 KERN='regex:sweep|finalize|prep_query|merge|batched_tc|bucket_records|sample_threshold|queries_to_half|exchange'
 run_plain() { # workload steps
   $B --workload $1 --steps $2 --warmup 3 > $OUT/plain_$1.json 2> $OUT/plain_$1.err
@@ -19,6 +19,7 @@ full() { # workload kernel-regex skip tag
 }
 run_plain c3_cosine_b1 5 && launch_list c3_cosine_b1 5 120 && full c3_cosine_b1 'sweep_kernel' 4 sweep_c3
 run_plain c5_hamming_b1 5 && launch_list c5_hamming_b1 5 120 && full c5_hamming_b1 'sweep_hamming' 4 ham_c5
-run_plain c3_cosine_b4096 3 && launch_list c3_cosine_b4096 3 60 && full c3_cosine_b4096 'batched_tc_pair' 2 pair_b4096
+run_plain c4_decay_mask_k100_clustered 3 && launch_list c4_decay_mask_k100_clustered 3 60 && full c4_decay_mask_k100_clustered 'sweep_staged' 3 staged_c4
+run_plain c5_manhattan_b8 3 && launch_list c5_manhattan_b8 3 60
 run_plain c3_cosine_b64 3 && full c3_cosine_b64 'batched_tc_kernel' 5 tc_b64
 ls -la $OUT
