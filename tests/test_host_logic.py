@@ -107,3 +107,60 @@ def test_builtin_lru_evicts_least_recently_used():
     off, _ = _shim_without_gpu(cache_size=0)
     off.query(q[0]); off.query(q[0])
     assert len(off.lru_cache) == 0 and off.cache_hits == 0
+
+
+def test_bench_mask_helpers():
+    """bench.py's synthetic metadata: categories are reproducible per global id and uniform; the packed keep bits are NumPy's
+    little-endian packbits (bit i of word i/32 = row i, the layout hdb_matrix_set_mask documents)."""
+    import torch
+    import bench
+    cat = bench.gen_category_torch(1000, 201_000, "cpu")
+    assert cat.min() >= 0 and cat.max() < bench.MASK_CATEGORIES
+    counts = torch.bincount(cat, minlength=bench.MASK_CATEGORIES).double()
+    assert (counts / counts.sum() - 1.0 / bench.MASK_CATEGORIES).abs().max() < 0.01
+    assert torch.equal(cat[500:700], bench.gen_category_torch(1500, 1700, "cpu"))      # a shard sees the same documents
+    keep = bench.gen_keep_torch(0, 100_003, "cpu")
+    assert abs(keep.double().mean().item() - len(bench.MASK_KEPT) / bench.MASK_CATEGORIES) < 0.01
+    bits = bench.pack_keep_bits(keep).numpy().view(np.uint32)
+    want = np.packbits(keep.numpy(), bitorder="little")
+    want = np.concatenate([want, np.zeros((-len(want)) % 4, np.uint8)]).view(np.uint32)
+    assert np.array_equal(bits, want)
+
+
+def test_shim_filter_semantics_without_gpu():
+    """hyperdb/hyperdb.py:1474-1481 applies only the FIRST skip_doc filter; metadata filters intersect; the subset tag is
+    stable under dict order (it keys the device-side subset / decay cache)."""
+    db, _ = _shim_without_gpu()
+    db.documents = [{"id": i, "g": "ab"[i % 2], "h": i % 3} for i in range(12)]
+    db.metadata_keys = ["g", "h"]
+    db._invalidate_columns()
+    lo, hi, keep, tag = db._apply_filters([("skip_doc", 2), ("skip_doc", -3)])
+    assert (lo, hi, keep) == (2, 12, None)
+    lo, hi, keep, tag = db._apply_filters([("skip_doc", -3), ("metadata", {"g": "a"}), ("metadata", {"h": 0})])
+    assert (lo, hi) == (0, 9) and list(np.flatnonzero(keep)) == [0, 6]
+    assert tag == db._apply_filters([("skip_doc", -3), ("metadata", {"g": "a"}), ("metadata", {"h": 0})])[3]
+    assert db._apply_filters([("metadata", {"g": "a", "h": 0})])[3] == db._apply_filters([("metadata", {"h": 0, "g": "a"})])[3]
+    import pytest
+    with pytest.raises(Exception):
+        db._apply_filters([("skip_doc", 12)])
+    with pytest.raises(ValueError):
+        db._apply_filters([("metadata", {"missing": 1})])
+    with pytest.raises(ValueError):
+        db._apply_filters([("nope", 1)])
+    # documents.index semantics: the first EQUAL document, whatever the dict order
+    db.documents[7] = {"h": 1, "g": "b", "id": 1}
+    db._invalidate_columns()
+    assert db._first_index(7) == 1 and db._first_index(8) == 8
+
+
+def test_shim_host_copy_is_lazy():
+    """`HyperDB.vectors` (the attribute the reference exposes) is concatenated only when somebody reads it: an `add` appends
+    a chunk instead of copying the whole matrix (hyperdb/hyperdb.py:504-509 does np.concatenate per call)."""
+    db, _ = _shim_without_gpu()
+    a, b = np.ones((3, 4), np.float32), np.zeros((2, 4), np.float32)
+    db._chunks = [a, b]
+    assert len(db._chunks) == 2
+    v = db.vectors
+    assert v.shape == (5, 4) and len(db._chunks) == 1 and np.array_equal(v[:3], a)
+    db.vectors = None
+    assert db.vectors is None and db._n == 0
