@@ -408,3 +408,41 @@ def test_two_processes_large_batch_exchange(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_one_gpu_large_batch_worker, args=(2, 29941 + (os.getpid() % 100), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_collect_repairs_only_uncertified_queries():
+    """submit / collect: a query whose certificate cannot hold (200 identical rows tie with everything outside the
+    candidate list, also for the wide class) is repeated ALONE -- wide class, then the exact path -- and patched into the
+    batch; the other queries of the batch are not run again.  Ties resolve to the lowest row ids."""
+    import hyperdb_b200 as hb
+    from hyperdb_b200 import _native as N
+    from hyperdb_b200.sharded import CudaEngine, ShardedMatrix
+    rng = np.random.default_rng(77)
+    n, d = 60_000, 64
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    dup = np.sort(rng.choice(n, size=200, replace=False))
+    V[dup] = V[dup[0]]
+    Q = rng.standard_normal((6, d)).astype(np.float32)
+    Q[2] = V[dup[0]]
+    m = hb.DeviceMatrix(V)
+    sm = ShardedMatrix(CudaEngine(m), n)
+    try:
+        for metric in ("euclidean_metric", "manhattan_distance", "cosine_similarity"):
+            N.lib().hdb_launch_count(1)
+            idx, sc, cnt = sm.collect(sm.submit(Q, 10, metric))
+            with_repair = N.lib().hdb_launch_count(0)
+            assert list(idx[2]) == list(dup[:10]), metric                      # the tie rule on the repaired query
+            assert np.all(sc[2] == sc[2][0])
+            for b in (0, 1, 3, 4, 5):
+                oi, os_ = K.rank(V, Q[b], 10, metric)
+                assert list(idx[b]) == list(oi), (metric, b)
+            N.lib().hdb_launch_count(1)
+            sm.collect(sm.submit(np.delete(Q, 2, axis=0), 10, metric))
+            clean = N.lib().hdb_launch_count(0)
+            # the repair costs a handful of launches for ONE query (wide sweep + certify, exact scores + sort + take),
+            # not a second pass of the whole batch through every stage
+            assert with_repair - clean <= 12, (metric, with_repair, clean)
+            one = sm.query(Q[2], 10, metric)
+            assert list(one[0][0]) == list(dup[:10])
+    finally:
+        m.close()
