@@ -106,7 +106,8 @@ int hdb_matrix_set_row_offset(hdb_matrix* m, int64_t row_offset);
 /* ---- row subset: replaces the filters' output (hyperdb/hyperdb.py:1119-1134, :1218-1308) ---- */
 /* Keep only rows whose bit is set (bit i of word i/32, LSB first, local row ids); NULL keeps all. */
 int hdb_matrix_set_mask(hdb_matrix* m, const uint32_t* bits, int src_space);
-/* Row order: the shard's rows are STORED in another order than the caller numbers them -- typically clustered by a
+/* Row order (replaces nothing in the reference, which filters Python lists: hyperdb/hyperdb.py:1218-1257 builds the kept
+ * rows per query): the shard's rows are STORED in another order than the caller numbers them -- typically clustered by a
  * metadata key at ingest, so that a metadata filter keeps a few contiguous runs of rows and the masked sweep streams them
  * at the full HBM rate instead of skipping every other 768-byte row.  order[p] = the caller's local index of physical row
  * p (a permutation of 0 .. n_rows-1; host or device).  Reported ids are row_offset + order[p] and ties resolve on them
@@ -252,7 +253,9 @@ int hdb_profile_read(hdb_matrix* m, int* n_launches, float* total_ms);
  * back), 3 = tensor-core batched path when eligible, 4 = streaming sweep with the WIDE candidate class (128 candidates;
  * the first repair step for a query the automatic path could not certify). */
 int hdb_matrix_set_path(hdb_matrix* m, int mode);
-/* Small batches on the streaming path share ONE read of the matrix between up to 8 queries (multi-query sweep; the
+/* The reference ranks one query per call (hyperdb/ranking_algorithm.py:149-204 is entered once per query, the metric
+ * functions :24-147 read the whole matrix each time).  Here
+ * small batches on the streaming path share ONE read of the matrix between up to 8 queries (multi-query sweep; the
  * group size follows from the shape: 8 for fp16/fp32 rows with top_k <= 16, 4 for fp64 rows, top_k <= 100 and the
  * bit-packed metrics).  This caps the group for A/B measurements and tests: 1 = one pass per query, 0 = no cap. */
 int hdb_matrix_set_max_group(hdb_matrix* m, int max_queries_per_pass);
