@@ -603,9 +603,17 @@ class Bench:
         import torch
         import torch.distributed as dist
         from hyperdb_b200.sharded import shard_bounds
-        if w["metric"] not in ("cosine_similarity", "dot_product") or w.get("decay"):
+        if w["metric"] not in ("cosine_similarity", "dot_product"):
             return None
         world, rank, dev = self.world, self.rank, self.dev
+        bias = 0.3 if w.get("decay") else 0.0
+        ts_max = None
+        if w.get("decay"):
+            # the decay reference is the newest timestamp over the KEPT rows of ALL shards (hyperdb/ranking_algorithm.py:183)
+            kept_ts = self.ts if self.keep is None else self.ts[self.keep]
+            ts_max = kept_ts.max() if kept_ts.numel() else torch.tensor(float("-inf"), dtype=torch.float64, device=self.dev)
+            if world > 1:
+                dist.all_reduce(ts_max, op=dist.ReduceOp.MAX)
         sm, rows, lo, hi = self.sm, self.rows, self.lo, self.hi
         n, d, k = w["n"], w["d"], w["k"]
         plants = [n // 3, (2 * n) // 3 + 1]
@@ -623,12 +631,12 @@ class Bench:
         qs.append(gen_queries(1, d, w["dtype"], seed=777)[0])
         out = {"queries": len(qs), "planted_first": True, "indices_equal": True, "max_rel_score_err": 0.0, "tolerance_ties": 0}
         for qi, q in enumerate(qs):
-            idx, sc, cnt = sm.query(q, k, w["metric"], 0.0)[:3]
+            idx, sc, cnt = sm.query(q, k, w["metric"], bias)[:3]
             idx, sc = idx[0], sc[0]
             # independent check
             qf = torch.as_tensor(q.astype(np.float32)).to(dev)
             qn = qf / qf.norm().clamp_min(1e-30) if w["metric"] == "cosine_similarity" else qf
-            best_s = torch.empty(0, dtype=torch.float32, device=dev)
+            best_s = torch.empty(0, dtype=torch.float64, device=dev)
             best_i = torch.empty(0, dtype=torch.int64, device=dev)
             step = 1 << 20
             for a in range(0, hi - lo, step):
@@ -637,12 +645,18 @@ class Bench:
                 if w["metric"] == "cosine_similarity":
                     nv = v.norm(dim=1)
                     s = s / torch.where(nv == 0, torch.ones_like(nv), nv)
+                s = s.double()
+                if ts_max is not None:
+                    s = s + bias * torch.exp(self.ts[a:a + step] - ts_max)
                 if self.keep is not None:
                     s = torch.where(self.keep[a:a + step], s, torch.full_like(s, float("-inf")))
                 kk = min(2 * k, s.numel())
                 ts_, ti_ = torch.topk(s, kk)
+                ti_ = ti_ + a
+                if self.perm is not None:
+                    ti_ = self.perm[ti_]                          # clustered storage: physical row -> the document's local index
                 best_s = torch.cat([best_s, ts_])
-                best_i = torch.cat([best_i, ti_ + (lo + a)])
+                best_i = torch.cat([best_i, ti_ + lo])
                 del v, s
             kk = min(2 * k, best_s.numel())
             ts_, sel = torch.topk(best_s, kk)
@@ -667,7 +681,8 @@ class Bench:
                     out["indices_equal"] = False
         tol = 1e-3 if w["dtype"] == "float16" else 1e-5
         out["ok"] = bool(out["planted_first"] and out["indices_equal"] and out["max_rel_score_err"] <= tol)
-        out["against"] = "torch fp32 chunked matmul + topk per shard, merged by (score desc, id asc); planted rows %s" % plants
+        out["against"] = ("torch fp32 chunked matmul (+ float64 decay, keep mask, row order) + topk per shard, merged by (score desc, id asc); "
+                          "planted rows %s" % plants)
         return out
 
 
@@ -735,6 +750,13 @@ def main():
             r = bench.measure(e, we, 5 if we["b"] > 1 else 20, 3, mb, mk, want_clocks=False)
         except Exception as ex:                                   # noqa: BLE001
             r = {"workload": e, "error": str(ex)[:300]} if rank == 0 else None
+        if we.get("mask") or we.get("decay"):
+            try:
+                pc = bench.parity_check(we)                      # the masked / decayed / clustered configs carry their own check
+            except Exception as ex:                               # noqa: BLE001
+                pc = {"ok": False, "error": str(ex)[:200]}
+            if r is not None and pc is not None:
+                r["parity_check"] = pc
         if r is not None:
             r.pop("clocks", None)
             extra_lines.append(r)
