@@ -233,6 +233,8 @@ int hdb_exchange_error(hdb_exchange* x, int* error);
  * kernel, 16 bytes per query back to the host), a host query on the host with the same function.  digest_out: HOST,
  * 2 words per query.  Device queries are read on the handle's stream. */
 int hdb_query_digest(hdb_matrix* m, const void* queries, int q_dtype, int q_space, int64_t n_queries, uint64_t* digest_out);
+/* The same digest of HOST queries without a handle (no device is touched): n_queries rows of `dim` values. */
+int hdb_query_digest_host(const void* queries, int q_dtype, int64_t n_queries, int64_t dim, uint64_t* digest_out);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */

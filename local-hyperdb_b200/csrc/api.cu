@@ -1267,6 +1267,14 @@ int hdb_scores_ex(hdb_matrix* m, int metric, const void* query, int q_dtype, int
   return rc;
 }
 
+int hdb_query_digest_host(const void* queries, int q_dtype, int64_t n_queries, int64_t dim, uint64_t* digest_out) {
+  if (!queries || !digest_out) return fail("hdb_query_digest_host: NULL argument");
+  if (q_dtype < 0 || q_dtype > 2) return fail("hdb_query_digest_host: bad dtype");
+  if (n_queries < 0 || dim <= 0) return fail("hdb_query_digest_host: bad shape");
+  query_digest_host(queries, q_dtype, n_queries, dim, reinterpret_cast<unsigned long long*>(digest_out));
+  return 0;
+}
+
 int hdb_query_digest(hdb_matrix* m, const void* queries, int q_dtype, int q_space, int64_t n_queries, uint64_t* digest_out) {
   if (!m) return fail("null handle");
   if (!queries || !digest_out) return fail("hdb_query_digest: NULL argument");

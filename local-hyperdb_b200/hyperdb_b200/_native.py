@@ -55,6 +55,7 @@ SIGNATURES = {
     "hdb_scores": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]),
     "hdb_scores_ex": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "hdb_query_digest": (C.c_int, [vp, vp, C.c_int, C.c_int, i64, vp]),
+    "hdb_query_digest_host": (C.c_int, [vp, C.c_int, i64, i64, vp]),
     "hdb_normalize_rows": (C.c_int, [C.c_int, C.c_int, i64, i64, vp, C.c_int, vp, C.c_int]),
     "hdb_merge_topk": (C.c_int, [C.c_int, vp, i64, i64, i64, i64, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]),
     "hdb_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, i64, C.POINTER(vp)]),

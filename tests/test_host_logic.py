@@ -164,3 +164,22 @@ def test_shim_host_copy_is_lazy():
     assert v.shape == (5, 4) and len(db._chunks) == 1 and np.array_equal(v[:3], a)
     db.vectors = None
     assert db.vectors is None and db._n == 0
+
+
+def test_native_digest_equals_numpy_statement():
+    """hdb_query_digest_host (the C++ twin of the device kernel's formula, no GPU needed) == hyperdb.query_digest_host (NumPy) for
+    every query dtype, incl. -0.0, subnormals, infinities and long vectors; a batch is digested row by row."""
+    import ctypes as C
+    from hyperdb_b200 import _native as N
+    from hyperdb_b200.hyperdb import query_digest_host
+    rng = np.random.default_rng(8)
+    for dt, code in ((np.float16, 0), (np.float32, 1), (np.float64, 2)):
+        for d in (1, 7, 768, 4099):
+            Q = rng.standard_normal((3, d)).astype(dt)
+            Q[0, 0] = -0.0
+            Q[1, -1] = np.inf
+            Q[2, d // 2] = np.finfo(dt).smallest_subnormal
+            out = (C.c_uint64 * 6)()
+            N.check(N.lib().hdb_query_digest_host(C.c_void_p(Q.ctypes.data), code, 3, d, out))
+            for b in range(3):
+                assert (int(out[2 * b]), int(out[2 * b + 1])) == query_digest_host(Q[b]), (dt, d, b)
