@@ -821,7 +821,11 @@ static int ensure_tc_workspace(hdb_matrix* m, int64_t nq, int kp) {
   double expect_rec = (double)m->n * (double)nq * kp / (double)(sample_tiles * 128) / sms;
   int64_t rec_cap = (int64_t)(3.0 * expect_rec) + 8192;
   if (rec_cap > (int64_t)1 << 21) rec_cap = (int64_t)1 << 21;
-  if (m->tc_nq >= nq && m->tc.cap >= cap && m->tc.sample_tiles == sample_tiles && m->tc.rec_cap >= (unsigned)rec_cap) return 0;
+  if (const char* e = getenv("HDB_TC_REC_CAP")) {                // tests: force the record buffers to overflow
+    const int64_t forced = atoll(e);
+    if (forced >= 16) rec_cap = forced;
+  }
+  if (m->tc_nq >= nq && m->tc.cap >= cap && m->tc.sample_tiles == sample_tiles && m->tc.rec_cap >= (unsigned)rec_cap && !getenv("HDB_TC_REC_CAP")) return 0;
   void* ptrs[] = {m->tc.q16, m->tc.dense, m->tc.tau0, m->tc.cand, m->tc.cand_count, m->tc.rec, m->tc.rec_count, m->tc.qsq};
   for (void* p : ptrs) if (p) cudaFree(p);
   m->tc = TcWorkspace{};

@@ -439,3 +439,32 @@ def test_row_order_clustered_storage(hb, vdt, metric):
         finally:
             m.close()
             ref.close()
+
+
+def test_tensor_path_record_overflow_is_repaired(hb):
+    """when the CTA-private record buffers of the batched contraction overflow, every query of the batch must come
+    back UNCERTIFIED (the poison survives concurrent appends) and the host call must repair it -- never a silently short candidate
+    list.  HDB_TC_REC_CAP forces the overflow; the answers must equal the unforced run and the oracle."""
+    import os
+    rng = np.random.default_rng(4)
+    n, d, b = 540_000, 64, 24
+    V = rng.standard_normal((n, d)).astype(np.float16)
+    Q = rng.standard_normal((b, d)).astype(np.float16)
+    m = hb.DeviceMatrix(V)
+    try:
+        want = m.query(Q, 10, "cosine_similarity")
+        assert (want[3] & hb._native.FLAG_TENSOR).any()                       # the batch did take the tensor-core path
+        os.environ["HDB_TC_REC_CAP"] = "16"
+        try:
+            got = m.query(Q, 10, "cosine_similarity")
+        finally:
+            del os.environ["HDB_TC_REC_CAP"]
+        assert not (got[3] & hb._native.FLAG_UNCERTIFIED).any()               # repaired by the host call ...
+        assert not (got[3] & hb._native.FLAG_TENSOR).all()                    # ... i.e. (most of) the batch did not keep its tensor-path answer
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        for qi in (0, 7, 23):
+            check_against_oracle(V, Q[qi], None, 0.0, 10, "cosine_similarity", got[0][qi], got[1][qi], None)
+        again = m.query(Q, 10, "cosine_similarity")                          # the workspace recovers once the cap is lifted
+        assert (again[3] & hb._native.FLAG_TENSOR).any() and np.array_equal(again[0], want[0])
+    finally:
+        m.close()
