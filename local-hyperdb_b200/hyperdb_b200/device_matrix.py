@@ -199,6 +199,12 @@ class DeviceMatrix:
         N.check(N.lib().hdb_matrix_set_timestamps(self._h, p, space))
         self._has_ts = True
 
+    def stage_column(self, values):
+        """A float64 per-row column (timestamps) as a device-resident tensor on this shard's GPU: the HyperDB shim keeps one per
+        timestamp key and hands it to `set_timestamps` (device -> device) instead of re-uploading N doubles per recency query."""
+        import torch
+        return torch.as_tensor(np.ascontiguousarray(values, np.float64)).to(f"cuda:{self.device}")
+
     def kept_ts_max(self):
         """(max timestamp over kept rows of this shard, number of kept rows)."""
         mx, cnt = C.c_double(), C.c_int64()

@@ -436,11 +436,10 @@ class HyperDB:
                 raise ValueError("All timestamps must be populated when recency_bias is not 0 or timestamp_key is provided.")
         n_loc = m.shape[0]
         if timestamp_key not in self._ts_dev:
-            import torch
             local_ts = ts[self._lo:self._lo + n_loc]
             if self._perm is not None:
                 local_ts = local_ts[self._perm]
-            self._ts_dev[timestamp_key] = torch.as_tensor(np.ascontiguousarray(local_ts)).to(f"cuda:{m.device}")
+            self._ts_dev[timestamp_key] = m.stage_column(local_ts)
         m.set_timestamps(self._ts_dev[timestamp_key])           # device -> device: the column is transformed in place below
 
         def global_max():
