@@ -508,8 +508,9 @@ class Bench:
         e2e_qps, depth = sync_qps, 1
         if use_tickets:
             depth = 3
-            for i in range(2):
-                sm.collect(sm.submit(qslice(q_np, i), k, w["metric"], bias))
+            warm = [sm.submit(qslice(q_np, i), k, w["metric"], bias) for i in range(4)]      # every ticket slot: its pinned block exists
+            for t in warm:
+                sm.collect(t)
             self.barrier()
             t0 = time.perf_counter()
             tickets = []
