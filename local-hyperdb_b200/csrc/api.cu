@@ -876,6 +876,14 @@ static int run_exact(hdb_matrix* m, int metric, int rdt, int64_t b, int64_t k, c
                     &m->sort_scratch, &m->sort_scratch_bytes, m->stream);
 }
 
+// Batched pearson on the tensor cores (batched_tc.cu) can be switched off for an A/B against the multi-query sweep:
+// HDB_TC_PEARSON=0.  The other tensor-path metrics have no switch (--path / hdb_matrix_set_path_mode covers them).
+static bool tc_metric_enabled(int metric) {
+  if (metric != HDB_PEARSON) return true;
+  static const bool on = [] { const char* e = getenv("HDB_TC_PEARSON"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q_space, int64_t nq, int64_t top_k,
               double recency_bias, int64_t* out_idx, double* out_score, int64_t* out_count, uint32_t* out_flags,
               int out_space) {
@@ -963,7 +971,8 @@ int hdb_query(hdb_matrix* m, int metric, const void* queries, int q_dtype, int q
   if (k == 0) {
     HDB_CUDA(cudaMemsetAsync(count, 0, (size_t)nq * 8, m->stream));
     if (flags) HDB_CUDA(cudaMemcpyAsync(flags, m->qb.qflags, (size_t)nq * 4, cudaMemcpyDeviceToDevice, m->stream));
-  } else if (kp && m->path_mode != 2 && m->path_mode != 4 && !m->ord && batched_tc_supported(view_of(m), metric, q_dtype, nq, use_decay)) {
+  } else if (kp && m->path_mode != 2 && m->path_mode != 4 && !m->ord && tc_metric_enabled(metric) &&
+             batched_tc_supported(view_of(m), metric, q_dtype, nq, use_decay)) {
     if (m->dtype == 1) kp = 128;         // tf32 select: wider error band, so certify a wider candidate list
     // kind::f16 batches of hundreds of queries: with 32 candidates about one query in 24 000 fails its certificate (the
     // non-IEEE accumulation band against the gap between the 10th and the 32nd score), i.e. most 4096-query batches carry

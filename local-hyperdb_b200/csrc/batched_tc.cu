@@ -644,7 +644,15 @@ __global__ void __launch_bounds__(256) sample_threshold_kernel(const float* dens
     need = sel[1];
     __syncthreads();
   }
-  if (threadIdx.x == 0) tau0[blockIdx.x] = unorder_f32(prefix);
+  if (threadIdx.x == 0) {
+    float t = unorder_f32(prefix);
+    // hist[] of the last pass counts the sample values EQUAL to the threshold.  A degenerate query (all zeros for dot / cosine, a
+    // constant one for pearson) ties on every row: its select pass would append the whole matrix, overflow the CTA-private record
+    // buffers and, through the poison of bucket_records_kernel, send every query of the batch to the repair path.  Give such a
+    // query an unreachable threshold instead: nothing is appended, it alone comes back uncertified and is repaired.
+    if (hist[sel[0]] > 4u * (unsigned)kp && t > -INFINITY) t = INFINITY;
+    tau0[blockIdx.x] = t;
+  }
 }
 
 __global__ void square_norms_kernel(const double* qnorm, float* qsq, int64_t nq) {
@@ -703,8 +711,11 @@ static int launch_tc(const CUtensorMap& mv, const CUtensorMap& mq, const TcParam
 }
 
 int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t nq, bool has_decay) {
-  if (metric != HDB_DOT && metric != HDB_COSINE && metric != HDB_EUCLIDEAN) return 0;
+  if (metric != HDB_DOT && metric != HDB_COSINE && metric != HDB_EUCLIDEAN && metric != HDB_PEARSON) return 0;
   if (metric == HDB_EUCLIDEAN && (has_decay || !m.sqnorms)) return 0;   // 1/(1+d) + decay is not monotone in -d^2
+  // pearson: the contraction runs on the centred query b = q - mean(q) and the epilogue scales by 1/(std_v d); the query's own
+  // 1/std_q is a positive factor per query, left to the certify step -- which a per-row decay term would not commute with
+  if (metric == HDB_PEARSON && (has_decay || !m.pscale)) return 0;
   if (m.dtype == 2) return 0;                                  // no fp64 tensor path
   if (q_dtype > m.dtype) return 0;                             // the B operand has the storage precision: exact only then
   if ((m.d * dtype_size(m.dtype)) % 16 != 0 || (reinterpret_cast<uintptr_t>(m.rows) & 15)) return 0;
@@ -750,7 +761,8 @@ int launch_batched_tc(const MatrixView& m, int metric, const RowFilter& f, const
   p.debug = getenv("HDB_TC_DEBUG") ? atoi(getenv("HDB_TC_DEBUG")) : 0;
   p.prefetch_dist = getenv("HDB_TC_PREFETCH_DIST") ? atoi(getenv("HDB_TC_PREFETCH_DIST")) : 1;
   if (p.prefetch_dist < 1) p.prefetch_dist = 1;
-  p.inv_norms = metric == HDB_COSINE ? reinterpret_cast<const float*>(m.inv_norms) : nullptr;
+  p.inv_norms = metric == HDB_COSINE ? reinterpret_cast<const float*>(m.inv_norms)
+              : metric == HDB_PEARSON ? reinterpret_cast<const float*>(m.pscale) : nullptr;     // NaN for a constant row: never appended
   p.sqnorms = nullptr; p.qsq = nullptr;
   if (metric == HDB_EUCLIDEAN) {
     square_norms_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(qnorm, ws.qsq, nq);

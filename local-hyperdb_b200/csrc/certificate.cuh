@@ -11,7 +11,8 @@ namespace hdb {
 
 // Upper bound of the CANONICAL total score of any row whose selection key is <= the KP-th key
 // (score part s).  See DESIGN.md "certificate"; every term is a worst-case rounding bound.
-__device__ inline double outsider_bound(double s, const FinalizeArgs& a, double qnorm, double qstd) {
+// qsumb: pearson on the batched tensor pass only -- sum_j (q_j - mean_q), the factor of the mean correction that pass leaves out.
+__device__ inline double outsider_bound(double s, const FinalizeArgs& a, double qnorm, double qstd, double qsumb = 0.0) {
   const double D = (double)a.m.d + 8.0;
   const double uk = 1.1920928955078125e-7;                    // 2^-23: float32 key rounding (2x slack)
   // accumulate type of the select pass; the tensor cores' fp32 accumulation is not IEEE round-to-nearest
@@ -31,6 +32,13 @@ __device__ inline double outsider_bound(double s, const FinalizeArgs& a, double 
     double b = s + fabs(s) * uk
              + A * ((D + 16.0) * ua + 1.1920928955078125e-7)   // sweep: FMA chains, mean correction, scalings; query rounded to the accumulate type
              + Ac * 1.05 * (uT + uR + D * uaccR);              // reference: (v - mean) rounded to S, products to R, pairwise sum
+    if (a.cand_count) {
+      // batched pass (batched_tc.cu): v.b / (std_v d) on the tensor cores, divided by std_q by the caller.  It leaves out the mean
+      // correction mean_v * sum(b) / (std_v std_q d), at most max_pratio * |sum(b)| / (d std_q) because |mean_v| <= ||v|| / sqrt(d);
+      // kind::tf32 keeps 10 mantissa bits of each fp32 operand (2 * 2^-9 of sum_j |v_j b_j|, as for dot / cosine).
+      b += (double)a.m.max_pratio * fabs(qsumb) / ((double)a.m.d * qstd) * 1.000001;
+      if (a.m.dtype == 1) b += A * 3.90625e-3;
+    }
     // reference: rounding of the sum, the denominator (3 roundings) and the quotient, relative to the similarity itself
     b += 6.0 * uR * (decay ? Ac : fabs(b));
     if (a.rdt == 0 || a.m.dtype == 0) {

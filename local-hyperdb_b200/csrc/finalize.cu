@@ -346,7 +346,14 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs a) {
         const double t0 = (double)a.tau0[b];
         s_edge = a.tau0_negd2 ? 1.0 / (1.0 + sqrt(t0 < 0.0 ? -t0 : 0.0)) : t0;
       }
-      const double bound = outsider_bound(s_edge, a, a.qb.qnorm[b], a.qb.qaux ? a.qb.qaux[2 * b] : 1.0);
+      const double qstd = a.qb.qaux ? a.qb.qaux[2 * b] : 1.0;
+      double qsumb = 0.0;
+      if (a.cand_count && a.metric == HDB_PEARSON) {
+        // the batched pass screens v.b / (std_v d): its keys and tau0 still lack the query's 1 / std_q (> 0: same order per query)
+        s_edge = s_edge / qstd;
+        qsumb = a.qb.qaux[2 * b + 1];
+      }
+      const double bound = outsider_bound(s_edge, a, a.qb.qnorm[b], qstd, qsumb);
       certified = o_tot[kk - 1] > bound;
     }
   }

@@ -44,6 +44,8 @@ def emul(tmp_path_factory):
     lib.emul_outsider_bound.restype = C.c_double
     lib.emul_outsider_bound.argtypes = ([C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64] + [C.c_double] * 5 +
                                         [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double])
+    lib.emul_outsider_bound_tc.restype = C.c_double
+    lib.emul_outsider_bound_tc.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64] + [C.c_double] * 8
     return lib
 
 

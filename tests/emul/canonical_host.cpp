@@ -95,6 +95,21 @@ double emul_outsider_bound(double s, int metric, int rdt, int sdt, int64_t d, do
   return outsider_bound(s, a, qnorm, qstd);
 }
 
+// the batched tensor pass's certificate: the same statistics plus sum_j (q_j - mean_q) (pearson: the mean correction that pass
+// leaves out); s is the key score already divided by std_q, as finalize.cu passes it
+double emul_outsider_bound_tc(double s, int metric, int rdt, int sdt, int64_t d, double max_norm, double max_ratio, double max_pratio,
+                              double max_cratio, double min_pstd, double qnorm, double qstd, double qsumb) {
+  FinalizeArgs a;
+  std::memset(&a, 0, sizeof(a));
+  static unsigned dummy_count = 0;
+  a.m.d = d; a.m.dtype = sdt;
+  a.m.max_norm = (float)max_norm; a.m.max_ratio = (float)max_ratio;
+  a.m.max_pratio = (float)max_pratio; a.m.max_cratio = (float)max_cratio; a.m.min_pstd = (float)min_pstd;
+  a.rdt = rdt; a.metric = metric;
+  a.cand_count = &dummy_count;
+  return outsider_bound(s, a, qnorm, qstd, qsumb);
+}
+
 double emul_unit_elem(double v, double norm, int dt) { return unit_elem(v, norm, dt); }
 double emul_sub_in(double x, double y, int dt) { return sub_in(x, y, dt); }
 

@@ -113,3 +113,65 @@ def test_pearson_bound_of_the_product_code(emul, sdt):
                     assert canon[i] <= bound, (qdt.__name__, d, scale, shift, i, canon[i], sweep[i], bound)
                     rows += 1
     assert rows > 2000
+
+
+def _trunc_tf32(x):
+    """kind::tf32 reads fp32 operands with 10 explicit mantissa bits (the low 13 bits are ignored)."""
+    return (np.asarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+@pytest.mark.parametrize("sdt", [np.float16, np.float32])
+def test_pearson_bound_of_the_batched_tensor_pass(emul, sdt):
+    """Batched pearson on the tensor cores (csrc/batched_tc.cu, VERDICT round 1 missing #6): the select pass screens
+    u = fl32(acc * pscale) with acc = V . b on tcgen05 (b = q - mean(q); fp16 operands exact, fp32 operands cut to tf32), WITHOUT
+    the mean correction mean_v * sum(b) and without 1 / std_q; finalize.cu divides the edge key by std_q and calls outsider_bound
+    with sum(b).  Property: for every row the reference's value stays below the bound of the row's own key -- with the
+    accumulator pushed DOWN by half of the error band the certificate grants the tensor cores (d * 2^-20 of sum |v_j b_j|), the
+    worst case for an outsider."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(("tensor" + sdt.__name__).encode()))
+    dts = {np.dtype(np.float16): 0, np.dtype(np.float32): 1}
+    rows = 0
+    worst = 0.0
+    for qdt in ((np.float16,) if sdt == np.float16 else (np.float16, np.float32)):     # batched_tc_supported: q_dtype <= storage
+        for d in (8, 96, 384, 768):
+            for scale, shift in ((1.0, 0.0), (0.04, 0.0), (0.04, 0.3), (1.0, 5.0), (3.0, 20.0)):
+                n = 150
+                V = (rng.standard_normal((n, d)) * scale * rng.uniform(0.2, 3, (n, 1)) + shift * rng.uniform(-1, 1, (n, 1))).astype(sdt)
+                q = (rng.standard_normal(d) * scale + shift).astype(qdt)
+                R = np.promote_types(sdt, qdt)
+                with np.errstate(all="ignore"):
+                    canon = K.pearson(V, q)
+                    vmean, vstd = K.row_mean(V).astype(np.float64), K.row_std(V).astype(np.float64)
+                    qmean = K.row_mean(q[None, :], scalar=True)[0]
+                    qstd = float(K.row_std(q[None, :])[0])
+                    b = (q - qmean).astype(np.float32)                  # qb.qa: exact, the query dtype is at most fp32
+                    sumb = float(np.sum(b.astype(np.float64)))          # qb.qaux[2b + 1]
+                    if sdt == np.float32:
+                        Vop, bop = _trunc_tf32(V).astype(np.float64), _trunc_tf32(b).astype(np.float64)
+                    else:
+                        Vop, bop = V.astype(np.float64), b.astype(np.float16).astype(np.float64)
+                        assert np.array_equal(bop, b.astype(np.float64))          # fp16 query: the B operand is exact
+                    acc = Vop @ bop - d * 2.0 ** -20 * (np.abs(Vop) @ np.abs(bop))
+                    pscale = (1.0 / (vstd * d)).astype(np.float32)
+                    u = (acc.astype(np.float32) * pscale).astype(np.float32).astype(np.float64)     # the key's score part
+                ok = (vstd > 0) & np.isfinite(vstd) & np.isfinite(canon) & np.isfinite(u)
+                if not ok.any() or not (qstd > 0):
+                    continue
+                Vd = V.astype(np.float64)
+                f32 = lambda x: float(np.float32(x))
+                max_norm = f32(np.max(np.linalg.norm(Vd, axis=1)) * (1 + 1e-6))
+                max_pratio = f32(np.max(np.linalg.norm(Vd[ok], axis=1) / (vstd[ok] * np.sqrt(d))) * (1 + 1e-6))
+                max_cratio = f32(np.max(np.linalg.norm(Vd[ok] - vmean[ok, None], axis=1) / (vstd[ok] * np.sqrt(d))) * (1 + 1e-6))
+                min_pstd = f32(np.min(vstd[ok]) * (1 - 1e-6))
+                qn = float(np.linalg.norm((q - qmean).astype(np.float64)) / (qstd * np.sqrt(d)))
+                for i in np.flatnonzero(ok):
+                    s = float(u[i]) / qstd
+                    bound = emul.emul_outsider_bound_tc(s, 6, dts[np.dtype(R)], dts[np.dtype(sdt)], d, max_norm, 1.0, max_pratio,
+                                                        max_cratio, min_pstd, qn, qstd, sumb)
+                    assert canon[i] <= bound, (qdt.__name__, d, scale, shift, i, canon[i], s, bound)
+                    if np.isfinite(bound):
+                        worst = max(worst, (canon[i] - s) / max(bound - s, 1e-300))
+                        rows += 1
+    assert rows > 1500
+    assert worst < 0.95, worst            # the band is used, not exhausted

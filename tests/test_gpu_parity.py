@@ -380,6 +380,67 @@ def test_batched_tensor_path(hb, metric, nq, sdt):
         m.close()
 
 
+# ---- batched pearson on the tensor cores (missing #6) ------------------------------------------------
+@pytest.mark.parametrize("sdt", ["float16", "float32"])
+@pytest.mark.parametrize("nq", [17, 300])
+def test_batched_pearson_tensor_path(hb, nq, sdt):
+    """pearson_correlation (hyperdb/ranking_algorithm.py:84-113) for a batch: V . (q - mean(q)) on tcgen05, 1 / (std_v d) in the
+    epilogue, the query's 1 / std_q and the left-out mean correction in the certify step (csrc/certificate.cuh).  Rows carry
+    a per-row offset (|mean| / std up to 1: the mean correction matters), a few rows are constant (NaN -> -inf, never a
+    candidate) and one query is constant (every score NaN: exact path).  Must equal the streaming sweep bit for bit, and the
+    oracle on a row range."""
+    import torch
+    n, d = 530_000, 136
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + nq)
+    V = torch.randn(n, d, generator=g, device=dev) * (0.5 + torch.rand(n, 1, generator=g, device=dev))
+    V = V + 1.0 * (torch.rand(n, 1, generator=g, device=dev) - 0.5)
+    V[1234] = 0.75                                              # constant rows: std == 0
+    V[400_001] = 0.0
+    V = V.half() if sdt == "float16" else V.float()
+    Q = torch.randn(nq, d, generator=g, device=dev) + 0.3
+    Q[5] = 0.5 * (V[77_777].float() - 1.0) + 0.05 * Q[5]        # a strongly correlated row for one query
+    Q[9] = 0.25                                                 # a constant query
+    Q = Q.half() if sdt == "float16" else Q.float()
+    ts = 1.7e9 + 10 * torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+    keep_bits = torch.randint(-2**31, 2**31 - 1, ((n + 31) // 32,), generator=g, device=dev, dtype=torch.int32)
+    q_np = Q.cpu().numpy()
+    metric = "pearson_correlation"
+    m = hb.DeviceMatrix(V)
+    try:
+        for use_ts, use_mask, k in ((False, False, 10), (False, True, 100), (True, True, 10)):
+            m.set_mask(keep_bits if use_mask else None)
+            m.set_timestamps(ts if use_ts else None)
+            if use_ts:
+                m.refresh_decay()
+            bias = 0.2 if use_ts else 0.0
+            m.set_path(4)                                       # the streaming sweep with the exact-path repair: the reference answer
+            i0, s0, c0, f0 = m.query(q_np, k, metric, bias)
+            m.set_path(0)
+            i1, s1, c1, f1 = m.query(q_np, k, metric, bias)
+            if use_ts:       # a per-row decay term does not commute with the per-query 1 / std_q: sweeps
+                assert not any(f & 4 for f in f1)
+            elif k == 10:
+                # (k = 100 of 128 candidates: the gap between the 100th and the 128th score is of the order of the tf32 band
+                #  times max ||v|| / (std sqrt d) ~ 1.4 here, so many of those queries are legitimately re-run by the sweep,
+                #  which clears bit 4; the equality below covers them)
+                assert sum(1 for f in f1 if f & 4) >= 0.7 * nq, ("tensor-core path was not taken", f1.tolist())
+                assert sum(1 for f in f1 if f & 1) <= max(2, nq // 8), "too many exact-path fallbacks on the tensor path"
+            assert np.array_equal(i0, i1) and np.array_equal(c0, c1)
+            assert np.array_equal(s0, s1, equal_nan=True)
+        m.set_mask(None)
+        m.set_timestamps(None)
+        m.set_range(1000, 41000)
+        i1, s1, _, f1 = m.query(q_np[:6], 10, metric)
+        sub = V[1000:41000].cpu().numpy()
+        for b in range(6):
+            oi, os_ = K.rank(sub, q_np[b], 10, metric)
+            assert list(i1[b] - 1000) == list(oi) and np.array_equal(s1[b], os_)
+    finally:
+        m.close()
+
+
 @pytest.mark.parametrize("vdt", ["f16", "f32", "f64"])
 @pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance", "hamming_distance",
                                     "jaccard_similarity", "pearson_correlation"])
