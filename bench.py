@@ -62,6 +62,8 @@ WORKLOADS = {
     "c5_hamming_b8": dict(n=5_000_000, d=1024, dtype="float32", metric="hamming_distance", k=10, b=8),
     "c3_cosine_b8": dict(n=10_000_000, d=768, dtype="float16", metric="cosine_similarity", k=10, b=8),
     "c3_pearson_b8": dict(n=10_000_000, d=768, dtype="float16", metric="pearson_correlation", k=10, b=8),
+    # pearson batches on the tensor cores: V . (q - mean q), 1 / (std_v d) in the epilogue, 1 / std_q in the certify step
+    "c3_pearson_b1024": dict(n=10_000_000, d=768, dtype="float16", metric="pearson_correlation", k=10, b=1024),
     "c4_decay_mask_k100": dict(n=100_000_000, d=384, dtype="float16", metric="cosine_similarity", k=100, b=1,
                                decay=True, mask=True),
     # the same store CLUSTERED by the filtered metadata key at ingest (hdb_matrix_set_row_order): same ids, ties and answers,
@@ -70,7 +72,7 @@ WORKLOADS = {
                                          decay=True, mask=True, cluster=True),
 }
 # the short passes attached to the default line as "extra" (same matrix as the headline first, then config C5's)
-EXTRAS = ["c3_cosine_b8", "c3_cosine_b64", "c3_cosine_b4096", "c5_hamming_b1", "c5_manhattan_b8", "c2_cosine_b1024",
+EXTRAS = ["c3_cosine_b8", "c3_cosine_b64", "c3_cosine_b4096", "c3_pearson_b1024", "c5_hamming_b1", "c5_manhattan_b8", "c2_cosine_b1024",
           "c4_decay_mask_k100", "c4_decay_mask_k100_clustered"]
 CHUNK = 262_144          # rows per generator chunk: chunk c of the GLOBAL matrix is seeded with (seed, c)
 ITEM = {"float16": 2, "float32": 4, "float64": 8}
