@@ -588,12 +588,19 @@ class HyperDB:
         return results
 
     def query_batch(self, queries, top_k=5, return_similarities=True, filters=None, recency_bias=0, timestamp_key=None,
-                    metric='cosine_similarity'):
+                    metric='cosine_similarity', native_dtype=False):
         """B queries in one call -- `queries` is a (B, d) array, a CUDA tensor (e.g. the embedding model's output, used as
         the query tile without a host round trip) or a list of texts for `embedding_function`.  One result list per query,
         each equal to what `query` returns for that row (the reference has no batched API: hyperdb/hyperdb.py:1584 is
-        called once per query).  Small batches share one read of the matrix (multi-query sweep); large dot / cosine /
-        euclidean batches run on the tensor cores.  The query cache is not consulted."""
+        called once per query).  The query cache is not consulted.
+
+        native_dtype=False (default): the tile is ranked as FLOAT64, the dtype `query`'s cache round trip gives every vector
+        query (hyperdb/hyperdb.py:1369-1370) -- queries wider than the stored matrix: up to 8 of them share one read of the
+        matrix (multi-query sweep), the scores are float64 arithmetic.
+        native_dtype=True: a float16 / float32 / float64 tile is ranked in ITS OWN dtype -- the arithmetic of
+        `hyperDB_ranking_algorithm_sort(vectors, q)` called with that array (hyperdb/ranking_algorithm.py:116-204) instead of
+        `query`'s float64 detour.  A tile no wider than the stored matrix (the usual case: an fp16 / fp32 embedding model
+        over an fp16 / fp32 store) then runs as ONE tensor-core contraction for dot / cosine / euclidean / pearson."""
         if self._n == 0 or not self.documents:
             raise Exception("The database is empty. Cannot proceed with the query.")
         if metric not in _METRICS:
@@ -606,9 +613,14 @@ class HyperDB:
         if _is_torch(queries):
             import torch
             Q = queries if queries.dim() == 2 else queries.reshape(1, -1)
-            Q = Q.to(torch.float64) if Q.is_cuda else Q.to(torch.float64).numpy()
+            if not (native_dtype and Q.dtype in (torch.float16, torch.float32, torch.float64)):
+                Q = Q.to(torch.float64)
+            Q = Q if Q.is_cuda else Q.numpy()
         else:
-            Q = np.atleast_2d(np.asarray(queries, dtype=np.float64))
+            Q = np.asarray(queries)
+            if not (native_dtype and Q.dtype in (np.float16, np.float32, np.float64)):
+                Q = np.asarray(Q, dtype=np.float64)
+            Q = np.atleast_2d(Q)
         if Q.shape[-1] != self._d:
             raise ValueError(f"The dimension of the query_vector ({Q.shape[-1]}) must match the dimension of the vectors in the database ({self._d}).")
         top_k, bias = self._prepare(filters, recency_bias, timestamp_key, top_k)

@@ -85,6 +85,27 @@ def test_mutations_and_errors_on_cpu(shim):
     got = db.query_batch(queries[:3], top_k=4)
     for i in range(3):
         assert [x[0]["id"] for x in got[i]] == [x[0]["id"] for x in db.query(queries[i], top_k=4)]
+    # native_dtype: the tile reaches the engine in its own dtype (float32 queries over the float32 store: the tensor-core
+    # case) and the scores are those of the ranking function called with that array; default: float64, as `query`
+    from shim_fakes import FakeDeviceMatrix
+    from oracle import canonical as K
+    Q32 = np.asarray(queries[:3], np.float32)
+    seen = []
+    real_query = FakeDeviceMatrix.query
+    FakeDeviceMatrix.query = lambda self, q, *a, **kw: (seen.append(np.asarray(q).dtype), real_query(self, q, *a, **kw))[1]
+    try:
+        nat = db.query_batch(Q32, top_k=4, metric="euclidean_metric", native_dtype=True)
+        dflt = db.query_batch(Q32, top_k=4, metric="euclidean_metric")
+        db.query_batch(Q32.astype(np.int32), top_k=1, native_dtype=True)               # not a float tile: float64 as before
+    finally:
+        FakeDeviceMatrix.query = real_query
+    assert seen == [np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.float64)]
+    V = np.asarray(db.vectors)
+    for i in range(3):
+        oi, os_ = K.rank(V, Q32[i], 4, "euclidean_metric")
+        assert [x[2] for x in nat[i]] == list(oi) and [x[1] for x in nat[i]] == list(os_)
+        oi, os_ = K.rank(V, Q32[i].astype(np.float64), 4, "euclidean_metric")
+        assert [x[2] for x in dflt[i]] == list(oi) and [x[1] for x in dflt[i]] == list(os_)
 
 
 def _sharded_shim_worker(rank, world, port, out_dir):
