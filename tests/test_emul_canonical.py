@@ -207,3 +207,98 @@ def test_certificate_bound_covers_the_reference(emul, metric, decay):
             rows_checked += 1
     assert rows_checked > 3000
     assert worst_use < 0.95, worst_use
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The same certificate for the BATCHED TENSOR PASS (csrc/batched_tc.cu): operands as tcgen05 reads them (fp16 exact; fp32 cut
+# to tf32), the accumulator pushed DOWN by half of the band the certificate grants the tensor cores' non-IEEE fp32
+# accumulation (d * 2^-20 of sum |v_j q_j|) -- the worst case for a row left outside the candidates --, then the epilogue's own
+# float32 arithmetic (fma with the per-row factor and the decay addend; the norm expansion for euclidean).
+# ---------------------------------------------------------------------------------------------------------------------
+def _trunc_tf32(x):
+    return (np.asarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _tensor_pass_scores(V, q, metric, addend32):
+    from oracle import canonical as K
+    d = V.shape[1]
+    with np.errstate(all="ignore"):
+        c = (np.asarray(K.unit_rows(q)).reshape(-1) if metric == "cosine_similarity" else q).astype(np.float64)      # prep_query's canonical values
+        qnorm = float(np.sqrt(np.sum(c * c)))
+        qa = c.astype(np.float32)                                                             # qb.qa
+        if V.dtype == np.float16:
+            Vop, bop = V.astype(np.float64), qa.astype(np.float16).astype(np.float64)          # queries_to_half_kernel: round to nearest
+        else:
+            Vop, bop = _trunc_tf32(V).astype(np.float64), _trunc_tf32(qa).astype(np.float64)
+        acc = (Vop @ bop - d * 2.0 ** -20 * (np.abs(Vop) @ np.abs(bop))).astype(np.float32)
+        Vd = V.astype(np.float64)
+        if metric == "euclidean_metric":
+            sqn = np.sum(Vd * Vd, axis=1).astype(np.float32)                                  # ingest column ||v||^2
+            qsq = np.float32(qnorm * qnorm)
+            t = (np.float32(2) * acc.astype(np.float64) - sqn.astype(np.float64)).astype(np.float32)   # fma(acc, 2, -|v|^2)
+            d2 = (qsq - t).astype(np.float32)
+            key = (np.float32(1) / (np.float32(1) + np.sqrt(np.maximum(d2, np.float32(0))))).astype(np.float32)
+        else:
+            inv = np.ones(len(V), np.float32)
+            if metric == "cosine_similarity":
+                cn = K.row_norm(V).astype(np.float32)
+                cn[cn == 0] = 1
+                inv = (np.float32(1) / cn).astype(np.float32)
+            key = (acc.astype(np.float64) * inv.astype(np.float64) + addend32.astype(np.float64)).astype(np.float32)    # one fma
+    return key.astype(np.float64), qnorm
+
+
+@pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity", "euclidean_metric"])
+@pytest.mark.parametrize("decay", [False, True], ids=["plain", "decay"])
+def test_certificate_bound_of_the_batched_tensor_pass(emul, metric, decay):
+    import zlib
+    from oracle import canonical as K
+    if metric == "euclidean_metric" and decay:
+        pytest.skip("batched_tc_supported: euclidean with time decay stays on the sweeps")
+    rng = np.random.default_rng(zlib.crc32(("tc" + metric + str(decay)).encode()))
+    worst_use, rows_checked = 0.0, 0
+    for trial in range(80):
+        n, d = 64, int(rng.choice([8, 16, 96, 384, 768, 1536]))
+        vdt = DTS[trial % 2]
+        qdt = DTS[int(rng.integers(0, DT[np.dtype(vdt)] + 1))]          # batched_tc_supported: the query is never wider than the store
+        kind = (trial // 2) % 3
+        V = rng.standard_normal((n, d))
+        q = rng.standard_normal(d)
+        if kind == 0 or metric == "euclidean_metric":     # unit rows, unit query (the norm expansion only certifies embedding-like data)
+            V /= np.linalg.norm(V, axis=1, keepdims=True)
+            q /= np.linalg.norm(q)
+            if kind == 1:
+                V[:8] = q[None, :] + rng.standard_normal((8, d)) * 3e-2
+        elif kind == 1:
+            V *= rng.uniform(0.05, 4.0, (n, 1))
+            V[:8] = q[None, :] * rng.uniform(0.5, 1.5, (8, 1)) + rng.standard_normal((8, d)) * 1e-3
+        else:
+            V += 1.5
+            q += 1.5
+        V, q = np.ascontiguousarray(V.astype(vdt)), np.ascontiguousarray(q.astype(qdt))
+        rdt = np.promote_types(vdt, qdt)
+        with np.errstate(all="ignore"):
+            canon = K.scores(V, q, metric).astype(np.float64)
+            bias, dec = 0.0, np.zeros(n)
+            if decay:
+                bias = float(rng.choice([0.3, 1.0, -0.5]))
+                dec = np.exp(-rng.uniform(0, 5, n))
+            key, qnorm = _tensor_pass_scores(V, q, metric, (bias * dec).astype(np.float32))
+            total = canon + bias * dec
+            Vd = V.astype(np.float64)
+            true_norm = np.linalg.norm(Vd, axis=1)
+            cn = K.row_norm(V).astype(np.float64)
+            cn[cn == 0] = 1
+            max_norm = float(np.float32(min(true_norm.max() * (1 + 1e-6), 3e38)))
+            max_ratio = float(np.float32(min((true_norm / cn).max() * (1 + 1e-6), 3e38)))
+        for i in range(n):
+            if not (np.isfinite(total[i]) and np.isfinite(key[i])):
+                continue
+            b = emul.emul_outsider_bound(float(key[i]), METRIC[metric], DT[np.dtype(rdt)], DT[V.dtype], d, max_norm, max_ratio,
+                                         0.0, 0.0, 0.0, int(decay), bias, 1, qnorm, 1.0)
+            assert total[i] <= b, (trial, i, metric, vdt.__name__, qdt.__name__, d, kind, total[i], key[i], b)
+            if b > key[i] and np.isfinite(b):
+                worst_use = max(worst_use, (total[i] - key[i]) / (b - key[i]))
+            rows_checked += 1
+    assert rows_checked > 2500
+    assert worst_use < 0.95, worst_use
