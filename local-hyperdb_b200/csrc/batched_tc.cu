@@ -717,7 +717,12 @@ int batched_tc_supported(const MatrixView& m, int metric, int q_dtype, int64_t n
   // 1/std_q is a positive factor per query, left to the certify step -- which a per-row decay term would not commute with
   if (metric == HDB_PEARSON && (has_decay || !m.pscale)) return 0;
   if (m.dtype == 2) return 0;                                  // no fp64 tensor path
-  if (q_dtype > m.dtype) return 0;                             // the B operand has the storage precision: exact only then
+  // The B operand has the storage precision: exact only for a query no wider than the store.  HDB_TC_MIXED=1 lets wider queries
+  // (fp32 / fp64 queries over an fp16 store, fp64 over fp32) through as well: the operand is then the ROUNDED canonical query and the
+  // certificate carries the rounding (certificate.cuh, `qcut`; proven against the oracle on the CPU, tests/test_emul_canonical.py).
+  // Off by default: that configuration has not run on hardware yet.
+  static const bool mixed = [] { const char* e = getenv("HDB_TC_MIXED"); return e && e[0] == '1'; }();
+  if (q_dtype > m.dtype && !mixed) return 0;
   if ((m.d * dtype_size(m.dtype)) % 16 != 0 || (reinterpret_cast<uintptr_t>(m.rows) & 15)) return 0;
   if (m.n < 65536 || nq < 2) return 0;                         // one query, or a tiny shard (sample = n / 8 rows < 8192): the streaming sweep
   if (m.n >= (int64_t(1) << 31)) return 0;

@@ -22,6 +22,13 @@ __device__ inline double outsider_bound(double s, const FinalizeArgs& a, double 
   const bool decay = a.f.decay != nullptr;
   const double chain16 = (a.rdt == 0) ? D * 1.1920928955078125e-7 : 0.0;   // HALF_dot / f16 pairwise run in float32
   if (a.metric == HDB_HAMMING || a.metric == HDB_JACCARD) return s + fabs(s) * uk;     // exact on both sides: only the key rounding
+  // Batched pass with a query WIDER than the stored matrix (HDB_TC_MIXED=1): the B operand of the contraction is the canonical query
+  // rounded to the storage precision.  fp16 store: round to nearest (queries_to_half_kernel) -- 2^-11 relative (2^-24 more for a
+  // float64 query's float copy), or 2^-25 absolute below the normal range, and no overflow while |q_j| <= ||q|| < 65504 (checked per
+  // metric below).  fp32 store: only the float copy of a float64 query is new; the tf32 cut is in the 2 * 2^-9 band already.
+  const bool qcut = a.cand_count && a.rdt > a.m.dtype;
+  const double qrel = !qcut ? 0.0 : (a.m.dtype == 0 ? 4.8835e-4 : 1.1920928955078125e-7);
+  const double qabs = (qcut && a.m.dtype == 0) ? 2.98023223876953125e-8 : 0.0;          // per unit of sum_j |v_j| * (row factor)
   if (a.metric == HDB_PEARSON) {
     // Both sides evaluate rho~ = sum_j (v_j - mean_v) b_j / (std_v std_q d) from the SAME rounded statistics (b = q - mean_q).
     // Magnitudes: sum_j |v_j b_j| / (std_v std_q d) <= A := max_i ||v_i|| / (std_i sqrt d) * ||b|| / (std_q sqrt d)   (qnorm slot),
@@ -38,6 +45,11 @@ __device__ inline double outsider_bound(double s, const FinalizeArgs& a, double 
       // kind::tf32 keeps 10 mantissa bits of each fp32 operand (2 * 2^-9 of sum_j |v_j b_j|, as for dot / cosine).
       b += (double)a.m.max_pratio * fabs(qsumb) / ((double)a.m.d * qstd) * 1.000001;
       if (a.m.dtype == 1) b += A * 3.90625e-3;
+      if (qcut) {
+        // ||b|| = qnorm * std_q * sqrt(d) bounds every |b_j|;  sum_j |v_j| / (std_v d std_q) <= max_pratio / std_q
+        if (a.m.dtype == 0 && !(qnorm * qstd * sqrt(D) < 6.0e4)) return INFINITY;
+        b += A * qrel + qabs * (double)a.m.max_pratio / qstd;
+      }
     }
     // reference: rounding of the sum, the denominator (3 roundings) and the quotient, relative to the similarity itself
     b += 6.0 * uR * (decay ? Ac : fabs(b));
@@ -54,7 +66,12 @@ __device__ inline double outsider_bound(double s, const FinalizeArgs& a, double 
     double e = D * ua + chain16;
     if (a.cand_count && a.m.dtype == 1) e += 3.90625e-3;       // kind::tf32 keeps 10 mantissa bits of each fp32 operand (2 * 2^-9)
     if (a.metric == HDB_COSINE) e += 3.0 * uT + (a.m.dtype == 0 ? sqrt(D) * 5.9604644775390625e-8 : 0.0);
-    const double b = s + fabs(s) * uk + A * e;
+    double b = s + fabs(s) * uk + A * e;
+    if (qcut) {
+      // sum_j |v_j| * (row factor) <= sqrt(d) * max_norm (dot) or sqrt(d) * max ||v|| / norm (cosine: the unit query cannot overflow)
+      if (a.m.dtype == 0 && a.metric == HDB_DOT && !(qnorm < 6.0e4)) return INFINITY;
+      b += A * qrel + qabs * sqrt(D) * (double)(a.metric == HDB_DOT ? a.m.max_norm : a.m.max_ratio);
+    }
     return decay ? b + 2.0 * uR * A + fabs(b) * 1e-15 : b + 2.0 * uR * fabs(b);
   }
   // euclidean / manhattan: similarity in (0, 1]
@@ -82,6 +99,11 @@ __device__ inline double outsider_bound(double s, const FinalizeArgs& a, double 
       // batched pass: d^2 = |v|^2 + |q|^2 - 2 v.q on the tensor cores -> ABSOLUTE error from the cancellation
       const double A = (double)a.m.max_norm * qnorm;
       d2 -= 2.0 * A * (D * ua + (a.m.dtype == 1 ? 3.90625e-3 : 0.0)) + 8.0 * 1.1920928955078125e-7 * ((double)a.m.max_norm * a.m.max_norm + qnorm * qnorm);
+      if (qcut) {
+        // |q|^2 comes from the exact query, 2 v.q from the rounded one: 2 |v.(q^ - q)|
+        if (a.m.dtype == 0 && !(qnorm < 6.0e4)) return INFINITY;
+        d2 -= 2.0 * (A * qrel + qabs * sqrt(D) * (double)a.m.max_norm);
+      }
     }
     if (a.rdt == 0) d2 -= D * 5.9604644775390625e-8;                          // float16 squares flushed below 2^-24
     dc = sqrt(d2 > 0.0 ? d2 : 0.0) * (1.0 - 3.0 * uR);

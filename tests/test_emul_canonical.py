@@ -250,17 +250,23 @@ def _tensor_pass_scores(V, q, metric, addend32):
 
 @pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity", "euclidean_metric"])
 @pytest.mark.parametrize("decay", [False, True], ids=["plain", "decay"])
-def test_certificate_bound_of_the_batched_tensor_pass(emul, metric, decay):
+@pytest.mark.parametrize("mixed", [False, True], ids=["same-precision", "wider-query"])
+def test_certificate_bound_of_the_batched_tensor_pass(emul, metric, decay, mixed):
+    """mixed: the opt-in HDB_TC_MIXED=1 configuration -- a query wider than the store, whose B operand is the canonical query
+    ROUNDED to the storage precision (float copy, then fp16 round-to-nearest or the tf32 cut)."""
     import zlib
     from oracle import canonical as K
     if metric == "euclidean_metric" and decay:
         pytest.skip("batched_tc_supported: euclidean with time decay stays on the sweeps")
-    rng = np.random.default_rng(zlib.crc32(("tc" + metric + str(decay)).encode()))
+    rng = np.random.default_rng(zlib.crc32(("tc" + metric + str(decay) + str(mixed)).encode()))
     worst_use, rows_checked = 0.0, 0
     for trial in range(80):
         n, d = 64, int(rng.choice([8, 16, 96, 384, 768, 1536]))
         vdt = DTS[trial % 2]
-        qdt = DTS[int(rng.integers(0, DT[np.dtype(vdt)] + 1))]          # batched_tc_supported: the query is never wider than the store
+        if mixed:
+            qdt = DTS[int(rng.integers(DT[np.dtype(vdt)] + 1, 3))]      # fp32 / fp64 over fp16, fp64 over fp32
+        else:
+            qdt = DTS[int(rng.integers(0, DT[np.dtype(vdt)] + 1))]      # batched_tc_supported: the query is never wider than the store
         kind = (trial // 2) % 3
         V = rng.standard_normal((n, d))
         q = rng.standard_normal(d)

@@ -2,6 +2,8 @@
 committed outputs of the real reference.  Bar (north_star): top-k indices identical with ties to the
 lower index; scores bit-equal where NumPy's arithmetic is deterministic (all float16 metrics,
 euclidean/manhattan/hamming in every dtype), else within rel 1e-5 (fp32) / 1e-12 (fp64)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -435,6 +437,45 @@ def test_batched_pearson_tensor_path(hb, nq, sdt):
         i1, s1, _, f1 = m.query(q_np[:6], 10, metric)
         sub = V[1000:41000].cpu().numpy()
         for b in range(6):
+            oi, os_ = K.rank(sub, q_np[b], 10, metric)
+            assert list(i1[b] - 1000) == list(oi) and np.array_equal(s1[b], os_)
+    finally:
+        m.close()
+
+
+@pytest.mark.skipif(os.environ.get("HDB_TC_MIXED") != "1",
+                    reason="opt-in configuration (HDB_TC_MIXED=1, read once by the library): queries wider than the store on the tensor path")
+@pytest.mark.parametrize("sdt,qdt", [("float16", "float32"), ("float16", "float64"), ("float32", "float64")])
+@pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity", "euclidean_metric", "pearson_correlation"])
+def test_batched_tensor_path_wider_queries(hb, metric, sdt, qdt):
+    """HDB_TC_MIXED=1: a float32 / float64 query tile over a float16 store (float64 over float32) -- what `HyperDB.query_batch`
+    passes by default -- takes the tensor path with the canonical query ROUNDED to the storage precision as the B operand; the
+    certificate carries that rounding (tests/test_emul_canonical.py proves the bound on the CPU).  Answers must equal the
+    streaming sweep's bit for bit (same float64 / float32 result arithmetic), and the oracle's on a row range.
+    NOT run on hardware yet (the round's GPU minutes were spent): the switch is off by default."""
+    import torch
+    n, d, nq = 530_000, 136, 40
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+    V = torch.randn(n, d, generator=g, device=dev)
+    V = V / V.norm(dim=1, keepdim=True)
+    V = V.half() if sdt == "float16" else V.float()
+    Q = torch.randn(nq, d, generator=g, device=dev, dtype=torch.float64)
+    Q = Q / Q.norm(dim=1, keepdim=True)
+    q_np = Q.cpu().numpy().astype(qdt)
+    m = hb.DeviceMatrix(V)
+    try:
+        m.set_path(4)
+        i0, s0, c0, _ = m.query(q_np, 10, metric)
+        m.set_path(0)
+        i1, s1, c1, f1 = m.query(q_np, 10, metric)
+        assert sum(1 for f in f1 if f & 4) >= 0.7 * nq, ("tensor-core path was not taken", f1.tolist())
+        assert np.array_equal(i0, i1) and np.array_equal(s0, s1) and np.array_equal(c0, c1)
+        m.set_range(1000, 41000)
+        i1, s1, _, _ = m.query(q_np[:4], 10, metric)
+        sub = V[1000:41000].cpu().numpy()
+        for b in range(4):
             oi, os_ = K.rank(sub, q_np[b], 10, metric)
             assert list(i1[b] - 1000) == list(oi) and np.array_equal(s1[b], os_)
     finally:
