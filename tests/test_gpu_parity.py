@@ -358,7 +358,7 @@ def test_batched_tensor_path(hb, metric, nq, sdt):
             nref = nq if metric != "euclidean_metric" else min(nq, 24)
             m.set_path(2 if metric != "euclidean_metric" else 1)
             i0, s0, c0, f0 = m.query(q_np[:nref], k, metric, bias)
-            m.set_path(0)                                       # automatic: tensor cores for >= 16 queries
+            m.set_path(0)                                       # automatic: tensor cores for >= 2 queries on shards of >= 65 536 rows
             i1, s1, c1, f1 = m.query(q_np, k, metric, bias)
             i1c, s1c, c1c = i1[:nref], s1[:nref], c1[:nref]
             # bit 4 = answered by the tensor-core pass; queries its certificate rejected are re-run by the sweep
