@@ -22,3 +22,6 @@ except Exception as e:
     print(sys.argv[1],"ERR",e)
 PY
 done
+# opt-in configuration (not part of the default run): queries wider than the store on the tensor path
+HDB_TC_MIXED=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "wider_queries" > $O/val_tc_mixed.txt 2>&1; tail -3 $O/val_tc_mixed.txt
+timeout 300 python scratch/pearson_tc_ab.py 10000000 768 1024 2>&1 | tail -1
