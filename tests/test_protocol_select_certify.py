@@ -1,4 +1,4 @@
-"""The select -> certify PROTOCOL of the batched tensor path (csrc/batched_tc.cu + csrc/finalize.cu), run end to end on the CPU.
+"""The select -> certify PROTOCOL of the batched tensor path (csrc/batched_tc.cu + csrc/finalize.cu) and, below, of the streaming sweep, run end to end on the CPU.
 
 The per-row property "reference value <= bound of the row's own key" is checked in test_emul_canonical.py /
 test_certificate_math.py.  This file checks what the product builds on it: for a whole matrix and a query,
@@ -171,3 +171,61 @@ def test_certified_answers_equal_the_oracle(emul, metric, vdt, qdt):
     # the contract is not vacuous: embedding-like data certifies (all but the degenerate query, which never may)
     assert certified["unit"] >= asked["unit"] - 2, (certified, asked)
     assert sum(certified.values()) < sum(asked.values())        # ... and the degenerate queries did go to the repair path
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The same contract for the STREAMING SWEEP (csrc/sweep_float.cuh + finalize.cu), the path of the headline workload: the union of
+# the per-CTA candidate lists always contains the k' best keys overall, so the protocol is: k' best rows by (float32 key, row) ->
+# oracle re-scoring -> shipped certificate on the k'-th key.  Keys: the sweep's arithmetic in its accumulate type (NumPy's
+# summation order differs from the kernel's FMA chains; both lie inside the D * u_acc band the certificate grants).
+# ---------------------------------------------------------------------------------------------------------------------
+SWEEP_METRIC = dict(METRIC, manhattan_distance=3)
+
+
+@pytest.mark.parametrize("metric", ["dot_product", "cosine_similarity", "euclidean_metric", "manhattan_distance"])
+@pytest.mark.parametrize("vdt,qdt", [(np.float16, np.float16), (np.float32, np.float32), (np.float64, np.float64),
+                                     (np.float16, np.float64), (np.float32, np.float16)],
+                         ids=["f16", "f32", "f64", "f16-store-f64-query", "f32-store-f16-query"])
+@pytest.mark.parametrize("decay", [False, True], ids=["plain", "decay"])
+def test_sweep_certified_answers_equal_the_oracle(emul, metric, vdt, qdt, decay):
+    from test_emul_canonical import _sweep_scores
+    rng = np.random.default_rng(zlib.crc32(("sweep" + metric + np.dtype(vdt).name + np.dtype(qdt).name + str(decay)).encode()))
+    n, d, k = 6000, 48, 10
+    certified = asked = 0
+    for kind in ("unit", "clustered", "shifted"):
+        V = _matrix(rng, kind, n, d, vdt)
+        ts = 1.7e9 + rng.uniform(0, 5, n) if decay else None
+        bias = 0.3 if decay else 0.0
+        acc = np.float64 if V.dtype == np.float64 else np.float32
+        Vd = V.astype(np.float64)
+        true_norm = np.linalg.norm(Vd, axis=1)
+        cn = K.row_norm(V).astype(np.float64)
+        cn[cn == 0] = 1
+        max_norm = float(np.float32(true_norm.max() * (1 + 1e-6)))
+        max_ratio = float(np.float32((true_norm / cn).max() * (1 + 1e-6)))
+        for kp in (32, 128):
+            for x in [rng.standard_normal(d) for _ in range(3)] + [V[7].astype(np.float64) + 0.01 * rng.standard_normal(d)]:
+                if kind != "shifted":
+                    x = x / np.linalg.norm(x)
+                q = np.ascontiguousarray(x.astype(qdt))
+                rdt = np.promote_types(V.dtype, q.dtype)
+                with np.errstate(all="ignore"):
+                    sim, qnorm = _sweep_scores(V, q, metric, acc)
+                    dec = np.exp(-np.max(ts) + ts) if decay else np.zeros(n)
+                    key = (sim + bias * dec).astype(np.float32).astype(np.float64)
+                rows = np.arange(n)
+                top = rows[np.lexsort((rows, -key))][:kp]
+                with np.errstate(all="ignore"):
+                    canon = K.total_scores(V[top], q, metric) + (bias * dec[top] if decay else 0.0)
+                rk = np.lexsort((top, -canon))[:k]
+                asked += 1
+                bound = emul.emul_outsider_bound(float(key[top[-1]]), SWEEP_METRIC[metric], DT[np.dtype(rdt)], DT[V.dtype], d, max_norm,
+                                                 max_ratio, 0.0, 0.0, 0.0, int(decay), bias, 0, qnorm, 1.0)
+                if not (canon[rk][k - 1] > bound):
+                    continue
+                certified += 1
+                with np.errstate(all="ignore"):
+                    want_rows, want_sc = K.rank(V, q, k, metric, ts, bias)
+                assert list(top[rk]) == list(want_rows), (kind, kp, metric)
+                assert np.array_equal(canon[rk], want_sc), (kind, kp, metric)
+    assert certified >= asked // 3, (certified, asked)
