@@ -259,8 +259,9 @@ class ShardedMatrix:
 
     def enable_peer_exchange(self, max_batch=64, max_k=128):
         """Exchange candidates through NVLink peer memory instead of an NCCL all-gather (CUDA engines, world > 1).
-        Collective: the IPC handles travel once through torch.distributed; batches that do not fit the exchange buffer
-        (more than max_batch queries or top_k > max_k) keep using the all-gather."""
+        Collective: the IPC handles travel once through torch.distributed.  The buffer holds one step of max_batch queries
+        x max_k results (packed_len words); hdb_query refuses a larger step, so `query` cuts a larger batch into pieces that fit
+        (`exchange_batch_limit`) and callers of `submit` / `query_async` must do the same."""
         if self.world == 1 or self.xchg is not None:
             return self.xchg is not None
         import torch
@@ -466,9 +467,37 @@ class ShardedMatrix:
             idx[bad], sc[bad], cnt[bad] = r_idx, r_sc, r_cnt
         return idx, sc, cnt
 
+    def exchange_batch_limit(self, top_k):
+        """Largest batch one step can carry through the attached peer exchange for this top_k (None: no exchange, no limit;
+        0: not even one query fits).  hdb_query refuses a batch whose message exceeds the buffer (csrc/api.cu)."""
+        if self.xchg is None:
+            return None
+        k = max(int(top_k), 0)
+        words = int(self.xchg.max_words)
+        b = max(0, (2 * words) // (4 * k + 3))                   # packed_len(b, k) = 2bk + b + ceil(b/2) <= words
+        while b > 0 and packed_len(b, k) > words:
+            b -= 1
+        return b
+
     def query(self, queries, top_k, metric, recency_bias=0.0):
-        """Host results, identical on every rank: (idx [B,k], scores [B,k], counts [B])."""
+        """Host results, identical on every rank: (idx [B,k], scores [B,k], counts [B]).  A batch larger than the peer
+        exchange's buffer is cut into the largest pieces that fit (every rank cuts alike), three of them in flight."""
         if hasattr(self.engine, "m") and (self.world == 1 or self.xchg is not None):
+            shape = tuple(getattr(queries, "shape", ())) or (len(queries),)
+            b = 1 if len(shape) == 1 else int(shape[0])
+            fit = self.exchange_batch_limit(top_k)
+            if fit is not None and b > fit:
+                if fit < 1:
+                    raise ValueError(f"top_k = {top_k} does not fit the peer exchange buffer (enable_peer_exchange(max_batch, max_k))")
+                import numpy as np
+                tickets, parts = [], []
+                for i in range(0, b, fit):
+                    tickets.append(self.submit(queries[i:i + fit], top_k, metric, recency_bias))
+                    if len(tickets) == 3:
+                        parts.append(self.collect(tickets.pop(0)))
+                while tickets:
+                    parts.append(self.collect(tickets.pop(0)))
+                return tuple(np.concatenate([p[j] for p in parts]) for j in range(3))
             return self.collect(self.submit(queries, top_k, metric, recency_bias))
         idx, sc, cnt, flags = self.query_async(queries, top_k, metric, recency_bias)
         self.wait_results()

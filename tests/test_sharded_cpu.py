@@ -120,3 +120,53 @@ def test_world2_gloo(tmp_path, fail_first):
     port = 29600 + (os.getpid() % 200) + (50 if fail_first else 0)
     mp.spawn(_worker, args=(2, port, fail_first, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_query_cuts_batches_that_exceed_the_peer_exchange_buffer():
+    """ShardedMatrix.query with a peer exchange attached: hdb_query refuses a step whose message exceeds the exchange buffer
+    (csrc/api.cu), so a larger batch is cut into the largest pieces that fit, at most three in flight, and the answers are
+    concatenated in order.  Host logic only: submit / collect are stand-ins that record what they were asked."""
+    from hyperdb_b200.sharded import ShardedMatrix, packed_len
+
+    class Xchg:
+        max_words = packed_len(64, 128)
+
+    class Engine:
+        m = object()
+
+    sm = ShardedMatrix.__new__(ShardedMatrix)
+    sm.engine, sm.xchg, sm.world, sm.rank = Engine(), Xchg(), 2, 0
+    log, in_flight = [], []
+
+    def submit(q, k, metric, bias=0.0, _path=0):
+        q = np.atleast_2d(np.asarray(q))
+        in_flight.append(len(q))
+        assert len(in_flight) <= 3
+        log.append(len(q))
+        return (q, k)
+
+    def collect(t):
+        in_flight.pop(0)
+        q, k = t
+        b = len(q)
+        return (np.repeat(q[:, :1].astype(np.int64), k, axis=1), np.repeat(q[:, 1:2].astype(np.float64), k, axis=1), np.full(b, k, np.int64))
+
+    sm.submit, sm.collect = submit, collect
+    for k in (10, 128, 1000):
+        fit = sm.exchange_batch_limit(k)
+        assert packed_len(fit, k) <= Xchg.max_words < packed_len(fit + 1, k)
+        b = 2 * fit + 5
+        Q = np.stack([np.arange(b), np.arange(b) * 0.5, np.zeros(b)], axis=1)
+        log.clear()
+        idx, sc, cnt = sm.query(Q, k, "cosine_similarity")
+        assert log == [fit, fit, 5] and not in_flight
+        assert idx.shape == (b, k) and np.array_equal(idx[:, 0], np.arange(b)) and np.array_equal(sc[:, 0], np.arange(b) * 0.5)
+        assert cnt.tolist() == [k] * b
+        log.clear()
+        sm.query(Q[:fit], k, "cosine_similarity")                          # fits: one step, as before
+        sm.query(Q[0], k, "cosine_similarity")                             # a single 1-D query
+        assert log == [fit, 1]
+    with pytest.raises(ValueError, match="does not fit"):
+        sm.query(Q, 10 ** 6, "cosine_similarity")
+    sm.xchg = None
+    assert sm.exchange_batch_limit(10) is None
