@@ -690,6 +690,44 @@ class Bench:
 
 
 # ------------------------------------------------------------------------------------------------
+def hyperdb_query_extra(dev, steps=200, warmup=5):
+    """End to end through the REFERENCE-FACING call, `HyperDB.query(query_vector, top_k=10)` (hyperdb/hyperdb.py:1584 -> the
+    brute-force branch :1429-1582) of the drop-in shim, on config C2 (1M x 384 fp32, one document dict per row): a host query
+    vector in, a list of (document, score, index) out, every step; query cache off (every query is new anyway).  Second figure:
+    the same with a metadata predicate (`filters=[("metadata", {"category": 3})]`, 1 of 8 categories: the mask is compiled from the
+    documents once and cached, hyperdb/hyperdb.py:1218-1257).  One GPU only; the shim's INFO lines go to a buffer, not to stdout."""
+    import contextlib
+    import io
+    from hyperdb_b200.hyperdb import HyperDB
+    w = WORKLOADS["c2_cosine_b1"]
+    n, d = w["n"], w["d"]
+    out = {"workload": "hyperdb_query_c2", "unit": "queries/s", "steps": steps, "warmup": warmup,
+           "api": "hyperdb_b200.hyperdb.HyperDB.query(query_vector, top_k=10, metric='cosine_similarity'): host vector in, "
+                  "[(document, score, index)] out; 1M documents, query cache off"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        rows = gen_rows_torch(0, n, d, w["dtype"], dev, seed=0).cpu().numpy()
+        cat = gen_category_torch(0, n, dev).cpu().numpy()
+        docs = [{"id": i, "category": int(c)} for i, c in enumerate(cat)]
+        db = HyperDB(documents=docs, vectors=rows, metadata_keys=["category"], fp_precision=w["dtype"], cache_size=0,
+                     device=dev.index, sharded=False)
+        try:
+            qs = gen_queries(2 * (steps + warmup), d, w["dtype"], seed=99)
+            hit = db.query(rows[n // 8], top_k=1)                  # a stored row as the query must come back first
+            out["planted_first"] = bool(hit and hit[0][0]["id"] == n // 8)
+            for name, kw, off in (("value", {}, 0), ("filtered_value", {"filters": [("metadata", {"category": 3})]}, steps + warmup)):
+                for i in range(warmup):
+                    db.query(qs[off + i], top_k=10, **kw)
+                t0 = time.perf_counter()
+                for i in range(steps):
+                    res = db.query(qs[off + warmup + i], top_k=10, **kw)
+                out[name] = steps / (time.perf_counter() - t0)
+                assert len(res) == 10 and (not kw or all(doc["category"] == 3 for doc, _s, _i in res))
+            out["filter"] = "metadata category == 3 (%d of %d documents kept)" % (int((cat == 3).sum()), n)
+        finally:
+            db.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -763,6 +801,12 @@ def main():
         if r is not None:
             r.pop("clocks", None)
             extra_lines.append(r)
+    if extras and world == 1:
+        # the reference-facing API itself (one GPU): HyperDB.query on config C2, plain and with a metadata predicate
+        try:
+            extra_lines.append(hyperdb_query_extra(dev))
+        except Exception as ex:                                   # noqa: BLE001
+            extra_lines.append({"workload": "hyperdb_query_c2", "error": str(ex)[:300]})
 
     if rank == 0:
         line = {

@@ -183,3 +183,22 @@ def test_native_digest_equals_numpy_statement():
             N.check(N.lib().hdb_query_digest_host(C.c_void_p(Q.ctypes.data), code, 3, d, out))
             for b in range(3):
                 assert (int(out[2 * b]), int(out[2 * b + 1])) == query_digest_host(Q[b]), (dt, d, b)
+
+
+def test_bench_hyperdb_query_extra_on_the_stand_in(monkeypatch, capsys):
+    """bench.py's `hyperdb_query_c2` extra (HyperDB.query end to end, plain and with a metadata predicate) run on the CPU with the
+    oracle-backed stand-in for the device matrix and a small row count: the record it returns, and nothing on stdout (the
+    driver parses ONE JSON line; the shim's INFO prints must stay in the buffer)."""
+    import torch
+    import bench
+    import hyperdb_b200.hyperdb as H
+    from shim_fakes import FakeDeviceMatrix
+    monkeypatch.setattr(H, "DeviceMatrix", FakeDeviceMatrix)
+    monkeypatch.setitem(bench.WORKLOADS, "c2_cosine_b1", dict(bench.WORKLOADS["c2_cosine_b1"], n=4000))
+    r = bench.hyperdb_query_extra(torch.device("cpu"), steps=4, warmup=1)
+    assert capsys.readouterr().out == ""
+    assert r["workload"] == "hyperdb_query_c2" and r["planted_first"] is True
+    assert r["value"] > 0 and r["filtered_value"] > 0 and r["unit"] == "queries/s"
+    assert "of 4000 documents kept" in r["filter"]
+    import json
+    json.dumps(r)
