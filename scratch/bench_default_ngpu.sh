@@ -6,7 +6,7 @@ import json, sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print("HEAD value=%.1f e2e=%.1f sync=%.1f ms=%.4f frac=%.3f launches=%d unc=%s parity=%s"%(d['value'],d['e2e']['value'],d['e2e']['sync_value'],d['ms_per_step'],d['roofline']['frac'] or 0,d['gpu_launches'],d['config']['uncertified_steps'],d.get('parity_check',{}).get('ok')))
 for e in d.get('extra',[]):
-    if 'error' in e: print("   extra", e); continue
+    if 'error' in e or 'roofline' not in e: print("   extra", e); continue
     print("   extra %-30s value=%.1f e2e=%.1f sync=%.1f ms=%.4f frac=%.3f unc=%s"%(e['workload'],e['value'],e['e2e']['value'],e['e2e']['sync_value'],e['ms_per_step'],e['roofline']['frac'] or 0,e['uncertified_steps']))
 PY
 tail -n 4 $O/default${NGPU:-8}.err

@@ -8,7 +8,7 @@ import json
 d=json.loads(open("gpurun_out/val_bench_default.json").read().strip().splitlines()[-1])
 print("HEAD value=%.1f e2e=%.1f sync=%.1f ms=%.4f frac=%.3f launches=%d unc=%s parity=%s cpu=%s clocks=%s"%(d['value'],d['e2e']['value'],d['e2e']['sync_value'],d['ms_per_step'],d['roofline']['frac'] or 0,d['gpu_launches'],d['config']['uncertified_steps'],d.get('parity_check',{}).get('ok'),d.get('cpu_baseline',{}).get('value'),d['clocks']))
 for e in d.get('extra',[]):
-    if 'error' in e: print("   extra", e); continue
+    if 'error' in e or 'roofline' not in e: print("   extra", e); continue
     print("   extra %-30s value=%.1f e2e=%.1f sync=%.1f ms=%.4f frac=%.3f unc=%s %s"%(e['workload'],e['value'],e['e2e']['value'],e['e2e']['sync_value'],e['ms_per_step'],e['roofline']['frac'] or 0,e['uncertified_steps'],e['roofline']['kernel']))
 PY
 tail -n 3 $O/val_bench_default.err
